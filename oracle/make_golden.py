@@ -1,0 +1,217 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, numba, scipy):
+
+    NUMBA_CACHE_DIR=/tmp/numba_cache PYTHONDONTWRITEBYTECODE=1 \
+        python oracle/make_golden.py
+
+The GPU box has no /root/reference, so the vectors written here are committed
+and are what tests/ read.  TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("MF_REFERENCE", "/root/reference")
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+from microstructure_fingerprinting import mf_utils as mfu  # noqa: E402
+from microstructure_fingerprinting import mf as refmf  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "tests", "golden")
+FIX = os.path.join(REF, "tests", "integration", "fixtures")
+os.makedirs(OUT, exist_ok=True)
+
+
+def solver_cases():
+    """Seeded problems for every block count / branch of the solvers."""
+    rng = np.random.default_rng(20260101)
+    cases = {}
+    specs = [
+        ("s1_pos", 24, [37], "pos"), ("s1_signed", 24, [37], "signed"),
+        ("s2_pos", 30, [23, 19], "pos"), ("s2_signed", 30, [23, 19], "signed"),
+        ("s2_iso", 30, [41, 1], "pos"), ("s2_dup", 30, [12, 12], "dup"),
+        ("s3_pos_iso", 28, [17, 15, 1], "pos"), ("s3_signed", 28, [9, 11, 7], "signed"),
+        ("s3_pos_ear", 28, [13, 1, 6], "pos"), ("s3_dup", 28, [8, 8, 1], "dup"),
+        ("s4_pos", 26, [6, 5, 1, 4], "pos"), ("s4_signed", 26, [4, 3, 2, 3], "signed"),
+        ("s5_pos", 26, [3, 3, 3, 1, 2], "pos"),
+    ]
+    for name, M, sizes, kind in specs:
+        nt = int(np.sum(sizes))
+        nvox = 6
+        if kind == "signed":
+            A = rng.standard_normal((M, nt))
+        else:
+            A = rng.random((M, nt)) + 0.05
+        if kind == "dup":           # identical sub-dictionaries -> exact ties / Det == 0
+            A[:, sizes[0]:2 * sizes[0]] = A[:, :sizes[0]]
+        st = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+        Y = np.zeros((nvox, M))
+        for v in range(nvox):
+            gt = st + np.array([rng.integers(0, n) for n in sizes])
+            wgt = rng.random(len(sizes))
+            if v % 3 == 1:
+                wgt[rng.integers(0, len(sizes))] = 0.0      # inactive compartment
+            Y[v] = A[:, gt] @ wgt
+            if v % 2 == 0:
+                Y[v] += 0.05 * rng.standard_normal(M)       # noisy
+            if kind == "signed" and v == 5:
+                Y[v] = -np.abs(Y[v])                         # pushes towards w = 0
+        W = np.zeros((nvox, len(sizes)))
+        SUB = np.zeros((nvox, len(sizes)), dtype=np.int64)
+        OBJ = np.zeros(nvox)
+        YREC = np.zeros((nvox, M))
+        for v in range(nvox):
+            w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(
+                A, Y[v].copy(), np.asarray(sizes))
+            W[v], SUB[v], OBJ[v], YREC[v] = w, sub, obj, yrec
+        cases[name + "_A"] = A
+        cases[name + "_Y"] = Y
+        cases[name + "_sizes"] = np.asarray(sizes)
+        cases[name + "_w"] = W
+        cases[name + "_sub"] = SUB
+        cases[name + "_obj"] = OBJ
+        cases[name + "_yrec"] = YREC
+    np.savez_compressed(os.path.join(OUT, "solver_cases.npz"), **cases)
+    print("solver_cases:", len(specs), "cases")
+
+
+def ukbb_subset(n_atoms=48, n_ear=3):
+    d = mfu.loadmat(os.path.join(FIX, "ukbb_90_dirs_dictionary_hcp_deltas.mat"))
+    rng = np.random.default_rng(7)
+    cols = np.sort(rng.choice(d["dictionary"].shape[1], n_atoms, replace=False))
+    dic = {
+        "dictionary": np.ascontiguousarray(d["dictionary"][:, cols]),
+        "sch_mat": d["sch_mat"],
+        "orientation": d["orientation"],
+        "num_atom": n_atoms,
+        "num_ear": n_ear,
+        "T2_csf": d["T2_csf"], "DIFF_csf": d["CSF_DIFF"],
+        "T2_ear": d["T2_ear"], "DIFF_ear": d["Dear"][:n_ear].copy(),
+        "fasc_propnames": ["rad", "fin"],
+        "rad": d["rad"][cols].copy(), "fin": d["fin"][cols].copy(),
+    }
+    return dic
+
+
+def rotation_and_fit_cases():
+    dic = ukbb_subset()
+    bvals = np.loadtxt(os.path.join(FIX, "1000521_bvals.txt"))
+    bvecs = np.loadtxt(os.path.join(FIX, "1000521_bvecs.txt"))
+    sch_dense = dic["sch_mat"]
+    # exact-G scheme (what MFModel.fit builds from bvals/bvecs, mf:838)
+    sch_exact = mfu.get_PGSE_scheme_from_bval_bvec_dense(sch_dense, bvals, bvecs, 1e-3)
+    # between-shell scheme: true (unsnapped) G values, as in the reference's
+    # tests/integration/test_PGSE_from_multishell.py UKBB half
+    gam = mfu.get_gyromagnetic_ratio("H")
+    Del, dlt = sch_dense[0, 4], sch_dense[0, 5]
+    sch_between = sch_exact.copy()
+    sch_between[:, 3] = np.sqrt(bvals * 1e6 / (Del - dlt / 3)) / (gam * dlt)
+    Gmax = np.max(sch_dense[:, 3])
+    sch_between[:, 3] = np.minimum(sch_between[:, 3], Gmax)  # stay inside dense range
+
+    msi = mfu.init_PGSE_multishell_interp(dic["dictionary"], sch_dense, dic["orientation"])
+    rng = np.random.default_rng(11)
+    dirs = rng.standard_normal((6, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs[0] = [0.0, 0.0, 1.0]
+    dirs[1] = [1.0, 0.0, 0.0]
+    rot_exact = np.stack([mfu.interp_PGSE_from_multishell(sch_exact, d, msinterp=msi)
+                          for d in dirs])
+    rot_between = np.stack([mfu.interp_PGSE_from_multishell(sch_between, d, msinterp=msi)
+                            for d in dirs])
+    # flattened interpolator of the reference itself (nodes/rows per shell)
+    nodes = np.concatenate([f.x for f in msi["interpolators"]])
+    table = np.vstack([f._y for f in msi["interpolators"]])
+    off = np.cumsum([0] + [f.x.size for f in msi["interpolators"]])
+
+    # ---- MFModel.fit on a small phantom: mixed numfasc / csf / ear ----
+    model = refmf.MFModel(dic)
+    shape = (4, 3, 2)
+    V = int(np.prod(shape))
+    N = dic["num_atom"]
+    numfasc = rng.integers(0, 3, size=shape)
+    numfasc.flat[0] = 2
+    numfasc.flat[1] = 0
+    csf = (rng.random(shape) < 0.5).astype(float)
+    ear = np.zeros(shape)
+    ear.flat[[2, 5, 7]] = 1                # K-dependent: gives 3-, and 4-block voxels
+    mask = np.ones(shape)
+    mask.flat[3] = 0
+    peaks = rng.standard_normal(shape + (6,))
+    peaks[..., :3] /= np.linalg.norm(peaks[..., :3], axis=-1, keepdims=True)
+    peaks[..., 3:] /= np.linalg.norm(peaks[..., 3:], axis=-1, keepdims=True)
+    sig_csf = np.exp(-sch_exact[:, 6] / dic["T2_csf"]) * np.exp(
+        -(gam * sch_exact[:, 3] * sch_exact[:, 5]) ** 2
+        * (sch_exact[:, 4] - sch_exact[:, 5] / 3) * dic["DIFF_csf"])
+    data = np.zeros(shape + (sch_exact.shape[0],))
+    for idx in np.ndindex(shape):
+        K = numfasc[idx]
+        y = np.zeros(sch_exact.shape[0])
+        for k in range(K):
+            a = mfu.interp_PGSE_from_multishell(sch_exact, peaks[idx][3 * k:3 * k + 3],
+                                                msinterp=msi)
+            y += rng.uniform(0.2, 0.6) * a[:, rng.integers(0, N)]
+        y += csf[idx] * rng.uniform(0.05, 0.3) * sig_csf
+        if K == 0 and csf[idx] == 0:
+            y += 0.3 * sig_csf
+        y *= 700.0
+        y += 700.0 / 30.0 * rng.standard_normal(y.size)
+        data[idx] = y
+    fit_maps = {}
+    for tag, kw in [
+        ("A", dict(numfasc=numfasc, csf_mask=csf, ear_mask=None)),
+        ("B", dict(numfasc=numfasc, csf_mask=None, ear_mask=None)),
+        ("C", dict(numfasc=np.minimum(numfasc, 1), csf_mask=csf, ear_mask=ear)),
+        ("D", dict(numfasc=numfasc, csf_mask=csf, ear_mask=ear)),
+    ]:
+        ft = model.fit(data, mask, kw["numfasc"], peaks=peaks, bvals=bvals, bvecs=bvecs,
+                       csf_mask=kw["csf_mask"], ear_mask=kw["ear_mask"], verbose=0,
+                       parallel=False)
+        for p in ft.param_names:
+            fit_maps["fit%s_%s" % (tag, p)] = getattr(ft, p)
+        fit_maps["fit%s_param_names" % tag] = np.array(ft.param_names)
+        print("fit", tag, ft.param_names)
+    np.savez_compressed(
+        os.path.join(OUT, "ukbb_subset.npz"),
+        dictionary=dic["dictionary"], sch_mat=dic["sch_mat"],
+        orientation=np.asarray(dic["orientation"], dtype=np.float64),
+        T2_csf=dic["T2_csf"], DIFF_csf=dic["DIFF_csf"], T2_ear=dic["T2_ear"],
+        DIFF_ear=dic["DIFF_ear"], rad=dic["rad"], fin=dic["fin"],
+        bvals=bvals, bvecs=bvecs, sch_exact=sch_exact, sch_between=sch_between,
+        dirs=dirs, rot_exact=rot_exact, rot_between=rot_between,
+        ref_nodes=nodes, ref_table=table, ref_off=off, ref_Gms_un=msi["Gms_un"],
+        data=data, mask=mask, numfasc=numfasc, csf=csf, ear=ear, peaks=peaks,
+        **fit_maps)
+    print("ukbb_subset written")
+
+
+def reference_test_vectors():
+    """Outputs of the reference on its own seeded test (test_synthetic_data,
+    tests/integration/test_exhaustive_fingerprinting.py:94-153, shrunk)."""
+    np.random.seed(141414)
+    Nfasc, Natoms, M, Nvox = 2, 60, 100, 5
+    A = np.random.randn(M * (Nfasc * Natoms + 1)).reshape((M, Nfasc * Natoms + 1), order="F")
+    ID = np.zeros((3, Nvox), dtype=int)
+    ID[0] = np.random.randint(0, Natoms, Nvox)
+    ID[1] = np.random.randint(0, Natoms, Nvox) + Natoms
+    ID[2] = 2 * Natoms
+    w_gt = np.random.rand(3, Nvox)
+    Y = np.stack([A[:, ID[:, i]] @ w_gt[:, i] for i in range(Nvox)])
+    Y += 0.1 * (2.0 * np.random.rand(Nvox, M) - 1.0)
+    sizes = np.array([Natoms, Natoms, 1])
+    res = [mfu.solve_exhaustive_posweights(A, Y[i].copy(), sizes) for i in range(Nvox)]
+    np.savez_compressed(os.path.join(OUT, "ref_synthetic.npz"), A=A, Y=Y, sizes=sizes,
+                        ID=ID, w=np.stack([r[0] for r in res]),
+                        tot=np.stack([r[2] for r in res]),
+                        obj=np.array([r[3] for r in res]))
+    print("ref_synthetic written")
+
+
+if __name__ == "__main__":
+    solver_cases()
+    reference_test_vectors()
+    rotation_and_fit_cases()
