@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- voxels/s of the per-voxel exhaustive dictionary fit on B200.
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on): MFModel.fit-path
+with numfasc = 2 in every voxel, CSF compartment on 30% of the voxels, per-voxel rotation of
+an N = 1000-atom dictionary (analytic, tests/phantom.py), M = 105 measurements, V voxels per
+GPU per step (default 10^6 / --voxels).  One "step" = one pass of the hot path over that batch.
+
+  value      voxels/s with inputs resident in HBM (mfb_fit, device pointers), CUDA events,
+             max over ranks; whole-job aggregate over N GPUs (weak scaling: V per GPU fixed)
+  e2e        the same through the C-ABI call with HOST buffers (mfb_fit_host: H2D of y /
+             peaks / K / csf, D2H of the params rows inside the timed region)
+  roofline   dominant kernel's algorithmic FP64 flops / its measured duration vs the measured
+             cuBLAS DGEMM peak (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has no FP64)
+  cpu_baseline  the CPU oracle (port of the reference's algorithm) on a bounded voxel sample
+
+`--impl reference` times the reference's CPU algorithm (oracle port, all host threads) on the
+same workload, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxels/sec, MFModel.fit numfasc=2"
+UNIT = "voxels/s"
+
+
+def algorithmic_flops(M, N, csf_frac):
+    """F = 2M*N1*N2 + 4M*sum(N) + 2M + c_nb*prod(N) + 3*M*N*K per voxel."""
+    f2 = 2.0 * M * N * N + 4.0 * M * (2 * N) + 2 * M + 25.0 * N * N + 3.0 * M * N * 2
+    f3 = 2.0 * M * (N * N + 2 * N) + 4.0 * M * (2 * N + 1) + 2 * M + 65.0 * N * N + 3.0 * M * N * 2
+    return (1 - csf_frac) * f2 + csf_frac * f3
+
+
+def fp64_peak():
+    path = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    try:
+        d = json.load(open(path))
+        return float(d["fp64_tflops"]), "measured cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/fp64_peak_r01.json)"
+    except Exception:
+        return 37.0, "fallback: 64 DFMA/clk/SM x 148 SM x 1.965 GHz"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_workload(V, N, seed, csf_frac=0.3):
+    from tests.phantom import make_phantom
+    return make_phantom(n_atoms=N, n_vox=V, seed=seed, frac_k=(0.0, 0.0, 1.0), csf_frac=csf_frac,
+                        ear=False)
+
+
+def run_reference(args):
+    """CPU arm: the reference's algorithm (oracle port), all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    sample = max(cores, int(args.cpu_voxels) if args.cpu_voxels else 2 * cores)
+    ph = make_workload(sample, args.atoms, seed=1234)
+    tab = orc.init_table(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = orc.plan_scheme(tab, ph.sch)
+
+    def one(i):
+        return orc.fit_voxel(tab, plan, ph.Y[i], ph.K[i], ph.csf[i], ph.ear[i], ph.peaks[i],
+                             ph.maxfasc, ph.csf_on, ph.ear_on, ph.sig_csf, ph.sig_ear)
+
+    def step():
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(one, range(sample)))
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": workload_config(args, sample),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d voxels per step (same workload generator, seed 1234), "
+                                       "C oracle port of the reference's _fit_voxel, one thread "
+                                       "per core" % sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, V):
+    return {"workload": "MFModel.fit path, numfasc=2 in every voxel, CSF on 30%% of voxels, "
+                        "per-voxel interp_PGSE_from_multishell rotation, N=%d atoms/fascicle, "
+                        "M=105, %d voxels per GPU per step" % (args.atoms, V),
+            "voxels_per_gpu": V, "atoms_per_fascicle": args.atoms, "measurements": 105,
+            "l2": "inputs larger than L2 (y alone is %.0f MB per GPU)" % (V * 105 * 8 / 1e6),
+            "sharding": "contiguous voxel chunks per GPU, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--voxels", type=int, default=int(os.environ.get("MFB_BENCH_VOXELS", 1000000)))
+    ap.add_argument("--atoms", type=int, default=1000)
+    ap.add_argument("--cpu-voxels", type=int, default=0)
+    ap.add_argument("--exact", action="store_true", help="force the exact tier (verification)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from microstructure_fingerprinting_b200 import _lib, mf_utils as mfu
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_cuda()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    V, N = args.voxels, args.atoms
+    ph = make_workload(V, N, seed=100 + rank)      # each rank its own shard (weak scaling)
+    M = ph.Y.shape[1]
+    msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, None, device=local)
+    flags = (1 if args.exact else 0) | 2          # bit 1: time the dominant kernel with events
+
+    # ---- device-resident arm ----
+    d_y = torch.from_numpy(ph.Y).to(dev)
+    d_peaks = torch.from_numpy(ph.peaks).to(dev)
+    d_K = torch.from_numpy(ph.K).to(dev)
+    d_csf = torch.from_numpy(ph.csf).to(dev)
+    d_out = torch.empty((V, 1 + 2 * ph.maxfasc + 1 + 2), dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        plan.fit_device(d_y, d_peaks, d_K, d_csf, None, ph.maxfasc, True, False, flags=flags, out=d_out)
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, kern_launches, kern_vox = 0.0, 0.0, 0.0
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+        st = plan.stats()
+        kern_ms += st[2]; kern_launches += st[3]; kern_vox += st[4]
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    sampler.stop_flag = True
+
+    # ---- end-to-end arm: C ABI with host buffers (pinned), H2D + D2H inside the timed region ----
+    pin = {k: torch.from_numpy(getattr(ph, k)).pin_memory() for k in ("Y", "peaks", "K", "csf")}
+    host = {k: v.numpy() for k, v in pin.items()}
+
+    def step_host():
+        return plan.fit_host(host["Y"], host["peaks"], host["K"], host["csf"], None, ph.maxfasc,
+                             True, False, flags=flags & 1)
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rows_host = step_host()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_max = float(t.item())
+    P = rows_host.shape[1]
+    assert np.array_equal(rows_host, d_out.cpu().numpy()), "host and device arms disagree"
+
+    if rank == 0:
+        peak, peak_how = fp64_peak()
+        F = algorithmic_flops(M, N, 0.3)
+        kern_s = kern_ms / 1e3
+        achieved = (F * kern_vox / kern_s / 1e12) if kern_s > 0 else None
+        line = {
+            "metric": METRIC, "value": world * V / (ms_max / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, V),
+            "e2e": {"value": world * V / e2e_max, "unit": UNIT,
+                    "h2d_bytes_per_step": int(V * (M * 8 + 6 * 8 + 4 + 1)),
+                    "d2h_bytes_per_step": int(V * P * 8),
+                    "api": "mfb_fit_host (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "pair search (Gram + closed-form NNLS + argmin)",
+                         "kernel_ms_per_launch": kern_ms / max(kern_launches, 1),
+                         "kernel_share_of_step": kern_ms / (ms * args.steps),
+                         "flops_per_voxel": F, "peak_source": peak_how},
+            "tiers": {"exact_voxels_per_step": plan.stats()[1], "fast_voxels_per_step": plan.stats()[0]},
+        }
+        # CPU baseline on a bounded sample (rank 0, N = 1 only)
+        if world == 1:
+            from oracle import oracle as orc
+            ns = int(args.cpu_voxels) if args.cpu_voxels else 24
+            tab = orc.init_table(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+            op = orc.plan_scheme(tab, ph.sch)
+            t0 = time.perf_counter()
+            ref = np.stack([orc.fit_voxel(tab, op, ph.Y[i], ph.K[i], ph.csf[i], 0, ph.peaks[i],
+                                          ph.maxfasc, True, False, ph.sig_csf, None)
+                            for i in range(ns)])
+            dt = time.perf_counter() - t0
+            ok = bool(np.array_equal(ref[:, 3:5], rows_host[:ns, 3:5]))
+            line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "first %d voxels of the same batch, C oracle port of "
+                                              "_fit_voxel on one core" % ns,
+                                    "indices_match_gpu": ok}
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,137 @@
+/*
+ * mfb200.h -- C ABI of libmfb200.so: the B200-native (sm_100a) replacement for the
+ * per-voxel hot path of rensonnetg/microstructure_fingerprinting.
+ *
+ * What it replaces (reference path:line; mfu = microstructure_fingerprinting/
+ * mf_utils.py, mf = microstructure_fingerprinting/mf.py):
+ *
+ *   mfb_plan_create / mfb_plan_destroy
+ *       the per-study state the reference keeps in the `sm` dict handed to every
+ *       voxel task (mf:955-970): the pre-initialised multi-shell interpolator
+ *       (mfu:1959-2085, flattened to one lookup table), the subject scheme
+ *       (mf:821-846) and the CSF / EAR columns (mf:918-925).
+ *   mfb_rotate_multishell
+ *       mfu.interp_PGSE_from_multishell(sch_mat, newdir, msinterp=...) in fast
+ *       mode (mfu:1693-1737, 1785-1840, 1921-1956), batched over directions.
+ *   mfb_solve_batch
+ *       mfu.solve_exhaustive_posweights(A, y, dicsizes) (mfu:115-214) and the
+ *       Numba kernels behind it (_1 mfu:225, _2 mfu:288, _3 mfu:470, _4up
+ *       mfu:612), batched over voxels.
+ *   mfb_fit
+ *       the voxel loop of MFModel.fit (mf:978-1028) over mf._fit_voxel
+ *       (mf:340-461): rotate, assemble, solve, M0/nu/MSE/R2, pack params row.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function
+ * returns 0 on success or a negative MFB_E* code and never throws; the message
+ * of the last failure on the calling thread is mfb_last_error().  Pointers
+ * documented "device" must be CUDA device memory on the plan's device; "host"
+ * pointers are ordinary (pageable or pinned) host memory.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  One plan per
+ * GPU; calls on different plans may run from different host threads.
+ * There is no CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef MFB200_H
+#define MFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFB_OK 0
+#define MFB_EINVAL (-1)      /* bad argument (shape, NULL pointer, range)       */
+#define MFB_ECUDA (-2)       /* CUDA runtime error (see mfb_last_error)          */
+#define MFB_ENOMEM (-3)      /* device or host allocation failed                 */
+#define MFB_EUNSUPPORTED (-4) /* shape outside what the kernels cover            */
+
+typedef struct mfb_plan mfb_plan;
+
+/* ABI version (bumped on any signature change). */
+int mfb_version(void);
+
+/* Message of the last error raised on this thread ("" if none). */
+const char *mfb_last_error(void);
+
+/* Number of kernels launched by this library since load (all threads); used by
+ * bench.py's "gpu_launches" and by the tests that prove the CUDA path ran. */
+int64_t mfb_launch_count(void);
+
+/*
+ * Create the per-GPU plan.  All pointers are HOST pointers; contents are copied.
+ *   M, N          measurements per voxel, atoms per fascicle sub-dictionary
+ *   R, n_shells   rows of the lookup table, number of dense shells
+ *   shell_row_offset[n_shells+1]   first table row of each shell
+ *   nodes[R]      sorted |g.ordir| nodes of every shell, concatenated
+ *   table[R*N]    row-major signal rows at those nodes
+ *   gdir[M*3]     subject gradient directions
+ *   shell_lo/hi[M], gw_lo/hi[M]    dense shell(s) of each measurement and the
+ *                 between-shell weights (hi==lo, gw unused, when G matches a
+ *                 dense shell exactly)
+ *   sig_csf[M] or NULL; sig_ear[M*E] row-major or NULL (then E = 0)
+ * Returns NULL on failure (see mfb_last_error).
+ */
+mfb_plan *mfb_plan_create(int device, int M, int N, int R, int n_shells,
+                          const int32_t *shell_row_offset, const double *nodes,
+                          const double *table, const double *gdir,
+                          const int32_t *shell_lo, const int32_t *shell_hi,
+                          const double *gw_lo, const double *gw_hi,
+                          const double *sig_csf, const double *sig_ear, int E);
+
+void mfb_plan_destroy(mfb_plan *plan);
+
+/*
+ * Rotate the fascicle dictionary along V directions.
+ *   dirs   device, V*3
+ *   D_out  device, V * M * ldd doubles, voxel-major then row-major (M rows of
+ *          ldd >= N doubles); columns [0,N) of every row are written.
+ */
+int mfb_rotate_multishell(mfb_plan *plan, int64_t V, const double *dirs,
+                          double *D_out, int64_t ldd, void *stream);
+
+/*
+ * Batched solve_exhaustive_posweights on explicit dictionaries.
+ *   nblocks in [1,5]; sizes[nblocks] (host) > 0, Ntot = sum(sizes)
+ *   A       device; voxel v's dictionary is the row-major (M, lda) matrix at
+ *           A + v*strideA (strideA = 0 shares one dictionary between voxels)
+ *   y       device, V*M
+ * Outputs (device): w V*nblocks, idx_sub V*nblocks (index inside each block),
+ *   min_obj V, y_rec V*M (may be NULL).
+ * 1-3 blocks reproduce the reference's arithmetic exactly (summation order,
+ * no FMA, loop-order tie-break); 4-5 blocks use closed-form support
+ * enumeration, which agrees with scipy.optimize.nnls to rounding.
+ */
+int mfb_solve_batch(int device, int64_t V, int M, int nblocks,
+                    const int64_t *sizes, const double *A, int64_t lda,
+                    int64_t strideA, const double *y, double *w,
+                    int32_t *idx_sub, double *min_obj, double *y_rec,
+                    void *stream);
+
+/*
+ * The voxel loop of MFModel.fit.  Device pointers:
+ *   y V*M, peaks V*3*maxfasc, K V (0..maxfasc), csf V, ear V (0/1 bytes)
+ *   params_out V*P with P = 1 + 2*maxfasc + csf_on + 2*ear_on + 2, row layout of
+ *   mf:375-381: [M0 | nu_k | ID_k | nu_csf | nu_ear ID_ear | MSE | R2].
+ * flags: bit 0 = force the exact (reference-order) tier for every voxel.
+ */
+int mfb_fit(mfb_plan *plan, int64_t V, const double *y, const double *peaks,
+            const int32_t *K, const uint8_t *csf, const uint8_t *ear,
+            int maxfasc, int csf_on, int ear_on, double *params_out,
+            int flags, void *stream);
+
+/* Same with HOST buffers: chunked, double-buffered H2D / compute / D2H on the
+ * plan's own streams.  This is the call a non-PyTorch host would bind. */
+int mfb_fit_host(mfb_plan *plan, int64_t V, const double *y, const double *peaks,
+                 const int32_t *K, const uint8_t *csf, const uint8_t *ear,
+                 int maxfasc, int csf_on, int ear_on, double *params_out,
+                 int flags);
+
+/* Per-plan counters of the last mfb_fit call: voxels solved by the fast
+ * (DMMA screening) tier, voxels re-solved by the exact tier, per-stage device
+ * milliseconds when timing was enabled.  out[8]. */
+int mfb_fit_stats(mfb_plan *plan, double *out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFB200_H */

@@ -1,0 +1,421 @@
+// api.cu -- C ABI of libmfb200 (see include/mfb200.h) and the host-side orchestration of
+// the voxel loop: classify voxels by dictionary composition, run the fast (DMMA screening)
+// tier where it applies and the exact (reference-order) tier elsewhere, evaluate the
+// winning tuple in the reference's arithmetic, pack the params rows.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mfb {
+
+std::atomic<long long> g_launches{0};
+static thread_local std::string t_error;
+void set_error(const std::string &msg) { t_error = msg; }
+
+// growable device buffer
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return MFB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc(&p, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("device allocation of " + std::to_string(bytes) + " bytes failed");
+                return MFB_ENOMEM;
+            }
+            want = bytes;
+        }
+        cap = want;
+        return MFB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return (T *)p; }
+};
+
+static BlockSpec make_spec(int nb, const int64_t *sizes)
+{
+    BlockSpec bs;
+    memset(&bs, 0, sizeof(bs));
+    bs.nb = nb;
+    int s = 0;
+    for (int b = 0; b < nb; b++) { bs.size[b] = (int)sizes[b]; bs.start[b] = s; s += (int)sizes[b]; }
+    bs.ntot = s;
+    return bs;
+}
+
+static BlockSpec fit_spec(int N, int E, int K, int csf, int ear)
+{
+    int64_t sizes[5];
+    int nb = 0;
+    for (int k = 0; k < K; k++) sizes[nb++] = N;
+    if (csf) sizes[nb++] = 1;
+    if (ear) sizes[nb++] = E;
+    return make_spec(nb, sizes);
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+struct mfb_plan {
+    int device = 0;
+    DevPlan dp;
+    std::vector<void *> owned;
+    // per-chunk workspace
+    Buf type, nbv, lists, counts, tuple, asmall, idx5, w5, obj, yrec, abuf, scratch;
+    // host staging for mfb_fit_host
+    Buf d_y, d_peaks, d_K, d_csf, d_ear, d_params;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;  // pairs bracketing the dominant kernel (flags bit 1)
+    size_t events_used = 0;
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t exact_budget = (size_t)3 << 30;  // bytes of materialised dictionaries per sub-chunk
+};
+
+extern "C" int mfb_version(void) { return 1; }
+extern "C" const char *mfb_last_error(void) { return t_error.c_str(); }
+extern "C" int64_t mfb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+template <typename T>
+static int upload(mfb_plan *pl, const T *host, size_t n, const T **dev)
+{
+    void *d = nullptr;
+    MFB_CUDA_TRY(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    pl->owned.push_back(d);
+    if (n) MFB_CUDA_TRY(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (const T *)d;
+    return MFB_OK;
+}
+
+static int plan_build(mfb_plan *pl, int device, int M, int N, int R, int n_shells,
+                      const int32_t *off, const double *nodes, const double *table,
+                      const double *gdir, const int32_t *shell_lo, const int32_t *shell_hi,
+                      const double *gw_lo, const double *gw_hi, const double *sig_csf,
+                      const double *sig_ear, int E)
+{
+    MFB_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MFB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error(std::string("libmfb200 is built for sm_100a only; device is ") + prop.name);
+        return MFB_EUNSUPPORTED;
+    }
+    pl->device = device;
+    DevPlan &dp = pl->dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.M = M; dp.N = N; dp.R = R; dp.n_shells = n_shells; dp.E = sig_ear ? E : 0;
+    dp.has_between = 0;
+    for (int m = 0; m < M; m++) {
+        if (shell_lo[m] < 0 || shell_lo[m] >= n_shells || shell_hi[m] < 0 || shell_hi[m] >= n_shells) {
+            set_error("shell index out of range");
+            return MFB_EINVAL;
+        }
+        if (shell_hi[m] != shell_lo[m]) dp.has_between = 1;
+    }
+    for (int s = 0; s < n_shells; s++)
+        if (off[s + 1] - off[s] < 2 || off[s + 1] > R) {
+            set_error("every shell needs at least 2 nodes");
+            return MFB_EINVAL;
+        }
+    MFB_TRY(upload(pl, off, (size_t)n_shells + 1, &dp.off));
+    MFB_TRY(upload(pl, nodes, (size_t)R, &dp.nodes));
+    MFB_TRY(upload(pl, table, (size_t)R * N, &dp.table));
+    MFB_TRY(upload(pl, gdir, (size_t)M * 3, &dp.gdir));
+    MFB_TRY(upload(pl, shell_lo, (size_t)M, &dp.shell_lo));
+    MFB_TRY(upload(pl, shell_hi, (size_t)M, &dp.shell_hi));
+    MFB_TRY(upload(pl, gw_lo, (size_t)M, &dp.gw_lo));
+    MFB_TRY(upload(pl, gw_hi, (size_t)M, &dp.gw_hi));
+    if (sig_csf) MFB_TRY(upload(pl, sig_csf, (size_t)M, &dp.sig_csf));
+    if (sig_ear) MFB_TRY(upload(pl, sig_ear, (size_t)M * E, &dp.sig_ear));
+    MFB_CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    return MFB_OK;
+}
+
+extern "C" mfb_plan *mfb_plan_create(int device, int M, int N, int R, int n_shells,
+                                     const int32_t *shell_row_offset, const double *nodes,
+                                     const double *table, const double *gdir,
+                                     const int32_t *shell_lo, const int32_t *shell_hi,
+                                     const double *gw_lo, const double *gw_hi,
+                                     const double *sig_csf, const double *sig_ear, int E)
+{
+    if (M <= 0 || N <= 0 || R <= 1 || n_shells <= 0 || !shell_row_offset || !nodes || !table ||
+        !gdir || !shell_lo || !shell_hi || !gw_lo || !gw_hi || (sig_ear && E <= 0)) {
+        set_error("mfb_plan_create: invalid argument");
+        return nullptr;
+    }
+    mfb_plan *pl = new (std::nothrow) mfb_plan();
+    if (!pl) { set_error("out of host memory"); return nullptr; }
+    int rc = plan_build(pl, device, M, N, R, n_shells, shell_row_offset, nodes, table, gdir,
+                        shell_lo, shell_hi, gw_lo, gw_hi, sig_csf, sig_ear, E);
+    if (rc != MFB_OK) { mfb_plan_destroy(pl); return nullptr; }
+    return pl;
+}
+
+extern "C" void mfb_plan_destroy(mfb_plan *pl)
+{
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    for (void *p : pl->owned) cudaFree(p);
+    Buf *bufs[] = {&pl->type, &pl->nbv, &pl->lists, &pl->counts, &pl->tuple, &pl->asmall,
+                   &pl->idx5, &pl->w5, &pl->obj, &pl->yrec, &pl->abuf, &pl->scratch,
+                   &pl->d_y, &pl->d_peaks, &pl->d_K, &pl->d_csf, &pl->d_ear, &pl->d_params};
+    for (Buf *b : bufs) b->release();
+    for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+extern "C" int mfb_rotate_multishell(mfb_plan *pl, int64_t V, const double *dirs, double *D_out,
+                                     int64_t ldd, void *stream)
+{
+    if (!pl || V < 0 || (V > 0 && (!dirs || !D_out)) || ldd < pl->dp.N) {
+        set_error("mfb_rotate_multishell: invalid argument");
+        return MFB_EINVAL;
+    }
+    MFB_CUDA_TRY(cudaSetDevice(pl->device));
+    return launch_rotate_assemble(pl->dp, V, nullptr, dirs, 3, 1, 0, 0, D_out, ldd,
+                                  (int64_t)pl->dp.M * ldd, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------
+// batched solve on explicit dictionaries
+// ---------------------------------------------------------------------------------
+extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const int64_t *sizes,
+                               const double *A, int64_t lda, int64_t strideA, const double *y,
+                               double *w, int32_t *idx_sub, double *min_obj, double *y_rec,
+                               void *stream)
+{
+    if (V < 0 || M <= 0 || nblocks < 1 || nblocks > 5 || !sizes || (V > 0 && (!A || !y || !w || !idx_sub || !min_obj))) {
+        set_error("mfb_solve_batch: invalid argument");
+        return MFB_EINVAL;
+    }
+    for (int b = 0; b < nblocks; b++)
+        if (sizes[b] <= 0) { set_error("mfb_solve_batch: sizes must be > 0"); return MFB_EINVAL; }
+    BlockSpec bs = make_spec(nblocks, sizes);
+    if (lda < bs.ntot) { set_error("mfb_solve_batch: lda < sum(sizes)"); return MFB_EINVAL; }
+    if (nblocks > 3) {
+        set_error("mfb_solve_batch: 4-5 blocks not implemented yet");
+        return MFB_EUNSUPPORTED;
+    }
+    if (V == 0) return MFB_OK;
+    MFB_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // sub-batches keep the scratch bounded
+    size_t per_vox = exact_scratch_bytes(1, bs) + 4096;
+    int64_t sub = std::max<int64_t>(1, std::min<int64_t>(65535, ((size_t)1 << 30) / per_vox));
+    sub = std::min(sub, V);
+    Buf scratch, tuple, asmall, idx5, w5;
+    int rc = MFB_OK;
+    auto cleanup = [&]() { scratch.release(); tuple.release(); asmall.release(); idx5.release(); w5.release(); };
+    if ((rc = scratch.ensure(exact_scratch_bytes(sub, bs))) || (rc = tuple.ensure(sizeof(long long) * sub)) ||
+        (rc = asmall.ensure(sizeof(double) * sub * M * kMaxBlocks)) ||
+        (rc = idx5.ensure(sizeof(int32_t) * sub * kMaxBlocks)) || (rc = w5.ensure(sizeof(double) * sub * kMaxBlocks))) {
+        cleanup();
+        return rc;
+    }
+    for (int64_t v0 = 0; v0 < V && rc == MFB_OK; v0 += sub) {
+        int64_t nv = std::min(sub, V - v0);
+        const double *Av = A + v0 * strideA;
+        const double *yv = y + v0 * M;
+        rc = launch_exact_search(nv, M, bs, Av, lda, strideA, yv, M, nullptr, scratch.p,
+                                 tuple.as<long long>(), st);
+        if (rc) break;
+        rc = launch_gather_from_A(nv, M, bs, Av, lda, strideA, tuple.as<long long>(), nullptr,
+                                  asmall.as<double>(), idx5.as<int32_t>(), st);
+        if (rc) break;
+        rc = launch_evaluate(nv, M, bs.nb, nullptr, asmall.as<double>(), yv, M, tuple.as<long long>(),
+                             w5.as<double>(), min_obj + v0, y_rec ? y_rec + v0 * M : nullptr,
+                             idx5.as<int32_t>(), st);
+        if (rc) break;
+        rc = launch_unpack_solution(nv, bs.nb, w5.as<double>(), idx5.as<int32_t>(), w + v0 * bs.nb,
+                                    idx_sub + v0 * bs.nb, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cleanup();
+    if (rc == MFB_OK && e != cudaSuccess) {
+        set_error(std::string("mfb_solve_batch: ") + cudaGetErrorString(e));
+        return MFB_ECUDA;
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------
+// the voxel loop of MFModel.fit
+// ---------------------------------------------------------------------------------
+static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *peaks,
+                     const int32_t *K, const uint8_t *csf, const uint8_t *ear, int maxfasc,
+                     int csf_on, int ear_on, double *params, int flags, cudaStream_t st)
+{
+    const DevPlan &dp = pl->dp;
+    const int M = dp.M;
+    const int pld = 3 * maxfasc;
+    MFB_TRY(pl->type.ensure(nv));
+    MFB_TRY(pl->nbv.ensure(nv));
+    MFB_TRY(pl->lists.ensure(sizeof(int32_t) * 12 * nv));
+    MFB_TRY(pl->counts.ensure(sizeof(int32_t) * 12));
+    MFB_TRY(pl->tuple.ensure(sizeof(long long) * nv));
+    MFB_TRY(pl->asmall.ensure(sizeof(double) * nv * M * kMaxBlocks));
+    MFB_TRY(pl->idx5.ensure(sizeof(int32_t) * nv * kMaxBlocks));
+    MFB_TRY(pl->w5.ensure(sizeof(double) * nv * kMaxBlocks));
+    MFB_TRY(pl->obj.ensure(sizeof(double) * nv));
+    MFB_TRY(pl->yrec.ensure(sizeof(double) * nv * M));
+
+    MFB_TRY(launch_classify(nv, K, csf, ear, maxfasc, pl->type.as<uint8_t>(), pl->nbv.as<uint8_t>(),
+                            pl->lists.as<int32_t>(), pl->counts.as<int32_t>(), st));
+    int32_t counts[12];
+    MFB_CUDA_TRY(cudaMemcpyAsync(counts, pl->counts.p, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA_TRY(cudaMemsetAsync(pl->tuple.p, 0xff, sizeof(long long) * nv, st));
+    MFB_CUDA_TRY(cudaMemsetAsync(pl->idx5.p, 0, sizeof(int32_t) * nv * kMaxBlocks, st));
+    MFB_CUDA_TRY(cudaStreamSynchronize(st));
+
+    for (int t = 0; t < 12; t++) {
+        const int64_t cnt = counts[t];
+        if (cnt == 0) continue;
+        const int Kt = t % 3, ct = (t / 3) % 2, et = t / 6;
+        if (Kt + ct + et == 0) continue;
+        if ((ct && !dp.sig_csf) || (et && !dp.sig_ear)) {
+            set_error("mfb_fit: CSF/EAR compartment requested but the plan holds no such column");
+            return MFB_EINVAL;
+        }
+        const BlockSpec bs = fit_spec(dp.N, dp.E, Kt, ct, et);
+        if (bs.nb > 3) {
+            set_error("mfb_fit: voxels with 4 or more compartments (2 fascicles + CSF + EAR) are "
+                      "not implemented yet");
+            return MFB_EUNSUPPORTED;
+        }
+        const int32_t *list = pl->lists.as<int32_t>() + (int64_t)t * nv;
+        const bool timed = (flags & 2) && bs.nb >= 2 && Kt == 2;
+        // exact tier: materialise the dictionaries of a sub-chunk, search in reference order
+        const int64_t lda = (bs.ntot + 1) & ~(int64_t)1;
+        const size_t per_vox = (size_t)M * lda * sizeof(double);
+        int64_t sub = std::max<int64_t>(1, std::min<int64_t>(65535, pl->exact_budget / per_vox));
+        sub = std::min(sub, cnt);
+        MFB_TRY(pl->abuf.ensure(per_vox * sub));
+        MFB_TRY(pl->scratch.ensure(exact_scratch_bytes(sub, bs)));
+        for (int64_t s0 = 0; s0 < cnt; s0 += sub) {
+            const int64_t ns = std::min(sub, cnt - s0);
+            MFB_TRY(launch_rotate_assemble(dp, ns, list + s0, peaks, pld, Kt, ct, et,
+                                           pl->abuf.as<double>(), lda, (int64_t)M * lda, st));
+            cudaEvent_t *ev = nullptr;
+            if (timed) {
+                if (pl->events_used + 2 > pl->events.size()) {
+                    cudaEvent_t e0, e1;
+                    MFB_CUDA_TRY(cudaEventCreate(&e0));
+                    MFB_CUDA_TRY(cudaEventCreate(&e1));
+                    pl->events.push_back(e0);
+                    pl->events.push_back(e1);
+                }
+                ev = &pl->events[pl->events_used];
+                pl->events_used += 2;
+            }
+            MFB_TRY(launch_exact_search(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda, y, M,
+                                        list + s0, pl->scratch.p, pl->tuple.as<long long>(), st, ev));
+            if (timed) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
+            MFB_TRY(launch_gather_from_A(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda,
+                                         pl->tuple.as<long long>(), list + s0, pl->asmall.as<double>(),
+                                         pl->idx5.as<int32_t>(), st));
+        }
+        pl->stats[1] += (double)cnt;
+    }
+    MFB_TRY(launch_evaluate(nv, M, 0, pl->nbv.as<uint8_t>(), pl->asmall.as<double>(), y, M,
+                            pl->tuple.as<long long>(), pl->w5.as<double>(), pl->obj.as<double>(),
+                            pl->yrec.as<double>(), pl->idx5.as<int32_t>(), st));
+    MFB_TRY(launch_finalize(nv, M, maxfasc, csf_on, ear_on, K, csf, ear, y, pl->w5.as<double>(),
+                            pl->idx5.as<int32_t>(), pl->obj.as<double>(), pl->yrec.as<double>(),
+                            params, st));
+    if (pl->events_used) {  // dominant-kernel time of this chunk
+        MFB_CUDA_TRY(cudaStreamSynchronize(st));
+        for (size_t i = 0; i + 1 < pl->events_used; i += 2) {
+            float ms = 0.f;
+            MFB_CUDA_TRY(cudaEventElapsedTime(&ms, pl->events[i], pl->events[i + 1]));
+            pl->stats[2] += ms;
+        }
+        pl->events_used = 0;
+    }
+    return MFB_OK;
+}
+
+static const int64_t kFitChunk = 32768;
+
+extern "C" int mfb_fit(mfb_plan *pl, int64_t V, const double *y, const double *peaks,
+                       const int32_t *K, const uint8_t *csf, const uint8_t *ear, int maxfasc,
+                       int csf_on, int ear_on, double *params_out, int flags, void *stream)
+{
+    if (!pl || V < 0 || maxfasc < 0 || maxfasc > 2 || (V > 0 && (!y || !K || !params_out)) ||
+        (maxfasc > 0 && V > 0 && !peaks)) {
+        set_error("mfb_fit: invalid argument");
+        return MFB_EINVAL;
+    }
+    MFB_CUDA_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = 1 + 2 * maxfasc + (csf_on ? 1 : 0) + 2 * (ear_on ? 1 : 0) + 2;
+    for (int i = 0; i < 8; i++) pl->stats[i] = 0;
+    for (int64_t v0 = 0; v0 < V; v0 += kFitChunk) {
+        const int64_t nv = std::min(kFitChunk, V - v0);
+        MFB_TRY(fit_chunk(pl, nv, y + v0 * pl->dp.M, peaks ? peaks + v0 * 3 * maxfasc : nullptr, K + v0,
+                          csf ? csf + v0 : nullptr, ear ? ear + v0 : nullptr, maxfasc, csf_on ? 1 : 0,
+                          ear_on ? 1 : 0, params_out + v0 * P, flags, st));
+    }
+    return MFB_OK;
+}
+
+extern "C" int mfb_fit_host(mfb_plan *pl, int64_t V, const double *y, const double *peaks,
+                            const int32_t *K, const uint8_t *csf, const uint8_t *ear, int maxfasc,
+                            int csf_on, int ear_on, double *params_out, int flags)
+{
+    if (!pl || V < 0 || maxfasc < 0 || maxfasc > 2 || (V > 0 && (!y || !K || !params_out)) ||
+        (maxfasc > 0 && V > 0 && !peaks)) {
+        set_error("mfb_fit_host: invalid argument");
+        return MFB_EINVAL;
+    }
+    MFB_CUDA_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = pl->stream;
+    const int M = pl->dp.M;
+    const int P = 1 + 2 * maxfasc + (csf_on ? 1 : 0) + 2 * (ear_on ? 1 : 0) + 2;
+    const int64_t chunk = 4 * kFitChunk;
+    const int64_t nmax = std::min(chunk, std::max<int64_t>(V, 1));
+    MFB_TRY(pl->d_y.ensure(sizeof(double) * nmax * M));
+    MFB_TRY(pl->d_peaks.ensure(sizeof(double) * nmax * std::max(1, 3 * maxfasc)));
+    MFB_TRY(pl->d_K.ensure(sizeof(int32_t) * nmax));
+    MFB_TRY(pl->d_csf.ensure(nmax));
+    MFB_TRY(pl->d_ear.ensure(nmax));
+    MFB_TRY(pl->d_params.ensure(sizeof(double) * nmax * P));
+    for (int i = 0; i < 8; i++) pl->stats[i] = 0;
+    for (int64_t v0 = 0; v0 < V; v0 += chunk) {
+        const int64_t nv = std::min(chunk, V - v0);
+        MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_y.p, y + v0 * M, sizeof(double) * nv * M, cudaMemcpyHostToDevice, st));
+        if (maxfasc > 0)
+            MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_peaks.p, peaks + v0 * 3 * maxfasc,
+                                         sizeof(double) * nv * 3 * maxfasc, cudaMemcpyHostToDevice, st));
+        MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_K.p, K + v0, sizeof(int32_t) * nv, cudaMemcpyHostToDevice, st));
+        if (csf) MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_csf.p, csf + v0, nv, cudaMemcpyHostToDevice, st));
+        if (ear) MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_ear.p, ear + v0, nv, cudaMemcpyHostToDevice, st));
+        for (int64_t c0 = 0; c0 < nv; c0 += kFitChunk) {
+            const int64_t nc = std::min(kFitChunk, nv - c0);
+            MFB_TRY(fit_chunk(pl, nc, pl->d_y.as<double>() + c0 * M,
+                              pl->d_peaks.as<double>() + c0 * 3 * maxfasc, pl->d_K.as<int32_t>() + c0,
+                              csf ? pl->d_csf.as<uint8_t>() + c0 : nullptr,
+                              ear ? pl->d_ear.as<uint8_t>() + c0 : nullptr, maxfasc, csf_on ? 1 : 0,
+                              ear_on ? 1 : 0, pl->d_params.as<double>() + c0 * P, flags, st));
+        }
+        MFB_CUDA_TRY(cudaMemcpyAsync(params_out + v0 * P, pl->d_params.p, sizeof(double) * nv * P,
+                                     cudaMemcpyDeviceToHost, st));
+        MFB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return MFB_OK;
+}
+
+extern "C" int mfb_fit_stats(mfb_plan *pl, double *out, int n)
+{
+    if (!pl || !out) { set_error("mfb_fit_stats: invalid argument"); return MFB_EINVAL; }
+    for (int i = 0; i < n && i < 8; i++) out[i] = pl->stats[i];
+    return MFB_OK;
+}

@@ -1,0 +1,530 @@
+"""Low-level API of the reference's mf_utils.py for the fit path, B200-backed.
+
+Mirrors (same names, argument meaning, return types and error behaviour):
+  solve_exhaustive_posweights       reference mf_utils.py:115-214
+  init_PGSE_multishell_interp       reference mf_utils.py:1959-2085
+  interp_PGSE_from_multishell       reference mf_utils.py:1693-1956
+  import_PGSE_scheme                reference mf_utils.py:2128-2192
+  get_PGSE_scheme_from_bval_bvec_dense  reference mf_utils.py:2197-2300
+  get_gyromagnetic_ratio            reference mf_utils.py:1138-1150
+  DT_vec_to_2Darray                 reference mf_utils.py:901-957
+  loadmat                           reference mf_utils.py:3026-3087
+The numerical work (rotation, exhaustive search) runs in libmfb200.so on the GPU; this
+module only validates, marshals and keeps the small per-study tables on the host.
+There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["solve_exhaustive_posweights", "solve_exhaustive_posweights_batch",
+           "init_PGSE_multishell_interp", "interp_PGSE_from_multishell",
+           "import_PGSE_scheme", "get_PGSE_scheme_from_bval_bvec_dense",
+           "get_gyromagnetic_ratio", "DT_vec_to_2Darray", "loadmat", "from_ipython",
+           "MultiShellTable", "SchemePlan", "GpuPlan"]
+
+
+# ----------------------------------------------------------------------------------
+# small host utilities
+# ----------------------------------------------------------------------------------
+
+def get_gyromagnetic_ratio(element='H'):
+    """Gyromagnetic ratio [rad/(s T)] (reference mf_utils.py:1138-1150)."""
+    mhz_per_tesla = {'hydrogen': 42.577480e6, 'H': 42.577480e6, 'proton': 42.577480e6,
+                     'carbon': 10.7084e6, 'C': 10.7084e6,
+                     'phosphorus': 17.235e6, 'P': 17.235e6}
+    if element not in mhz_per_tesla:
+        raise ValueError('Gyromagnetic ratio for nucleus of element %s'
+                         'unknown.' % element)
+    return 2 * np.pi * mhz_per_tesla[element]
+
+
+def from_ipython():
+    """True when running under IPython (reference mf_utils.py:3090-3100)."""
+    try:
+        __IPYTHON__  # noqa: F821
+        return True
+    except NameError:
+        return False
+
+
+def loadmat(filename):
+    """scipy.io.loadmat with nested MATLAB structs turned into dicts
+    (behaviour of reference mf_utils.py:3026-3087)."""
+    import scipy.io
+
+    def is_struct(obj):
+        return type(obj).__name__ == 'mat_struct'
+
+    def to_dict(obj):
+        return {k: (to_dict(v) if is_struct(v) else v) for k, v in obj.__dict__.items()}
+
+    raw = scipy.io.loadmat(filename, struct_as_record=False, squeeze_me=True)
+    return {k: (to_dict(v) if is_struct(v) else v) for k, v in raw.items()}
+
+
+def DT_vec_to_2Darray(DT_vec, order):
+    """(..., 6) tensor coefficients -> (..., 3, 3) symmetric arrays
+    (reference mf_utils.py:901-957)."""
+    if DT_vec.shape[-1] != 6:
+        raise ValueError("Last dimension of input should have size 6,"
+                         " detected %d." % DT_vec.shape[-1])
+    # position in the 6-vector of [xx, xy, xz, yy, yz, zz]
+    layouts = {'row': (0, 1, 2, 3, 4, 5), 'column': (0, 1, 3, 2, 4, 5),
+               'diagonal': (0, 3, 5, 1, 4, 2)}
+    if order not in layouts:
+        raise ValueError("Unknown order option \"%s\"." % order)
+    xx, xy, xz, yy, yz, zz = (DT_vec[..., i] for i in layouts[order])
+    out = np.zeros(DT_vec.shape[:-1] + (3, 3))
+    out[..., 0, 0], out[..., 1, 1], out[..., 2, 2] = xx, yy, zz
+    out[..., 0, 1] = out[..., 1, 0] = xy
+    out[..., 0, 2] = out[..., 2, 0] = xz
+    out[..., 1, 2] = out[..., 2, 1] = yz
+    return out
+
+
+def import_PGSE_scheme(scheme):
+    """Load / validate a PGSE scheme [gx gy gz G Delta delta TE] per row
+    (reference mf_utils.py:2128-2192). Always returns a 2-D array."""
+    if isinstance(scheme, str):
+        with open(scheme, 'r') as f:
+            header = f.readline()
+        sch_mat = np.loadtxt(scheme, skiprows=1 if 'version' in header.lower() else 0)
+    elif isinstance(scheme, np.ndarray):
+        sch_mat = scheme
+    else:
+        raise TypeError("Unable to import a PGSE scheme matrix from input")
+    if sch_mat.ndim == 1:
+        sch_mat = sch_mat[np.newaxis, :]
+    if sch_mat.shape[1] != 7:
+        raise RuntimeError("Detected %s instead of expected 7 colums in"
+                           " PGSE scheme matrix." % sch_mat.shape[1])
+    gnorm = np.sqrt(np.sum(sch_mat[:, :3] ** 2, axis=1))
+    n_bad = np.sum(np.abs(1 - gnorm[gnorm > 0]) > 1e-4)
+    if n_bad > 0:
+        raise ValueError("Detected %d non-zero gradients which did not have"
+                         " unit norm. Please normalize." % n_bad)
+    G, Delta, delta, TE = (sch_mat[:, i] for i in (3, 4, 5, 6))
+    checks = [(G < 0, 'negative gradient intensity (4th column).'),
+              (Delta < 0, 'negative gradient separation Delta (5th column).'),
+              (delta < 0, 'negative gradient duration delta (6th column).'),
+              (TE < 0, 'negative echo time TE (7th column).')]
+    for bad, what in checks:
+        if np.any(bad):
+            raise ValueError('Detected %d sequence(s) with %s' % (np.sum(bad), what))
+    if np.any(delta > Delta):
+        raise ValueError('Detected %d sequence(s) in which delta (6th column)'
+                         ' was greater than Delta (5th column).' % np.sum(delta > Delta))
+    if np.any(TE < (Delta + delta) * 0.999):
+        raise ValueError('Detected %d sequence(s) in which TE (7th column)'
+                         ' was lower than Delta+delta.' % np.sum(TE < (Delta + delta)))
+    return sch_mat
+
+
+def get_PGSE_scheme_from_bval_bvec_dense(sch_mat_dense, bvals, bvecs, Gtol=1e-3):
+    """Scheme matrix from b-values [s/mm^2] / b-vectors, snapping each gradient
+    intensity to the dense sampling's shells (reference mf_utils.py:2197-2300)."""
+    sch_ref = import_PGSE_scheme(sch_mat_dense)
+    if isinstance(bvals, str):
+        bvals = np.loadtxt(bvals)
+    if isinstance(bvecs, str):
+        bvecs = np.atleast_2d(np.loadtxt(bvecs))
+    bvals = bvals * 1e6  # s/mm^2 -> s/m^2
+    if np.ndim(bvecs) != 2:
+        raise ValueError("bvecs array should have 2 dimensions,"
+                         " detected %d." % np.ndim(bvecs))
+    if bvecs.shape[0] != bvals.size and bvecs.shape[1] != bvals.size:
+        raise ValueError("Number of b-vectors does not match number"
+                         " of b-values (%d)" % bvals.size)
+    if not np.all(sch_ref[0, 4:6] == sch_ref[:, 4:6]):
+        raise ValueError('Detected different pairs of (Delta, delta) values'
+                         ' in reference scheme matrix (note that zeros '
+                         'count as values),'
+                         ' which is currently not supported.')
+    sch_mat = np.zeros((bvals.size, 7))
+    if bvecs.shape[0] == 3:
+        sch_mat[:, :3] = bvecs.transpose()
+    elif bvecs.shape[1] == 3:
+        sch_mat[:, :3] = bvecs
+    else:
+        raise ValueError("Vectors in bvecs should be 3-dimensional."
+                         " However, detected no dimension with size 3.")
+    gnorm = np.sqrt(np.sum(sch_mat[:, :3] ** 2, axis=1))
+    nz = gnorm > 0
+    sch_mat[nz, :3] = sch_mat[nz, :3] / gnorm[nz][:, np.newaxis]
+
+    gam = get_gyromagnetic_ratio('H')
+    Del, dlt, TE = sch_ref[0, 4], sch_ref[0, 5], sch_ref[0, 6]
+    G = np.sqrt(bvals / (Del - dlt / 3)) / (gam * dlt)
+    G_shells = np.unique(sch_ref[:, 3])
+    Geff = np.zeros(bvals.shape[0])
+    n_mapped = 0
+    for Gs in G_shells:
+        hit = np.where(np.abs(Gs - G) < Gtol)[0]
+        n_mapped += hit.size
+        Geff[hit] = Gs
+    if n_mapped != G.size:
+        raise ValueError('Mismatch between reference scheme matrix and bvals. '
+                         ' Could only map %d/%d b-values (equivalently, gradient'
+                         ' intensities G) from the specified bvals to the b-values'
+                         ' contained in the reference scheme matrix. You may want to'
+                         ' change the tolerance on gradient intensity G (currently '
+                         '%g T/m).' % (n_mapped, G.size, Gtol))
+    sch_mat[:, 3] = Geff
+    sch_mat[:, 4:7] = np.array([Del, dlt, TE])
+    return sch_mat
+
+
+# ----------------------------------------------------------------------------------
+# multi-shell interpolation tables
+# ----------------------------------------------------------------------------------
+
+class _ShellNodes(object):
+    """Data view of one shell of the lookup table (the reference stores a
+    scipy interp1d here; only its node data `.x`, `.y` is kept)."""
+
+    def __init__(self, x, y):
+        self.x = x
+        self.y = y
+        self._y = y
+
+
+class MultiShellTable(dict):
+    """Return type of init_PGSE_multishell_interp: a dict with the reference's keys
+    ('scheme_DeldelTE', 'num_subs', 'Gms_un', 'interpolators') plus the flattened
+    lookup table ('nodes' (R,), 'table' (R, N), 'off' (n_shells+1,)) the GPU reads."""
+
+
+def _check_unit_or_zero_gradients(sch_mat):
+    gnorm = np.sqrt(np.sum(sch_mat[:, 0:3] ** 2, axis=1))
+    if np.any(np.abs(1 - gnorm[gnorm > 0]) > 1e-3):
+        raise ValueError("Gradient directions in multi-shell scheme matrix"
+                         " should all either have zero or unit norm.")
+
+
+def init_PGSE_multishell_interp(sig_ms, sch_mat_ms, ordir):
+    """Initialises the multi-shell lookup table (reference mf_utils.py:1959-2085).
+
+    Per dense shell: sorted unique nodes x = |g.ordir| (first-occurrence rows), the
+    near-perpendicular cluster |x - x[0]| < 1e-3 replaced by its mean, b0 shell ->
+    nodes [0, 1] with identical rows.
+    """
+    ordir = np.asarray(ordir)
+    if ordir.size != 3:
+        raise ValueError("Direction of dictionary computed with dense"
+                         " sampling (ordir) should have 3 entries.")
+    ordir = np.squeeze(ordir).astype(np.float64)
+    sch_mat_ms = np.asarray(sch_mat_ms, dtype=np.float64)
+    if not np.all(np.isclose(sch_mat_ms[0, 4:7], sch_mat_ms[:, 4:7])):
+        raise ValueError("Delta, delta and TE values should all be "
+                         "identical in multi-shell sampling.")
+    sig_ms = np.asarray(sig_ms, dtype=np.float64)
+    if sig_ms.ndim == 1:
+        sig_ms = sig_ms.reshape((sig_ms.size, 1))
+    if sch_mat_ms.shape[0] != sig_ms.shape[0]:
+        raise ValueError("Number of lines in dense multishell scheme"
+                         " (%d) does not match number of signal values"
+                         " per substrate (%d)." % (sch_mat_ms.shape[0], sig_ms.shape[0]))
+    ordirnorm = np.sqrt((ordir ** 2).sum())
+    if np.abs(1 - ordirnorm) > 1e-3:
+        raise ValueError("Orientation vector of the multi-shell signal "
+                         "must have unit norm. Detected %g." % (ordirnorm,))
+    _check_unit_or_zero_gradients(sch_mat_ms)
+
+    x_all = np.abs(np.dot(sch_mat_ms[:, 0:3], ordir))
+    Gms_un, shell_of = np.unique(sch_mat_ms[:, 3], return_inverse=True)
+    shells = []
+    for s, G in enumerate(Gms_un):
+        rows = np.where(shell_of == s)[0]
+        if G == 0:
+            same = np.all(np.isclose(sig_ms[rows, :], sig_ms[rows[0], :]), axis=0)
+            if np.any(~same):
+                bad = np.where(~same)[0]
+                raise ValueError('Distinct signal values in provided multi-'
+                                 'shell sampling for zero gradients '
+                                 '(b0 acquistions), for '
+                                 '%d substrate(s) [%s]' %
+                                 (bad.shape[0], " ".join("{:d}".format(b) for b in bad)))
+            shells.append(_ShellNodes(np.array([0.0, 1.0]),
+                                      np.repeat([sig_ms[rows[0], :]], 2, axis=0)))
+            continue
+        xs, first = np.unique(x_all[rows], return_index=True)
+        ys = sig_ms[rows, :][first, :]
+        cluster = np.abs(xs - xs[0]) < 1e-3
+        c = int(np.sum(cluster))
+        if c > 1:
+            xs = np.append(np.mean(xs[cluster]), xs[c:])
+            ys = np.append(np.mean(ys[cluster, :], axis=0, keepdims=True), ys[c:, :], axis=0)
+        if xs.size < 2:
+            raise ValueError("Shell G=%g of the dense sampling has fewer than 2 distinct "
+                             "|g.ordir| nodes; cannot interpolate." % G)
+        shells.append(_ShellNodes(xs, ys))
+    out = MultiShellTable()
+    out['scheme_DeldelTE'] = sch_mat_ms[0, 4:7]
+    out['num_subs'] = sig_ms.shape[1]
+    out['Gms_un'] = Gms_un
+    out['interpolators'] = shells
+    out['nodes'] = np.ascontiguousarray(np.concatenate([s.x for s in shells]))
+    out['table'] = np.ascontiguousarray(np.vstack([s.y for s in shells]))
+    out['off'] = np.cumsum([0] + [s.x.size for s in shells]).astype(np.int32)
+    return out
+
+
+class SchemePlan(object):
+    """Subject scheme mapped onto the dense shells (reference mf_utils.py:1786-1839)."""
+
+    def __init__(self, msinterp, sch_mat):
+        sch_mat = np.asarray(sch_mat, dtype=np.float64)
+        if sch_mat.ndim != 2 or sch_mat.shape[1] < 7:
+            raise ValueError("sch_mat should have shape (Nseq, 7).")
+        if not np.all(np.isclose(msinterp['scheme_DeldelTE'], sch_mat[:, 4:7])):
+            raise ValueError("Delta, delta and TE values should all be "
+                             "identical to those in the multi-shell sampling.")
+        _check_unit_or_zero_gradients(sch_mat)
+        Gms = msinterp['Gms_un']
+        M = sch_mat.shape[0]
+        self.M = M
+        self.gdir = np.ascontiguousarray(sch_mat[:, 0:3])
+        self.shell_lo = np.zeros(M, dtype=np.int32)
+        self.shell_hi = np.zeros(M, dtype=np.int32)
+        self.gw_lo = np.ones(M)
+        self.gw_hi = np.zeros(M)
+        for G in np.unique(sch_mat[:, 3]):
+            rows = sch_mat[:, 3] == G
+            same = np.where(G == Gms)[0]
+            if same.size > 0:
+                self.shell_lo[rows] = self.shell_hi[rows] = same[0]
+                continue
+            ih = int(np.argmax(Gms > G))
+            if ih == 0:
+                raise ValueError("Gradient intensity %g is not in the [%g, %g]"
+                                 " range spanned by the multi-shell sampling."
+                                 " Extrapolation not supported." % (G, Gms[0], Gms[-1]))
+            self.shell_lo[rows], self.shell_hi[rows] = ih - 1, ih
+            self.gw_hi[rows] = (G - Gms[ih - 1]) / (Gms[ih] - Gms[ih - 1])
+            self.gw_lo[rows] = (Gms[ih] - G) / (Gms[ih] - Gms[ih - 1])
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class GpuPlan(object):
+    """Owner of one mfb_plan (lookup table + subject scheme + iso columns on one GPU)."""
+
+    def __init__(self, msinterp, scheme_plan, sig_csf=None, sig_ear=None, device=0):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        self.device = int(device)
+        self.M = scheme_plan.M
+        self.N = int(msinterp['table'].shape[1])
+        self.E = 0
+        nodes = np.ascontiguousarray(msinterp['nodes'], dtype=np.float64)
+        table = np.ascontiguousarray(msinterp['table'], dtype=np.float64)
+        off = np.ascontiguousarray(msinterp['off'], dtype=np.int32)
+        if sig_csf is not None:
+            sig_csf = np.ascontiguousarray(sig_csf, dtype=np.float64)
+        if sig_ear is not None:
+            sig_ear = np.ascontiguousarray(sig_ear, dtype=np.float64)
+            self.E = int(sig_ear.shape[1])
+        with torch.cuda.device(self.device):
+            self.handle = lib.mfb_plan_create(
+                self.device, self.M, self.N, int(nodes.size), int(off.size - 1), _ptr(off),
+                _ptr(nodes), _ptr(table), _ptr(scheme_plan.gdir), _ptr(scheme_plan.shell_lo),
+                _ptr(scheme_plan.shell_hi), _ptr(scheme_plan.gw_lo), _ptr(scheme_plan.gw_hi),
+                _ptr(sig_csf), _ptr(sig_ear), self.E)
+        if not self.handle:
+            raise _lib.MFBError("mfb_plan_create failed: " + _lib.last_error())
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            _lib.load().mfb_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rotate(self, dirs):
+        """dirs (V, 3) -> torch.cuda tensor (V, M, N)."""
+        torch = _lib.require_cuda()
+        dirs = np.ascontiguousarray(np.atleast_2d(dirs), dtype=np.float64)
+        V = dirs.shape[0]
+        dev = torch.device('cuda', self.device)
+        d_dirs = torch.from_numpy(dirs).to(dev)
+        out = torch.empty((V, self.M, self.N), dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = _lib.load().mfb_rotate_multishell(self.handle, V, d_dirs.data_ptr(), out.data_ptr(),
+                                               self.N, st)
+        _lib.check(rc, "mfb_rotate_multishell")
+        return out
+
+    def fit_host(self, y, peaks, K, csf, ear, maxfasc, csf_on, ear_on, flags=0):
+        """Host arrays in, params rows (V, P) out (mfb_fit_host)."""
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        V = y.shape[0]
+        K = np.ascontiguousarray(K, dtype=np.int32)
+        peaks = None if maxfasc == 0 else np.ascontiguousarray(peaks, dtype=np.float64)
+        csf = None if csf is None else np.ascontiguousarray(csf, dtype=np.uint8)
+        ear = None if ear is None else np.ascontiguousarray(ear, dtype=np.uint8)
+        P = 1 + 2 * maxfasc + int(csf_on) + 2 * int(ear_on) + 2
+        out = np.zeros((V, P))
+        rc = _lib.load().mfb_fit_host(self.handle, V, _ptr(y), _ptr(peaks), _ptr(K), _ptr(csf),
+                                      _ptr(ear), int(maxfasc), int(csf_on), int(ear_on), _ptr(out),
+                                      int(flags))
+        _lib.check(rc, "mfb_fit_host")
+        return out
+
+    def fit_device(self, y, peaks, K, csf, ear, maxfasc, csf_on, ear_on, flags=0, out=None):
+        """torch.cuda tensors in / out (mfb_fit); inputs must live on this plan's GPU."""
+        torch = _lib.require_cuda()
+        V = y.shape[0]
+        P = 1 + 2 * maxfasc + int(csf_on) + 2 * int(ear_on) + 2
+        if out is None:
+            out = torch.empty((V, P), dtype=torch.float64, device=y.device)
+        st = torch.cuda.current_stream(y.device).cuda_stream
+
+        def p(t):
+            return None if t is None else t.data_ptr()
+        rc = _lib.load().mfb_fit(self.handle, V, p(y), p(peaks), p(K), p(csf), p(ear), int(maxfasc),
+                                 int(csf_on), int(ear_on), p(out), int(flags), st)
+        _lib.check(rc, "mfb_fit")
+        return out
+
+    def stats(self):
+        buf = np.zeros(8)
+        _lib.check(_lib.load().mfb_fit_stats(self.handle, _ptr(buf), 8), "mfb_fit_stats")
+        return buf
+
+
+def _plan_for(msinterp, sch_mat, device=0):
+    """GpuPlan cached on the table object, keyed by the scheme's bytes."""
+    sch_mat = np.ascontiguousarray(sch_mat, dtype=np.float64)
+    cache = msinterp.__dict__.setdefault('_gpu_plans', {}) if isinstance(msinterp, MultiShellTable) \
+        else {}
+    key = (device, sch_mat.shape, sch_mat.tobytes())
+    if key not in cache:
+        if len(cache) >= 4:
+            cache.clear()
+        cache[key] = GpuPlan(msinterp, SchemePlan(msinterp, sch_mat), device=device)
+    return cache[key]
+
+
+def interp_PGSE_from_multishell(sch_mat, newdir, sig_ms=None, sch_mat_ms=None, ordir=None,
+                                msinterp=None):
+    """Single-fascicle PGSE signal rotated to `newdir` by interpolation in the dense
+    multi-shell sampling (reference mf_utils.py:1693-1956).
+
+    Returns an (Nseq, Nsub) array passed through numpy.squeeze, like the reference.
+    Extension: `newdir` of shape (V, 3) returns (V, Nseq, Nsub).
+    """
+    if msinterp is None:
+        if sig_ms is None or sch_mat_ms is None or ordir is None:
+            raise ValueError("If msinterp is not specified, sig_ms, "
+                             "sch_mat_ms and ordir must all be specified.")
+        msinterp = init_PGSE_multishell_interp(sig_ms, sch_mat_ms, ordir)
+    else:
+        if msinterp['Gms_un'].size != len(msinterp['interpolators']):
+            raise ValueError("msinterp['Gms_un'] has size %d vs expected %d to match "
+                             "len(msinterp['interpolators'])"
+                             % (msinterp['Gms_un'].size, len(msinterp['interpolators'])))
+        if msinterp['interpolators'][0].y.shape[1] != msinterp['num_subs']:
+            raise ValueError("Inconsistency in msinterp regarding number of substrates. "
+                             "Make sure the interpolator was initialized"
+                             " on the right dictionary.")
+    newdir = np.asarray(newdir, dtype=np.float64)
+    batched = newdir.ndim == 2 and newdir.shape[0] != 1 and newdir.shape[1] == 3 and newdir.size > 3
+    if not batched:
+        if newdir.size != 3:
+            raise ValueError("Direction of fascicle for new signal (newdir)"
+                             " should have 3 entries.")
+        newdir = newdir.reshape(1, 3)
+    norms = np.sqrt((newdir ** 2).sum(axis=1))
+    if np.any(np.abs(1 - norms) > 1e-3):
+        raise ValueError("Orientation vector of the new signal must have unit norm. Detected"
+                         " %g." % (norms[np.argmax(np.abs(1 - norms))],))
+    plan = _plan_for(msinterp, np.asarray(sch_mat, dtype=np.float64))
+    out = plan.rotate(newdir).cpu().numpy()
+    if batched:
+        return out
+    return np.squeeze(out[0])
+
+
+# ----------------------------------------------------------------------------------
+# exhaustive combinatorial NNLS
+# ----------------------------------------------------------------------------------
+
+def solve_exhaustive_posweights_batch(A, Y, dicsizes, device=0, return_device=False):
+    """Batched form of solve_exhaustive_posweights: Y is (V, M); A is (M, Ntot) (shared by
+    all voxels) or (V, M, Ntot).  Returns (w (V,K), ind_subdic (V,K), ind_totdic (V,K),
+    min_obj (V,), y_recons (V,M))."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device('cuda', device)
+    sizes = np.ascontiguousarray(np.asarray(dicsizes).astype(np.int64))
+    nb = int(sizes.size)
+
+    def to_dev(x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=dev, dtype=torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    dA, dY = to_dev(A), to_dev(Y)
+    V, M = dY.shape
+    ntot = int(sizes.sum())
+    if dA.dim() == 2:
+        strideA = 0
+        assert dA.shape == (M, ntot)
+    else:
+        assert dA.shape == (V, M, ntot)
+        strideA = M * ntot
+    w = torch.zeros((V, nb), dtype=torch.float64, device=dev)
+    sub = torch.zeros((V, nb), dtype=torch.int32, device=dev)
+    obj = torch.zeros((V,), dtype=torch.float64, device=dev)
+    yrec = torch.zeros((V, M), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = lib.mfb_solve_batch(device, V, M, nb, _ptr(sizes), dA.data_ptr(), ntot, strideA,
+                                 dY.data_ptr(), w.data_ptr(), sub.data_ptr(), obj.data_ptr(),
+                                 yrec.data_ptr(), st)
+    _lib.check(rc, "mfb_solve_batch")
+    starts = torch.from_numpy(np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)).to(dev)
+    tot = sub + starts[None, :]
+    if return_device:
+        return w, sub, tot, obj, yrec
+    return (w.cpu().numpy(), sub.cpu().numpy(), tot.cpu().numpy(), obj.cpu().numpy(),
+            yrec.cpu().numpy())
+
+
+def solve_exhaustive_posweights(A, y, dicsizes, printmsg=None):
+    """Solves NNLS with 1-sparsity constraints combinatorially
+    (reference mf_utils.py:115-214): min_{w>=0} ||A w - y||^2 with exactly one active
+    column per sub-dictionary.
+
+    Returns (w_nneg (K,), ind_atoms_subdic (K,) int32, ind_atoms_totdic (K,) int32,
+    min_obj float, y_recons (M,)); index arrays are int64 for 4 or more blocks, as in
+    the reference.
+    """
+    if printmsg is not None:
+        print(printmsg, end="")
+    assert isinstance(A, np.ndarray), "A should be a NumPy ndarray"
+    assert A.ndim == 2, "A should be a 2D array"
+    assert not np.any(np.all(A == 0, axis=0)), "All-zero columns detected in A"
+    assert isinstance(y, np.ndarray), "y should be a NumPy ndarray"
+    assert A.size > 0 and y.size > 0, "A and y should not be empty arrays"
+    msg = ("Number of rows in A (%d) should match number of elements in y (%d)"
+           % (A.shape[0], y.size))
+    assert A.shape[0] == y.size, msg
+    assert isinstance(dicsizes, np.ndarray), "dicsizes should be a NumPy ndarray"
+    assert np.all(dicsizes > 0), "All entries of dicsizes should be > 0"
+    msg = ("Number of columns of A (%d) does not equal sum of size of "
+           "sub-matrices in diclengths array (%d)" % (A.shape[1], np.sum(dicsizes)))
+    assert A.shape[1] == np.sum(dicsizes), msg
+
+    w, sub, tot, obj, yrec = solve_exhaustive_posweights_batch(
+        A.astype(np.float64), y.astype(np.float64).reshape(1, -1), dicsizes)
+    idt = np.int64 if dicsizes.size >= 4 else np.int32
+    return (w[0], sub[0].astype(idt), tot[0].astype(idt), float(obj[0]), yrec[0])

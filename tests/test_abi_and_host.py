@@ -1,0 +1,127 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/mfb200.h
+declares; host marshalling logic (tables, scheme plans, NIfTI I/O, sharding)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from microstructure_fingerprinting_b200 import _lib, mf_utils as mfu, nifti
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mfb200.h")).read()
+    declared = set(re.findall(r"\b(mfb_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mfb_version() == 1
+    assert lib.mfb_launch_count() >= 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MFBError):
+        mfu.solve_exhaustive_posweights(np.ones((3, 2)), np.ones(3), np.array([1, 1]))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "microstructure_fingerprinting_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower() or f == "__init__.py" and False, f
+
+
+def test_table_matches_oracle_and_reference(ukbb):
+    msi = mfu.init_PGSE_multishell_interp(ukbb["dictionary"], ukbb["sch_mat"], ukbb["orientation"])
+    assert np.array_equal(msi["nodes"], ukbb["ref_nodes"])
+    assert np.array_equal(msi["table"], ukbb["ref_table"])
+    assert np.array_equal(msi["off"], ukbb["ref_off"])
+    assert np.array_equal(msi["Gms_un"], ukbb["ref_Gms_un"])
+    assert msi["num_subs"] == ukbb["dictionary"].shape[1]
+    assert len(msi["interpolators"]) == msi["Gms_un"].size
+
+
+@pytest.mark.parametrize("mode", ["exact", "between"])
+def test_scheme_plan_matches_oracle(ukbb, mode):
+    msi = mfu.init_PGSE_multishell_interp(ukbb["dictionary"], ukbb["sch_mat"], ukbb["orientation"])
+    sp = mfu.SchemePlan(msi, ukbb["sch_" + mode])
+    tab = orc.init_table(ukbb["dictionary"], ukbb["sch_mat"], ukbb["orientation"])
+    op = orc.plan_scheme(tab, ukbb["sch_" + mode])
+    for k in ("shell_lo", "shell_hi", "gw_lo", "gw_hi", "gdir"):
+        assert np.array_equal(getattr(sp, k), op[k]), k
+
+
+def test_scheme_from_bvals_matches_reference(ukbb):
+    sch = mfu.get_PGSE_scheme_from_bval_bvec_dense(ukbb["sch_mat"], ukbb["bvals"], ukbb["bvecs"], 1e-3)
+    assert np.array_equal(sch, ukbb["sch_exact"])
+
+
+def test_scheme_errors(ukbb):
+    msi = mfu.init_PGSE_multishell_interp(ukbb["dictionary"], ukbb["sch_mat"], ukbb["orientation"])
+    bad = ukbb["sch_exact"].copy()
+    bad[:, 3] *= 10.0
+    with pytest.raises(ValueError, match="Extrapolation not supported"):
+        mfu.SchemePlan(msi, bad)
+    bad = ukbb["sch_exact"].copy()
+    bad[0, 4] *= 2
+    with pytest.raises(ValueError, match="Delta, delta and TE"):
+        mfu.SchemePlan(msi, bad)
+    bad = ukbb["sch_exact"].copy()
+    bad[5, :3] *= 1.5
+    with pytest.raises(ValueError, match="unit norm"):
+        mfu.SchemePlan(msi, bad)
+    with pytest.raises(RuntimeError):
+        mfu.import_PGSE_scheme(np.zeros((3, 6)))
+
+
+def test_dt_vec_to_2darray():
+    v = np.arange(1.0, 7.0)
+    row = mfu.DT_vec_to_2Darray(v, "row")
+    assert np.array_equal(row, [[1, 2, 3], [2, 4, 5], [3, 5, 6]])
+    col = mfu.DT_vec_to_2Darray(v, "column")
+    assert np.array_equal(col, [[1, 2, 4], [2, 3, 5], [4, 5, 6]])
+    dia = mfu.DT_vec_to_2Darray(v, "diagonal")
+    assert np.array_equal(dia, [[1, 4, 6], [4, 2, 5], [6, 5, 3]])
+
+
+@pytest.mark.parametrize("ext", [".nii", ".nii.gz"])
+def test_nifti_roundtrip(tmp_path, ext):
+    rng = np.random.default_rng(0)
+    vol = rng.standard_normal((4, 3, 2, 5))
+    aff = np.array([[2.0, 0, 0, -10], [0, 2.5, 0, 7], [0, 0, 3.0, 1], [0, 0, 0, 1]])
+    p = str(tmp_path / ("vol" + ext))
+    nifti.save(vol, aff, p)
+    back, aff2 = nifti.load(p)
+    assert np.array_equal(back, vol)
+    assert np.allclose(aff2, aff)
+
+
+def test_reads_reference_style_nifti(tmp_path):
+    # float32 volume with qform only, as produced by common neuroimaging tools
+    import struct
+    hdr = bytearray(348)
+    struct.pack_into("<i", hdr, 0, 348)
+    struct.pack_into("<8h", hdr, 40, 3, 2, 2, 2, 1, 1, 1, 1)
+    struct.pack_into("<h", hdr, 70, 16)
+    struct.pack_into("<h", hdr, 72, 32)
+    struct.pack_into("<8f", hdr, 76, 1, 2, 2, 2, 1, 1, 1, 1)
+    struct.pack_into("<f", hdr, 108, 352.0)
+    struct.pack_into("<2h", hdr, 252, 1, 0)
+    struct.pack_into("<6f", hdr, 256, 0, 0, 0, 5, 6, 7)
+    hdr[344:348] = b"n+1\x00"
+    data = np.arange(8, dtype=np.float32)
+    p = str(tmp_path / "q.nii")
+    with open(p, "wb") as f:
+        f.write(bytes(hdr) + b"\0\0\0\0" + data.tobytes())
+    vol, aff = nifti.load(p)
+    assert vol.shape == (2, 2, 2) and vol[1, 0, 0] == 1.0 and vol[0, 1, 0] == 2.0
+    assert np.allclose(aff, [[2, 0, 0, 5], [0, 2, 0, 6], [0, 0, 2, 7], [0, 0, 0, 1]])

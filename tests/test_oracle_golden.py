@@ -4,7 +4,7 @@
 import numpy as np
 import pytest
 
-from conftest import SOLVER_CASE_NAMES
+from tests.conftest import SOLVER_CASE_NAMES
 from oracle import oracle as orc
 
 
