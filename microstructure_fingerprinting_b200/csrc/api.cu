@@ -70,7 +70,7 @@ struct mfb_plan {
     DevPlan dp;
     std::vector<void *> owned;
     // per-chunk workspace
-    Buf type, nbv, lists, counts, tuple, asmall, idx5, w5, obj, yrec, abuf, scratch;
+    Buf type, nbv, lists, counts, tuple, asmall, idx5, w5, obj, yrec, abuf, scratch, fscratch, redo;
     // host staging for mfb_fit_host
     Buf d_y, d_peaks, d_K, d_csf, d_ear, d_params;
     cudaStream_t stream = nullptr;
@@ -165,7 +165,7 @@ extern "C" void mfb_plan_destroy(mfb_plan *pl)
     cudaSetDevice(pl->device);
     for (void *p : pl->owned) cudaFree(p);
     Buf *bufs[] = {&pl->type, &pl->nbv, &pl->lists, &pl->counts, &pl->tuple, &pl->asmall,
-                   &pl->idx5, &pl->w5, &pl->obj, &pl->yrec, &pl->abuf, &pl->scratch,
+                   &pl->idx5, &pl->w5, &pl->obj, &pl->yrec, &pl->abuf, &pl->scratch, &pl->fscratch, &pl->redo,
                    &pl->d_y, &pl->d_peaks, &pl->d_K, &pl->d_csf, &pl->d_ear, &pl->d_params};
     for (Buf *b : bufs) b->release();
     for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
@@ -293,37 +293,65 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
         }
         const int32_t *list = pl->lists.as<int32_t>() + (int64_t)t * nv;
         const bool timed = (flags & 2) && bs.nb >= 2 && Kt == 2;
-        // exact tier: materialise the dictionaries of a sub-chunk, search in reference order
-        const int64_t lda = (bs.ntot + 1) & ~(int64_t)1;
-        const size_t per_vox = (size_t)M * lda * sizeof(double);
-        int64_t sub = std::max<int64_t>(1, std::min<int64_t>(65535, pl->exact_budget / per_vox));
-        sub = std::min(sub, cnt);
-        MFB_TRY(pl->abuf.ensure(per_vox * sub));
-        MFB_TRY(pl->scratch.ensure(exact_scratch_bytes(sub, bs)));
-        for (int64_t s0 = 0; s0 < cnt; s0 += sub) {
-            const int64_t ns = std::min(sub, cnt - s0);
-            MFB_TRY(launch_rotate_assemble(dp, ns, list + s0, peaks, pld, Kt, ct, et,
-                                           pl->abuf.as<double>(), lda, (int64_t)M * lda, st));
-            cudaEvent_t *ev = nullptr;
-            if (timed) {
-                if (pl->events_used + 2 > pl->events.size()) {
-                    cudaEvent_t e0, e1;
-                    MFB_CUDA_TRY(cudaEventCreate(&e0));
-                    MFB_CUDA_TRY(cudaEventCreate(&e1));
-                    pl->events.push_back(e0);
-                    pl->events.push_back(e1);
-                }
-                ev = &pl->events[pl->events_used];
-                pl->events_used += 2;
+        auto next_events = [&]() -> cudaEvent_t * {
+            if (pl->events_used + 2 > pl->events.size()) {
+                cudaEvent_t e0, e1;
+                if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return nullptr;
+                pl->events.push_back(e0);
+                pl->events.push_back(e1);
             }
-            MFB_TRY(launch_exact_search(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda, y, M,
-                                        list + s0, pl->scratch.p, pl->tuple.as<long long>(), st, ev));
-            if (timed) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
-            MFB_TRY(launch_gather_from_A(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda,
-                                         pl->tuple.as<long long>(), list + s0, pl->asmall.as<double>(),
-                                         pl->idx5.as<int32_t>(), st));
+            cudaEvent_t *ev = &pl->events[pl->events_used];
+            pl->events_used += 2;
+            return ev;
+        };
+        // exact tier: materialise the dictionaries of a sub-chunk, search in reference order
+        auto run_exact = [&](const int32_t *lst, int64_t n, bool time_it) -> int {
+            const int64_t lda = (bs.ntot + 1) & ~(int64_t)1;
+            const size_t per_vox = (size_t)M * lda * sizeof(double);
+            int64_t sub = std::max<int64_t>(1, std::min<int64_t>(65535, pl->exact_budget / per_vox));
+            sub = std::min(sub, n);
+            MFB_TRY(pl->abuf.ensure(per_vox * sub));
+            MFB_TRY(pl->scratch.ensure(exact_scratch_bytes(sub, bs)));
+            for (int64_t s0 = 0; s0 < n; s0 += sub) {
+                const int64_t ns = std::min(sub, n - s0);
+                MFB_TRY(launch_rotate_assemble(dp, ns, lst + s0, peaks, pld, Kt, ct, et,
+                                               pl->abuf.as<double>(), lda, (int64_t)M * lda, st));
+                cudaEvent_t *ev = time_it ? next_events() : nullptr;
+                MFB_TRY(launch_exact_search(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda, y, M,
+                                            lst + s0, pl->scratch.p, pl->tuple.as<long long>(), st, ev));
+                if (ev) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
+                MFB_TRY(launch_gather_from_A(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda,
+                                             pl->tuple.as<long long>(), lst + s0, pl->asmall.as<double>(),
+                                             pl->idx5.as<int32_t>(), st));
+            }
+            pl->stats[1] += (double)n;
+            return MFB_OK;
+        };
+        if (!(flags & 1) && fast_supported(dp, Kt, ct, et)) {
+            // fast tier: DMMA screening; uncertain voxels are redone by the exact tier
+            const int64_t fsub = std::min<int64_t>(cnt, 8192);
+            MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(dp, fsub)));
+            MFB_TRY(pl->redo.ensure(sizeof(int32_t) * (nv + 1)));
+            int32_t *redo_count = pl->redo.as<int32_t>();
+            int32_t *redo_list = redo_count + 1;
+            MFB_CUDA_TRY(cudaMemsetAsync(redo_count, 0, sizeof(int32_t), st));
+            for (int64_t s0 = 0; s0 < cnt; s0 += fsub) {
+                const int64_t ns = std::min(fsub, cnt - s0);
+                cudaEvent_t *ev = timed ? next_events() : nullptr;
+                MFB_TRY(launch_fast_search(dp, ns, ct, list + s0, peaks, pld, y, pl->fscratch.p,
+                                           pl->tuple.as<long long>(), redo_list, redo_count, st, ev));
+                if (ev) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
+            }
+            MFB_TRY(launch_gather_from_table(dp, cnt, Kt, ct, et, peaks, pld, pl->tuple.as<long long>(),
+                                             list, pl->asmall.as<double>(), pl->idx5.as<int32_t>(), st));
+            int32_t n_redo = 0;
+            MFB_CUDA_TRY(cudaMemcpyAsync(&n_redo, redo_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            MFB_CUDA_TRY(cudaStreamSynchronize(st));
+            pl->stats[0] += (double)(cnt - n_redo);
+            if (n_redo > 0) MFB_TRY(run_exact(redo_list, n_redo, false));
+        } else {
+            MFB_TRY(run_exact(list, cnt, timed));
         }
-        pl->stats[1] += (double)cnt;
     }
     MFB_TRY(launch_evaluate(nv, M, 0, pl->nbv.as<uint8_t>(), pl->asmall.as<double>(), y, M,
                             pl->tuple.as<long long>(), pl->w5.as<double>(), pl->obj.as<double>(),

@@ -118,6 +118,16 @@ int launch_classify(int64_t V, const int32_t *K, const uint8_t *csf, const uint8
                     int maxfasc, uint8_t *type, uint8_t *nbv, int32_t *lists /*12*V*/,
                     int32_t *counts /*12*/, cudaStream_t st);
 
+// ------------------------- fast tier (fast.cu) -------------------------------------
+// DMMA screening for 2-fascicle voxels ([N,N] and [N,N,1]); voxels whose winner is not
+// certain are appended to redo_list (exact tier).
+bool fast_supported(const DevPlan &p, int K, int csf, int ear);
+size_t fast_scratch_bytes(const DevPlan &p, int64_t V);
+int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_list,
+                       const double *peaks, int peaks_ld, const double *y, void *scratch,
+                       long long *tuple, int32_t *redo_list, int32_t *redo_count, cudaStream_t st,
+                       cudaEvent_t *ev);
+
 // solve_batch helpers
 int launch_unpack_solution(int64_t V, int nb, const double *w5, const int32_t *idx5,
                            double *w, int32_t *idx, cudaStream_t st);

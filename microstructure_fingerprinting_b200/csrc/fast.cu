@@ -1,0 +1,565 @@
+// fast.cu -- the screening ("fast") tier of libmfb200 for 2-fascicle voxels, sm_100a.
+//
+// For a voxel with two fascicles (optionally + the CSF column) the reference
+// (mf_utils.py:288-392 `_2`, 470-607 `_3`) forms the N x N cross-Gram of the two rotated
+// sub-dictionaries over the M measurements and solves a closed-form 2- or 3-variable NNLS
+// per atom pair.  Here:
+//   k_fast_prep   rotates each sub-dictionary once per voxel to get the per-atom
+//                 statistics (|a|^2, a.y, a.csf), stores the interpolation plan, and
+//                 reduces the best single-atom / atom+CSF gains (the pair-independent
+//                 branches of the NNLS);
+//   k_fast_pairs  one CTA per (voxel, 128-atom i1 tile): the rotated, CSF-projected and
+//                 normalised i1 tile stays resident in shared memory, i2 tiles of 32 atoms
+//                 are gathered from the L2-resident lookup table (register-prefetched,
+//                 double-buffered), the correlation tile is formed with FP64 tensor-core
+//                 DMMA (mma.sync.m8n8k4.f64) and consumed in registers by a division-free
+//                 closed-form NNLS + argmax epilogue;
+//   k_fast_select merges the tiles of a voxel and decides whether the winner is certain.
+// Screening works on gains (|y|^2 - residual) in a different summation order than the
+// reference, so it only *selects*: the winning tuple is re-evaluated in the reference's
+// arithmetic by the exact tier's evaluate kernel, and every voxel whose winner is not
+// separated from the runner-up (or from a pair-independent branch) by more than the
+// screening error bound is handed to the exact tier.
+#include <climits>
+
+#include "common.cuh"
+
+namespace mfb {
+
+#define FT_TI 128
+#define FT_TJ 32
+#define FT_THREADS 256
+#define FT_S1 (FT_TI + 4)  // row strides: == 4 mod 16 doubles -> conflict-free fragment loads
+#define FT_S2 (FT_TJ + 4)
+#define FT_NPAR 7          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu
+
+struct FastArgs {
+    DevPlan p;
+    int csf;
+    int Mp;            // M padded to a multiple of 4
+    int Npad;          // N padded to a multiple of FT_TJ
+    int ntI;           // i1 tiles per voxel
+    const int32_t *vox_list;
+    const double *peaks;
+    int peaks_ld;
+    const double *y;
+    int *ip_rows;      // [v][2][M][2]  rl, rh
+    double *ip_w;      // [v][2][M][2]  wl, wh
+    double *colp;      // [v][2][FT_NPAR][Npad]
+    double *voxp;      // [v][8]  y_sq, A33, Y3, gain_c, c0, Gpre(fasc 0), Gpre(fasc 1), -
+    double *cta_gain;  // [v][ntI]
+    double *cta_tol;   // [v][ntI]
+    int *cta_idx;      // [v][ntI]
+    int *cta_flag;     // [v][ntI]
+    long long *tuple;  // [row]
+    int32_t *redo_list;  // voxels handed to the exact tier
+    int32_t *redo_count;
+};
+
+__device__ __forceinline__ int search_left(const double *xs, int n, double x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (xs[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double block_max(double v, double *sm)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = sm[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmax(r, sm[w]);
+    return r;
+}
+
+// Gain (|y|^2 - residual) of the 2-variable NNLS in Gram form (screening precision).
+__device__ __forceinline__ double nnls2_gain(double A11, double A12, double A22, double Y1, double Y2)
+{
+    double w1d = A22 * Y1 - A12 * Y2, w2d = A11 * Y2 - A12 * Y1;
+    double g1 = Y1 > 0 ? Y1 * Y1 / A11 : 0.0, g2 = Y2 > 0 ? Y2 * Y2 / A22 : 0.0;
+    if (w1d > 0 && w2d > 0) {
+        double det = A11 * A22 - A12 * A12;
+        if (det > 0) return fmax((Y1 * w1d + Y2 * w2d) / det, fmax(g1, g2));
+    }
+    return fmax(g1, g2);
+}
+
+// ---------------------------------------------------------------------------------
+// prepass: grid (V, 2), block 256
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
+{
+    extern __shared__ double sm[];
+    const DevPlan &p = a.p;
+    const int M = p.M, N = p.N;
+    double *wl = sm, *wh = sm + M, *ys = sm + 2 * M, *cs = sm + 3 * M, *red = sm + 4 * M;
+    int *rl = (int *)(red + 32), *rh = rl + M;
+    const int64_t v = blockIdx.x;
+    const int k = blockIdx.y;
+    const int64_t row = a.vox_list[v];
+    const double *u = a.peaks + row * a.peaks_ld + 3 * k;
+    const double ux = u[0], uy = u[1], uz = u[2];
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        // same expression order as the exact tier (exact.cu dir_dot / shell_lerp)
+        double x = fabs(__dadd_rn(__dadd_rn(__dmul_rn(p.gdir[3 * m], ux), __dmul_rn(p.gdir[3 * m + 1], uy)),
+                                  __dmul_rn(p.gdir[3 * m + 2], uz)));
+        int s = p.shell_lo[m];
+        const double *xs = p.nodes + p.off[s];
+        int n = p.off[s + 1] - p.off[s];
+        int j = search_left(xs, n, x);
+        j = j < 1 ? 1 : (j > n - 1 ? n - 1 : j);
+        double den = __dsub_rn(xs[j], xs[j - 1]);
+        rl[m] = p.off[s] + j - 1;
+        rh[m] = p.off[s] + j;
+        wh[m] = __ddiv_rn(__dsub_rn(x, xs[j - 1]), den);
+        wl[m] = __ddiv_rn(__dsub_rn(xs[j], x), den);
+        ys[m] = a.y[row * M + m];
+        cs[m] = a.csf ? p.sig_csf[m] : 0.0;
+        int64_t o = ((v * 2 + k) * M + m) * 2;
+        a.ip_rows[o] = rl[m]; a.ip_rows[o + 1] = rh[m];
+        a.ip_w[o] = wl[m]; a.ip_w[o + 1] = wh[m];
+    }
+    __syncthreads();
+    double y_sq = 0.0, A33 = 0.0, Y3 = 0.0;
+    for (int m = 0; m < M; m++) {
+        y_sq = fma(ys[m], ys[m], y_sq);
+        A33 = fma(cs[m], cs[m], A33);
+        Y3 = fma(cs[m], ys[m], Y3);
+    }
+    const double gain_c = (a.csf && Y3 > 0) ? Y3 * Y3 / A33 : 0.0;
+    double *cp = a.colp + (v * 2 + k) * (int64_t)FT_NPAR * a.Npad;
+    double gbest = 0.0;
+    for (int i = threadIdx.x; i < a.Npad; i += blockDim.x) {
+        double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0};
+        if (i < N) {
+            double sq = 0.0, dy = 0.0, d3 = 0.0;
+            for (int m = 0; m < M; m++) {
+                double d = fma(wh[m], p.table[(size_t)rh[m] * N + i], wl[m] * p.table[(size_t)rl[m] * N + i]);
+                sq = fma(d, d, sq);
+                dy = fma(d, ys[m], dy);
+                d3 = fma(d, cs[m], d3);
+            }
+            const double r = rsqrt(sq);
+            if (!a.csf) {
+                par[0] = r;            // scale
+                par[2] = dy * r;       // z
+                gbest = fmax(gbest, dy > 0 ? dy * dy / sq : 0.0);
+            } else {
+                const double gam = d3 * r * rsqrt(A33);      // corr(atom, csf)
+                const double kap2 = fmax(1.0 - gam * gam, 1e-300);
+                const double kap = sqrt(kap2);
+                const double rp = r / kap;                   // 1/|a projected|
+                const double alpha = d3 / A33;
+                par[0] = rp;
+                par[1] = alpha;
+                par[2] = (dy - alpha * Y3) * rp;             // z'
+                par[3] = d3 * rp;                            // beta
+                par[4] = kap;
+                par[5] = gam;
+                par[6] = dy * r;                             // zu
+                gbest = fmax(gbest, nnls2_gain(sq, d3, A33, dy, Y3));
+            }
+        }
+        for (int q = 0; q < FT_NPAR; q++) cp[(size_t)q * a.Npad + i] = par[q];
+    }
+    gbest = block_max(gbest, red);
+    if (threadIdx.x == 0) {
+        double *vp = a.voxp + v * 8;
+        vp[5 + k] = fmax(gbest, gain_c);
+        if (k == 0) {
+            vp[0] = y_sq; vp[1] = A33; vp[2] = Y3; vp[3] = gain_c;
+            vp[4] = 4.0 * (M + 8) * 2.2204e-16 * y_sq;   // c0: screening error scale
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// pair scan
+// ---------------------------------------------------------------------------------
+struct Track {
+    double bnum, bdet;   // best gain as a fraction
+    double thr, c0bd;    // bnum - c0, c0 * bdet (threshold test without divisions)
+    int bidx, flag;
+};
+
+// Slow path: the pair is better than, or within tolerance of, the current best.
+__device__ __noinline__ void track_update(Track &t, double num, double det, int idx, double c0,
+                                          double wide)
+{
+    if (!(det > 1e-12)) { t.flag |= 2; return; }       // numerically singular pair: sticky
+    const double g = num / det, gb = t.bnum / t.bdet;
+    if (det < 1e-6) t.flag |= 2;                        // ill-conditioned and competitive: sticky
+    if (g > gb) {
+        if (g > gb + wide) t.flag &= 2;                 // clear the near-tie bit, keep sticky
+        else t.flag |= 1;
+        t.bnum = num; t.bdet = det; t.bidx = idx;
+        t.thr = num - c0; t.c0bd = c0 * det;
+    } else {
+        t.flag |= 1;
+    }
+}
+
+template <int CSF>
+__global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    const DevPlan &p = a.p;
+    const int M = p.M, N = p.N, Mp = a.Mp;
+    double *D1s = smem;                                   // [Mp][FT_S1]
+    double *D2s = D1s + (size_t)Mp * FT_S1;               // [2][Mp][FT_S2]
+    double *colq = D2s + (size_t)2 * Mp * FT_S2;          // [2][5][FT_TJ]  z, beta, kappa, gamma, zu
+    double *w2l = colq + 2 * 5 * FT_TJ;                   // [Mp] plan of fascicle 2
+    double *w2h = w2l + Mp;
+    double *cs = w2h + Mp;                                // [Mp] csf column
+    double *red = cs + Mp;                                // [64]
+    int *r2l = (int *)(red + 64);
+    int *r2h = r2l + Mp;
+
+    const int64_t v = blockIdx.y;
+    const int tI = blockIdx.x;
+    const int i0 = tI * FT_TI;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const double *vp = a.voxp + v * 8;
+    const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
+    const double y_sq = vp[0];
+    const double gpre = fmax(vp[5], vp[6]);
+    const double wide = 3e-7 * y_sq;
+    const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
+    const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
+
+    // ---- plans ----
+    for (int m = tid; m < Mp; m += FT_THREADS) {
+        if (m < M) {
+            int64_t o = ((v * 2 + 1) * M + m) * 2;
+            r2l[m] = a.ip_rows[o]; r2h[m] = a.ip_rows[o + 1];
+            w2l[m] = a.ip_w[o]; w2h[m] = a.ip_w[o + 1];
+            cs[m] = CSF ? p.sig_csf[m] : 0.0;
+        } else {
+            r2l[m] = 0; r2h[m] = 0; w2l[m] = 0.0; w2h[m] = 0.0; cs[m] = 0.0;
+        }
+    }
+    // ---- resident i1 tile: rotate, project out the CSF column, normalise ----
+    {
+        const int ii = tid & (FT_TI - 1);
+        const int i = i0 + ii;
+        const bool ok = i < N;
+        const double sc = ok ? cp1[i] : 0.0;
+        const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
+        const int *rows = a.ip_rows + (v * 2 + 0) * (int64_t)M * 2;
+        const double *wts = a.ip_w + (v * 2 + 0) * (int64_t)M * 2;
+        for (int m = tid / FT_TI; m < Mp; m += FT_THREADS / FT_TI) {
+            double val = 0.0;
+            if (ok && m < M) {
+                double d = fma(wts[2 * m + 1], p.table[(size_t)rows[2 * m + 1] * N + i],
+                               wts[2 * m] * p.table[(size_t)rows[2 * m] * N + i]);
+                if (CSF) d = fma(-al, p.sig_csf[m], d);
+                val = d * sc;
+            }
+            D1s[(size_t)m * FT_S1 + ii] = val;
+        }
+    }
+    __syncthreads();
+
+    // ---- per-thread row constants (rows g and g+8 of the warp's 16-row slab) ----
+    const int wrow = warp * 16;
+    double z1[2], b1[2], k1[2], g1[2], zu1[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int i = i0 + wrow + 8 * mt + g;
+        const bool ok = i < N;
+        z1[mt] = ok ? cp1[(size_t)2 * a.Npad + i] : 0.0;
+        b1[mt] = (CSF && ok) ? cp1[(size_t)3 * a.Npad + i] : 0.0;
+        k1[mt] = (CSF && ok) ? cp1[(size_t)4 * a.Npad + i] : 0.0;
+        g1[mt] = (CSF && ok) ? cp1[(size_t)5 * a.Npad + i] : 0.0;
+        zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
+    }
+
+    Track trk;
+    trk.bnum = gpre; trk.bdet = 1.0; trk.thr = gpre - c0; trk.c0bd = c0; trk.bidx = -1; trk.flag = 0;
+
+    // ---- i2 tile gather: thread -> column jj = tid % 32, rows m = tid/32 + 8*q ----
+    const int jj = tid & (FT_TJ - 1);
+    const int mrow0 = tid / FT_TJ;             // 0..7
+    constexpr int NQ = 14;                     // 8*14 = 112 >= Mp (Mp <= 112 checked on host)
+    double plo[NQ], phi[NQ];
+    double csc = 0.0, cal = 0.0;
+    const int ntJ = a.Npad / FT_TJ;
+
+    auto gather_issue = [&](int jt) {
+        const int j = jt * FT_TJ + jj;
+        const bool ok = j < N;
+        csc = ok ? cp2[j] : 0.0;
+        cal = (CSF && ok) ? cp2[(size_t)a.Npad + j] : 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int m = mrow0 + 8 * q;
+            plo[q] = 0.0; phi[q] = 0.0;
+            if (ok && m < M) {
+                plo[q] = __ldg(p.table + (size_t)r2l[m] * N + j);
+                phi[q] = __ldg(p.table + (size_t)r2h[m] * N + j);
+            }
+        }
+    };
+    auto gather_store = [&](int jt, int buf) {
+        double *dst = D2s + (size_t)buf * Mp * FT_S2;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int m = mrow0 + 8 * q;
+            if (m < Mp) {
+                double d = fma(w2h[m], phi[q], w2l[m] * plo[q]);
+                if (CSF) d = fma(-cal, cs[m], d);
+                dst[(size_t)m * FT_S2 + jj] = d * csc;
+            }
+        }
+        // column parameters of this tile
+        if (tid < 5 * FT_TJ) {
+            const int q = tid / FT_TJ, c = tid % FT_TJ;
+            const int j = jt * FT_TJ + c;
+            colq[(buf * 5 + q) * FT_TJ + c] = cp2[(size_t)(q + 2) * a.Npad + j];
+        }
+    };
+
+    gather_issue(0);
+    gather_store(0, 0);
+    __syncthreads();
+
+    for (int jt = 0; jt < ntJ; jt++) {
+        const int buf = jt & 1;
+        if (jt + 1 < ntJ) gather_issue(jt + 1);
+
+        // ---- correlation tile: 16 x 32 per warp, DMMA m8n8k4 over k ----
+        double acc[2][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+        const double *A_ = D1s + (size_t)t4 * FT_S1 + wrow + g;
+        const double *B_ = D2s + (size_t)buf * Mp * FT_S2 + (size_t)t4 * FT_S2 + g;
+#pragma unroll 3
+        for (int ks = 0; ks < Mp / 4; ks++) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                 : "d"(af[mt]), "d"(bf[nt]));
+        }
+
+        // ---- closed-form NNLS screening + argmax, in registers ----
+        const double *cq = colq + buf * 5 * FT_TJ;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int c = 8 * nt + 2 * t4;
+            const double2 z2v = *reinterpret_cast<const double2 *>(cq + c);
+            double2 b2v, k2v, g2v, zu2v;
+            if (CSF) {
+                b2v = *reinterpret_cast<const double2 *>(cq + FT_TJ + c);
+                k2v = *reinterpret_cast<const double2 *>(cq + 2 * FT_TJ + c);
+                g2v = *reinterpret_cast<const double2 *>(cq + 3 * FT_TJ + c);
+                zu2v = *reinterpret_cast<const double2 *>(cq + 4 * FT_TJ + c);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const double z2 = e ? z2v.y : z2v.x;
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const double rho = acc[mt][nt][e];
+                    const double w1 = fma(-rho, z2, z1[mt]);
+                    const double w2 = fma(-rho, z1[mt], z2);
+                    double det = fma(-rho, rho, 1.0);
+                    double num = fma(z1[mt], w1, z2 * w2);
+                    bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
+                    if (CSF) {
+                        const double b2 = e ? b2v.y : b2v.x;
+                        const double w3 = fma(-b2, w2, fma(-b1[mt], w1, Y3 * det));
+                        pos = pos && (__double2hiint(w3) > 0);
+                        num = fma(gain_c, det, num);
+                        if (!pos) {
+                            // best of the 2-column sub-problems: only the fascicle pair
+                            // depends on (i1, i2); the atom+CSF ones are in gpre
+                            const double k2 = e ? k2v.y : k2v.x, g2 = e ? g2v.y : g2v.x;
+                            const double zu2 = e ? zu2v.y : zu2v.x;
+                            const double r = fma(rho * k1[mt], k2, g1[mt] * g2);
+                            const double v1 = fma(-r, zu2, zu1[mt]);
+                            const double v2 = fma(-r, zu1[mt], zu2);
+                            pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
+                            det = fma(-r, r, 1.0);
+                            num = fma(zu1[mt], v1, zu2 * v2);
+                        }
+                    }
+                    // (num + c0)/det >= (bnum - c0)/bdet  <=>  num*bdet + c0*bdet >= thr*det
+                    if (pos && fma(num, trk.bdet, trk.c0bd) >= trk.thr * det) {
+                        const int i1 = i0 + wrow + 8 * mt + g;
+                        const int j = jt * FT_TJ + c + e;
+                        track_update(trk, num, det, i1 * N + j, c0, wide);
+                    }
+                }
+            }
+        }
+
+        if (jt + 1 < ntJ) gather_store(jt + 1, buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- CTA reduction: best gain, tie -> lower index; near-tie bookkeeping ----
+    double gt = trk.bidx >= 0 ? trk.bnum / trk.bdet : -1.0;
+    double tolt = trk.bidx >= 0 ? c0 / trk.bdet : 0.0;
+    double gm = gt;
+    int im = trk.bidx >= 0 ? trk.bidx : INT_MAX;
+    for (int o = 16; o > 0; o >>= 1) {
+        double og = __shfl_xor_sync(0xffffffffu, gm, o);
+        int oi = __shfl_xor_sync(0xffffffffu, im, o);
+        if (og > gm || (og == gm && oi < im)) { gm = og; im = oi; }
+    }
+    double *redg = red;
+    int *redi = (int *)(red + 8);
+    if (lane == 0) { redg[warp] = gm; redi[warp] = im; }
+    __syncthreads();
+    double G = redg[0];
+    int I = redi[0];
+    for (int w = 1; w < FT_THREADS / 32; w++)
+        if (redg[w] > G || (redg[w] == G && redi[w] < I)) { G = redg[w]; I = redi[w]; }
+    // tolerance of the winner
+    __shared__ double s_tolG;
+    __shared__ int s_flag;
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    if (trk.bidx >= 0 && trk.bidx == I) s_tolG = tolt;
+    __syncthreads();
+    const double tolG = I != INT_MAX ? s_tolG : 0.0;
+    if (trk.bidx >= 0) {
+        const bool winner = trk.bidx == I;
+        const bool close = gt + tolt >= G - tolG;
+        if ((winner && trk.flag) || (!winner && close) || (close && (trk.flag & 2))) atomicOr(&s_flag, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int64_t o = v * a.ntI + tI;
+        a.cta_gain[o] = G;
+        a.cta_tol[o] = tolG;
+        a.cta_idx[o] = I == INT_MAX ? -1 : I;
+        a.cta_flag[o] = s_flag;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// select: one thread per voxel
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const double *vp = a.voxp + v * 8;
+    const double c0 = vp[4];
+    const double gpre = fmax(vp[5], vp[6]);
+    double G = -1.0, tolG = 0.0;
+    int I = -1, best_t = -1;
+    for (int t = 0; t < a.ntI; t++) {
+        const int64_t o = v * a.ntI + t;
+        if (a.cta_idx[o] >= 0 && (a.cta_gain[o] > G || (a.cta_gain[o] == G && a.cta_idx[o] < I))) {
+            G = a.cta_gain[o]; tolG = a.cta_tol[o]; I = a.cta_idx[o]; best_t = t;
+        }
+    }
+    bool certain = I >= 0;
+    for (int t = 0; t < a.ntI && certain; t++) {
+        const int64_t o = v * a.ntI + t;
+        if (t == best_t) { if (a.cta_flag[o]) certain = false; continue; }
+        if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] >= G - tolG) certain = false;
+    }
+    // pair-independent branches (single atoms, atom + CSF, CSF alone) must be clearly worse
+    if (certain && !(G - tolG > gpre + 16.0 * c0)) certain = false;
+    const int64_t row = a.vox_list[v];
+    if (certain) {
+        a.tuple[row] = (long long)I;
+    } else {
+        int pos = atomicAdd(a.redo_count, 1);
+        a.redo_list[pos] = (int32_t)row;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+bool fast_supported(const DevPlan &p, int K, int csf, int ear)
+{
+    const int Mp = (p.M + 3) & ~3;
+    return K == 2 && !ear && !p.has_between && Mp <= 112 && p.N >= 8 && p.N <= 46000 &&
+           (csf == 0 || p.sig_csf);
+}
+
+size_t fast_scratch_bytes(const DevPlan &p, int64_t V)
+{
+    const int Npad = (p.N + FT_TJ - 1) / FT_TJ * FT_TJ;
+    const int ntI = (p.N + FT_TI - 1) / FT_TI;
+    size_t s = 0;
+    s += al256(sizeof(int) * V * 2 * p.M * 2);
+    s += al256(sizeof(double) * V * 2 * p.M * 2);
+    s += al256(sizeof(double) * V * 2 * FT_NPAR * Npad);
+    s += al256(sizeof(double) * V * 8);
+    s += 2 * al256(sizeof(double) * V * ntI);
+    s += 2 * al256(sizeof(int) * V * ntI);
+    return s;
+}
+
+int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_list,
+                       const double *peaks, int peaks_ld, const double *y, void *scratch,
+                       long long *tuple, int32_t *redo_list, int32_t *redo_count, cudaStream_t st,
+                       cudaEvent_t *ev)
+{
+    if (V == 0) return MFB_OK;
+    FastArgs a;
+    a.p = p; a.csf = csf;
+    a.Mp = (p.M + 3) & ~3;
+    a.Npad = (p.N + FT_TJ - 1) / FT_TJ * FT_TJ;
+    a.ntI = (p.N + FT_TI - 1) / FT_TI;
+    a.vox_list = vox_list; a.peaks = peaks; a.peaks_ld = peaks_ld; a.y = y;
+    char *q = (char *)scratch;
+    a.ip_rows = (int *)q; q += al256(sizeof(int) * V * 2 * p.M * 2);
+    a.ip_w = (double *)q; q += al256(sizeof(double) * V * 2 * p.M * 2);
+    a.colp = (double *)q; q += al256(sizeof(double) * V * 2 * FT_NPAR * a.Npad);
+    a.voxp = (double *)q; q += al256(sizeof(double) * V * 8);
+    a.cta_gain = (double *)q; q += al256(sizeof(double) * V * a.ntI);
+    a.cta_tol = (double *)q; q += al256(sizeof(double) * V * a.ntI);
+    a.cta_idx = (int *)q; q += al256(sizeof(int) * V * a.ntI);
+    a.cta_flag = (int *)q;
+    a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count;
+
+    const size_t smem_prep = sizeof(double) * (4 * p.M + 32) + sizeof(int) * 2 * p.M;
+    MFB_LAUNCH(k_fast_prep, dim3((unsigned)V, 2), 256, smem_prep, st, a);
+
+    const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)2 * a.Mp * FT_S2 + 2 * 5 * FT_TJ +
+                                          3 * a.Mp + 64) + sizeof(int) * 2 * a.Mp;
+    if (smem + 64 > 227 * 1024) {
+        set_error("fast tier: tile does not fit in shared memory");
+        return MFB_EUNSUPPORTED;
+    }
+    static size_t attr_set[2] = {0, 0};
+    if (attr_set[csf ? 1 : 0] < smem) {
+        if (csf) MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[csf ? 1 : 0] = smem;
+    }
+    if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
+    dim3 grid(a.ntI, (unsigned)V);
+    if (csf) MFB_LAUNCH(k_fast_pairs<1>, grid, FT_THREADS, smem, st, a);
+    else MFB_LAUNCH(k_fast_pairs<0>, grid, FT_THREADS, smem, st, a);
+    if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
+    MFB_LAUNCH(k_fast_select, (unsigned)((V + 127) / 128), 128, 0, st, a, V);
+    return MFB_OK;
+}
+
+}  // namespace mfb

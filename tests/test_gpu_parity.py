@@ -248,3 +248,34 @@ def test_full_size_properties():
     sub = np.arange(10, 40)
     ref = oracle_rows(ph, sub)                            # oracle on a subsample
     compare_rows(rows[sub], ref, ph, idx=sub)
+
+
+@pytest.mark.parametrize("n_atoms,n_vox,snr", [(200, 1500, 30.0), (1000, 600, 30.0), (333, 800, 1e9),
+                                                (64, 800, 10.0)])
+def test_fast_tier_equals_exact_tier(n_atoms, n_vox, snr):
+    """The DMMA screening tier only selects; the winner is re-evaluated in the reference's
+    arithmetic, so rows must be bit-identical to the exact (reference-order) tier."""
+    ph = make_phantom(n_atoms=n_atoms, n_vox=n_vox, seed=n_atoms, frac_k=(0.0, 0.1, 0.9),
+                      csf_frac=0.4, snr=snr)
+    fast = ph.gpu_rows(flags=0)
+    exact = ph.gpu_rows(flags=1)
+    assert np.array_equal(fast, exact)
+    sub = np.arange(0, 24)
+    compare_rows(fast[sub], oracle_rows(ph, sub), ph, idx=sub, exact_bits=True)
+
+
+def test_fast_tier_degenerate_voxels():
+    """Identical / nearly parallel peaks, single-fascicle data in a 2-fascicle voxel, zero
+    signal: the screening tier must hand these to the exact tier or agree with it."""
+    ph = make_phantom(n_atoms=120, n_vox=64, seed=77, frac_k=(0.0, 0.0, 1.0), csf_frac=0.5)
+    ph.peaks[0:8, 3:6] = ph.peaks[0:8, 0:3]                       # identical peaks
+    ph.peaks[8:16, 3:6] = ph.peaks[8:16, 0:3] + 1e-9              # nearly identical
+    ph.peaks[8:16, 3:6] /= np.linalg.norm(ph.peaks[8:16, 3:6], axis=1, keepdims=True)
+    ph.Y[16:20] = 0.0                                             # zero signal
+    ph.Y[20:24] = -np.abs(ph.Y[20:24])                            # nothing beats w = 0
+    from tests.phantom import rotate_columns
+    ph.Y[24:32] = 500.0 * rotate_columns(ph.dic, ph.sch, ph.peaks[24:32, :3], ph.atoms[24:32, 0])
+    fast = ph.gpu_rows(flags=0)
+    exact = ph.gpu_rows(flags=1)
+    assert np.array_equal(fast, exact)
+    compare_rows(fast, oracle_rows(ph), ph, exact_bits=True)
