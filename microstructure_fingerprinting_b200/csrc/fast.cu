@@ -33,6 +33,10 @@ namespace mfb {
 #define FT_S2 (FT_TJ + 4)
 #define FT_NPAR 7          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu
 
+// 1 - rho^2 below which a pair is tracked as ill-conditioned (its screening error bound
+// c0 / det is no longer small against typical gaps between competing pairs)
+static constexpr double kIllDet = 1e-4;
+
 struct FastArgs {
     DevPlan p;
     int csf;
@@ -51,6 +55,7 @@ struct FastArgs {
     double *cta_tol;   // [v][ntI]
     int *cta_idx;      // [v][ntI]
     int *cta_flag;     // [v][ntI]
+    double *cta_ill;   // [v][ntI]  best optimistic gain among ill-conditioned pairs
     long long *tuple;  // [row]
     int32_t *redo_list;  // voxels handed to the exact tier
     int32_t *redo_count;
@@ -181,27 +186,35 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
 // ---------------------------------------------------------------------------------
 // pair scan
 // ---------------------------------------------------------------------------------
-struct Track {
-    double bnum, bdet;   // best gain as a fraction
-    double thr, c0bd;    // bnum - c0, c0 * bdet (threshold test without divisions)
-    int bidx, flag;
-};
-
-// Slow path: the pair is better than, or within tolerance of, the current best.
-__device__ __noinline__ void track_update(Track &t, double num, double det, int idx, double c0,
-                                          double wide)
+// Screening quantities of one (i1, i2) pair from its correlation rho (registers only).
+// Returns false when the pair has no both-positive closed form worth tracking.
+template <int CSF>
+__device__ __forceinline__ bool pair_gain(double rho, double z1, double z2, double b1, double b2,
+                                          double k1, double k2, double g1, double g2, double zu1,
+                                          double zu2, double Y3, double gain_c, double &num,
+                                          double &det)
 {
-    if (!(det > 1e-12)) { t.flag |= 2; return; }       // numerically singular pair: sticky
-    const double g = num / det, gb = t.bnum / t.bdet;
-    if (det < 1e-6) t.flag |= 2;                        // ill-conditioned and competitive: sticky
-    if (g > gb) {
-        if (g > gb + wide) t.flag &= 2;                 // clear the near-tie bit, keep sticky
-        else t.flag |= 1;
-        t.bnum = num; t.bdet = det; t.bidx = idx;
-        t.thr = num - c0; t.c0bd = c0 * det;
-    } else {
-        t.flag |= 1;
+    const double w1 = fma(-rho, z2, z1);
+    const double w2 = fma(-rho, z1, z2);
+    det = fma(-rho, rho, 1.0);
+    num = fma(z1, w1, z2 * w2);
+    bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
+    if (CSF) {
+        const double w3 = fma(-b2, w2, fma(-b1, w1, Y3 * det));
+        pos = pos && (__double2hiint(w3) > 0);
+        num = fma(gain_c, det, num);
+        if (!pos) {
+            // best of the 2-column sub-problems: only the fascicle pair depends on (i1, i2);
+            // the atom + CSF ones are pair-independent and live in gpre
+            const double r = fma(rho * k1, k2, g1 * g2);
+            const double v1 = fma(-r, zu2, zu1);
+            const double v2 = fma(-r, zu1, zu2);
+            pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
+            det = fma(-r, r, 1.0);
+            num = fma(zu1, v1, zu2 * v2);
+        }
     }
+    return pos;
 }
 
 template <int CSF>
@@ -213,12 +226,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     double *D1s = smem;                                   // [Mp][FT_S1]
     double *D2s = D1s + (size_t)Mp * FT_S1;               // [2][Mp][FT_S2]
     double *colq = D2s + (size_t)2 * Mp * FT_S2;          // [2][5][FT_TJ]  z, beta, kappa, gamma, zu
-    double *w2l = colq + 2 * 5 * FT_TJ;                   // [Mp] plan of fascicle 2
+    double *w2l = colq + 2 * 5 * FT_TJ;                   // [Mp] plan of fascicle 2 (fascicle 1 during build)
     double *w2h = w2l + Mp;
     double *cs = w2h + Mp;                                // [Mp] csf column
     double *red = cs + Mp;                                // [64]
     int *r2l = (int *)(red + 64);
     int *r2h = r2l + Mp;
+    __shared__ unsigned long long s_thr;                  // CTA-wide lower bound on the winning gain
+    __shared__ double s_tolG;
+    __shared__ int s_flag;
 
     const int64_t v = blockIdx.y;
     const int tI = blockIdx.x;
@@ -229,41 +245,62 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
     const double y_sq = vp[0];
     const double gpre = fmax(vp[5], vp[6]);
-    const double wide = 3e-7 * y_sq;
+    // pairs with det >= kIllDet have a screening error below c0 / kIllDet; two such pairs
+    // further apart than `wide` are ordered with certainty
+    const double wide = 4.0 * c0 / kIllDet;
+    const double negc0 = -c0;
     const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
     const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
 
-    // ---- plans ----
-    for (int m = tid; m < Mp; m += FT_THREADS) {
-        if (m < M) {
-            int64_t o = ((v * 2 + 1) * M + m) * 2;
-            r2l[m] = a.ip_rows[o]; r2h[m] = a.ip_rows[o + 1];
-            w2l[m] = a.ip_w[o]; w2h[m] = a.ip_w[o + 1];
-            cs[m] = CSF ? p.sig_csf[m] : 0.0;
-        } else {
-            r2l[m] = 0; r2h[m] = 0; w2l[m] = 0.0; w2h[m] = 0.0; cs[m] = 0.0;
+    auto load_plan = [&](int k) {
+        for (int m = tid; m < Mp; m += FT_THREADS) {
+            if (m < M) {
+                int64_t o = ((v * 2 + k) * M + m) * 2;
+                r2l[m] = a.ip_rows[o]; r2h[m] = a.ip_rows[o + 1];
+                w2l[m] = a.ip_w[o]; w2h[m] = a.ip_w[o + 1];
+                cs[m] = CSF ? p.sig_csf[m] : 0.0;
+            } else {
+                r2l[m] = 0; r2h[m] = 0; w2l[m] = 0.0; w2h[m] = 0.0; cs[m] = 0.0;
+            }
         }
-    }
+    };
     // ---- resident i1 tile: rotate, project out the CSF column, normalise ----
+    load_plan(0);
+    if (tid == 0) { s_thr = (unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0)); s_flag = 0; }
+    __syncthreads();
     {
         const int ii = tid & (FT_TI - 1);
         const int i = i0 + ii;
         const bool ok = i < N;
         const double sc = ok ? cp1[i] : 0.0;
         const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
-        const int *rows = a.ip_rows + (v * 2 + 0) * (int64_t)M * 2;
-        const double *wts = a.ip_w + (v * 2 + 0) * (int64_t)M * 2;
-        for (int m = tid / FT_TI; m < Mp; m += FT_THREADS / FT_TI) {
-            double val = 0.0;
-            if (ok && m < M) {
-                double d = fma(wts[2 * m + 1], p.table[(size_t)rows[2 * m + 1] * N + i],
-                               wts[2 * m] * p.table[(size_t)rows[2 * m] * N + i]);
-                if (CSF) d = fma(-al, p.sig_csf[m], d);
-                val = d * sc;
+        const double *Tc = p.table + (ok ? i : 0);
+        constexpr int RS = FT_THREADS / FT_TI;            // rows per pass (2)
+        constexpr int UB = 9;                              // loads in flight per thread: 2*UB
+        for (int mb = tid / FT_TI; mb < Mp; mb += RS * UB) {
+            double lo[UB], hi[UB];
+#pragma unroll
+            for (int q = 0; q < UB; q++) {
+                const int m = mb + RS * q;
+                lo[q] = 0.0; hi[q] = 0.0;
+                if (ok && m < M) {
+                    lo[q] = __ldg(Tc + (size_t)r2l[m] * N);
+                    hi[q] = __ldg(Tc + (size_t)r2h[m] * N);
+                }
             }
-            D1s[(size_t)m * FT_S1 + ii] = val;
+#pragma unroll
+            for (int q = 0; q < UB; q++) {
+                const int m = mb + RS * q;
+                if (m < Mp) {
+                    double d = fma(w2h[m], hi[q], w2l[m] * lo[q]);
+                    if (CSF) d = fma(-al, cs[m], d);
+                    D1s[(size_t)m * FT_S1 + ii] = d * sc;
+                }
+            }
         }
     }
+    __syncthreads();
+    load_plan(1);
     __syncthreads();
 
     // ---- per-thread row constants (rows g and g+8 of the warp's 16-row slab) ----
@@ -280,22 +317,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
     }
 
-    Track trk;
-    trk.bnum = gpre; trk.bdet = 1.0; trk.thr = gpre - c0; trk.c0bd = c0; trk.bidx = -1; trk.flag = 0;
+    // thread-local best (central gain gb, tolerance tb) and the shared screening threshold
+    double gb = -1.0, tb = 0.0, thr = fmax(gpre - c0, 0.0), gill = -1.0;
+    int bidx = -1, flag = 0;
 
     // ---- i2 tile gather: thread -> column jj = tid % 32, rows m = tid/32 + 8*q ----
     const int jj = tid & (FT_TJ - 1);
     const int mrow0 = tid / FT_TJ;             // 0..7
     constexpr int NQ = 14;                     // 8*14 = 112 >= Mp (Mp <= 112 checked on host)
     double plo[NQ], phi[NQ];
-    double csc = 0.0, cal = 0.0;
+    double csc = 0.0, cal = 0.0, cpar = 0.0;
     const int ntJ = a.Npad / FT_TJ;
 
     auto gather_issue = [&](int jt) {
         const int j = jt * FT_TJ + jj;
         const bool ok = j < N;
-        csc = ok ? cp2[j] : 0.0;
-        cal = (CSF && ok) ? cp2[(size_t)a.Npad + j] : 0.0;
+        csc = ok ? __ldg(cp2 + j) : 0.0;
+        cal = (CSF && ok) ? __ldg(cp2 + (size_t)a.Npad + j) : 0.0;
+        if (tid < 5 * FT_TJ)  // column parameter (q = tid / 32) of column tid % 32
+            cpar = __ldg(cp2 + (size_t)(tid / FT_TJ + 2) * a.Npad + jt * FT_TJ + jj);
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             const int m = mrow0 + 8 * q;
@@ -306,7 +346,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             }
         }
     };
-    auto gather_store = [&](int jt, int buf) {
+    auto gather_store = [&](int buf) {
         double *dst = D2s + (size_t)buf * Mp * FT_S2;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
@@ -317,21 +357,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 dst[(size_t)m * FT_S2 + jj] = d * csc;
             }
         }
-        // column parameters of this tile
-        if (tid < 5 * FT_TJ) {
-            const int q = tid / FT_TJ, c = tid % FT_TJ;
-            const int j = jt * FT_TJ + c;
-            colq[(buf * 5 + q) * FT_TJ + c] = cp2[(size_t)(q + 2) * a.Npad + j];
-        }
+        if (tid < 5 * FT_TJ) colq[(buf * 5 + tid / FT_TJ) * FT_TJ + jj] = cpar;
     };
 
     gather_issue(0);
-    gather_store(0, 0);
+    gather_store(0);
     __syncthreads();
 
     for (int jt = 0; jt < ntJ; jt++) {
         const int buf = jt & 1;
         if (jt + 1 < ntJ) gather_issue(jt + 1);
+        thr = fmax(thr, __longlong_as_double((long long)s_thr));
 
         // ---- correlation tile: 16 x 32 per warp, DMMA m8n8k4 over k ----
         double acc[2][4][2];
@@ -357,13 +393,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                                  : "d"(af[mt]), "d"(bf[nt]));
         }
 
-        // ---- closed-form NNLS screening + argmax, in registers ----
+        // ---- closed-form NNLS screening, branch-free over the thread's 16 pairs ----
+        // (num + c0)/det >= thr  <=>  fma(-thr, det, num) >= -c0
         const double *cq = colq + buf * 5 * FT_TJ;
+        unsigned hit = 0;
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
             const int c = 8 * nt + 2 * t4;
             const double2 z2v = *reinterpret_cast<const double2 *>(cq + c);
-            double2 b2v, k2v, g2v, zu2v;
+            double2 b2v = z2v, k2v = z2v, g2v = z2v, zu2v = z2v;
             if (CSF) {
                 b2v = *reinterpret_cast<const double2 *>(cq + FT_TJ + c);
                 k2v = *reinterpret_cast<const double2 *>(cq + 2 * FT_TJ + c);
@@ -371,78 +409,84 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 zu2v = *reinterpret_cast<const double2 *>(cq + 4 * FT_TJ + c);
             }
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const double z2 = e ? z2v.y : z2v.x;
+            for (int e = 0; e < 2; e++)
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++) {
-                    const double rho = acc[mt][nt][e];
-                    const double w1 = fma(-rho, z2, z1[mt]);
-                    const double w2 = fma(-rho, z1[mt], z2);
-                    double det = fma(-rho, rho, 1.0);
-                    double num = fma(z1[mt], w1, z2 * w2);
-                    bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
-                    if (CSF) {
-                        const double b2 = e ? b2v.y : b2v.x;
-                        const double w3 = fma(-b2, w2, fma(-b1[mt], w1, Y3 * det));
-                        pos = pos && (__double2hiint(w3) > 0);
-                        num = fma(gain_c, det, num);
-                        if (!pos) {
-                            // best of the 2-column sub-problems: only the fascicle pair
-                            // depends on (i1, i2); the atom+CSF ones are in gpre
-                            const double k2 = e ? k2v.y : k2v.x, g2 = e ? g2v.y : g2v.x;
-                            const double zu2 = e ? zu2v.y : zu2v.x;
-                            const double r = fma(rho * k1[mt], k2, g1[mt] * g2);
-                            const double v1 = fma(-r, zu2, zu1[mt]);
-                            const double v2 = fma(-r, zu1[mt], zu2);
-                            pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
-                            det = fma(-r, r, 1.0);
-                            num = fma(zu1[mt], v1, zu2 * v2);
-                        }
-                    }
-                    // (num + c0)/det >= (bnum - c0)/bdet  <=>  num*bdet + c0*bdet >= thr*det
-                    if (pos && fma(num, trk.bdet, trk.c0bd) >= trk.thr * det) {
-                        const int i1 = i0 + wrow + 8 * mt + g;
-                        const int j = jt * FT_TJ + c + e;
-                        track_update(trk, num, det, i1 * N + j, c0, wide);
-                    }
+                    double num, det;
+                    const bool pos = pair_gain<CSF>(acc[mt][nt][e], z1[mt], e ? z2v.y : z2v.x, b1[mt],
+                                                    e ? b2v.y : b2v.x, k1[mt], e ? k2v.y : k2v.x, g1[mt],
+                                                    e ? g2v.y : g2v.x, zu1[mt], e ? zu2v.y : zu2v.x, Y3,
+                                                    gain_c, num, det);
+                    if (pos && fma(-thr, det, num) >= negc0) hit |= 1u << (nt * 4 + e * 2 + mt);
                 }
+        }
+        // ---- rare: some lane of the warp has a competitive pair ----
+        if (__any_sync(0xffffffffu, hit != 0)) {
+            if (hit) {
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) {
+                            if (!(hit & (1u << (nt * 4 + e * 2 + mt)))) continue;
+                            const int c = 8 * nt + 2 * t4 + e;
+                            double num, det;
+                            pair_gain<CSF>(acc[mt][nt][e], z1[mt], cq[c], b1[mt], cq[FT_TJ + c], k1[mt],
+                                           cq[2 * FT_TJ + c], g1[mt], cq[3 * FT_TJ + c], zu1[mt],
+                                           cq[4 * FT_TJ + c], Y3, gain_c, num, det);
+                            if (!(det > 1e-12)) { gill = INFINITY; continue; }   // numerically singular
+                            const double gq = num / det, tq = c0 / det;
+                            if (det < kIllDet) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
+                            if (gq > gb) {
+                                flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
+                                gb = gq; tb = tq;
+                                bidx = (i0 + wrow + 8 * mt + g) * N + jt * FT_TJ + c;
+                            } else if (!(gb > gq + wide)) {
+                                flag = 1;
+                            }
+                        }
+            }
+            double lb = bidx >= 0 ? gb - tb : 0.0;               // certified lower bound
+            for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+            if (lb > thr) {
+                thr = lb;
+                if (lane == 0) atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
             }
         }
 
-        if (jt + 1 < ntJ) gather_store(jt + 1, buf ^ 1);
+        if (jt + 1 < ntJ) gather_store(buf ^ 1);
         __syncthreads();
     }
 
     // ---- CTA reduction: best gain, tie -> lower index; near-tie bookkeeping ----
-    double gt = trk.bidx >= 0 ? trk.bnum / trk.bdet : -1.0;
-    double tolt = trk.bidx >= 0 ? c0 / trk.bdet : 0.0;
+    const double gt = bidx >= 0 ? gb : -1.0;
+    const double tolt = bidx >= 0 ? tb : 0.0;
     double gm = gt;
-    int im = trk.bidx >= 0 ? trk.bidx : INT_MAX;
+    int im = bidx >= 0 ? bidx : INT_MAX;
     for (int o = 16; o > 0; o >>= 1) {
         double og = __shfl_xor_sync(0xffffffffu, gm, o);
         int oi = __shfl_xor_sync(0xffffffffu, im, o);
         if (og > gm || (og == gm && oi < im)) { gm = og; im = oi; }
     }
-    double *redg = red;
+    for (int o = 16; o > 0; o >>= 1) gill = fmax(gill, __shfl_xor_sync(0xffffffffu, gill, o));
+    double *redg = red, *redl = red + 16;
     int *redi = (int *)(red + 8);
-    if (lane == 0) { redg[warp] = gm; redi[warp] = im; }
+    if (lane == 0) { redg[warp] = gm; redi[warp] = im; redl[warp] = gill; }
     __syncthreads();
-    double G = redg[0];
+    double G = redg[0], Gill = redl[0];
     int I = redi[0];
-    for (int w = 1; w < FT_THREADS / 32; w++)
+    for (int w = 1; w < FT_THREADS / 32; w++) {
         if (redg[w] > G || (redg[w] == G && redi[w] < I)) { G = redg[w]; I = redi[w]; }
-    // tolerance of the winner
-    __shared__ double s_tolG;
-    __shared__ int s_flag;
-    if (tid == 0) s_flag = 0;
-    __syncthreads();
-    if (trk.bidx >= 0 && trk.bidx == I) s_tolG = tolt;
+        Gill = fmax(Gill, redl[w]);
+    }
+    if (bidx >= 0 && bidx == I) s_tolG = tolt;
     __syncthreads();
     const double tolG = I != INT_MAX ? s_tolG : 0.0;
-    if (trk.bidx >= 0) {
-        const bool winner = trk.bidx == I;
+    if (bidx >= 0) {
+        const bool winner = bidx == I;
         const bool close = gt + tolt >= G - tolG;
-        if ((winner && trk.flag) || (!winner && close) || (close && (trk.flag & 2))) atomicOr(&s_flag, 1);
+        if ((winner && flag) || (!winner && close)) atomicOr(&s_flag, 1);
     }
     __syncthreads();
     if (tid == 0) {
@@ -451,6 +495,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         a.cta_tol[o] = tolG;
         a.cta_idx[o] = I == INT_MAX ? -1 : I;
         a.cta_flag[o] = s_flag;
+        a.cta_ill[o] = Gill;
     }
 }
 
@@ -475,6 +520,7 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
     bool certain = I >= 0;
     for (int t = 0; t < a.ntI && certain; t++) {
         const int64_t o = v * a.ntI + t;
+        if (a.cta_ill[o] >= G - tolG) certain = false;
         if (t == best_t) { if (a.cta_flag[o]) certain = false; continue; }
         if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] >= G - tolG) certain = false;
     }
@@ -510,7 +556,7 @@ size_t fast_scratch_bytes(const DevPlan &p, int64_t V)
     s += al256(sizeof(double) * V * 2 * p.M * 2);
     s += al256(sizeof(double) * V * 2 * FT_NPAR * Npad);
     s += al256(sizeof(double) * V * 8);
-    s += 2 * al256(sizeof(double) * V * ntI);
+    s += 3 * al256(sizeof(double) * V * ntI);
     s += 2 * al256(sizeof(int) * V * ntI);
     return s;
 }
@@ -534,6 +580,7 @@ int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_
     a.voxp = (double *)q; q += al256(sizeof(double) * V * 8);
     a.cta_gain = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_tol = (double *)q; q += al256(sizeof(double) * V * a.ntI);
+    a.cta_ill = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_idx = (int *)q; q += al256(sizeof(int) * V * a.ntI);
     a.cta_flag = (int *)q;
     a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count;
