@@ -28,7 +28,10 @@ namespace mfb {
 
 #define FT_TI 128
 #define FT_TJ 32
-#define FT_THREADS 256
+#define FT_CONS 256         // consumer threads (8 DMMA warps)
+#define FT_PROD 128         // producer threads (4 gather warps)
+#define FT_THREADS (FT_CONS + FT_PROD)
+#define FT_NS 3             // stages of the i2-tile ring
 #define FT_S1 (FT_TI + 4)  // row strides: == 4 mod 16 doubles -> conflict-free fragment loads
 #define FT_S2 (FT_TJ + 4)
 #define FT_NPAR 7          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu
@@ -217,6 +220,37 @@ __device__ __forceinline__ bool pair_gain(double rho, double z1, double z2, doub
     return pos;
 }
 
+// ---- mbarrier helpers (producer / consumer ring) ----
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void consumer_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(FT_CONS) : "memory");
+}
+
+// Warp-specialised pair scan.  Warps 0..7 (consumers): DMMA correlation tile + closed-form
+// epilogue; warps 8..9 (producers): gather the next i2 tiles from the L2-resident lookup
+// table, rotate / project / normalise them and fill a 3-stage shared-memory ring.  full[] /
+// empty[] mbarriers are the only synchronisation inside the tile loop, so consumer warps
+// drift apart and one warp's scalar epilogue overlaps another warp's DMMA stream.
 template <int CSF>
 __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 {
@@ -224,15 +258,20 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const DevPlan &p = a.p;
     const int M = p.M, N = p.N, Mp = a.Mp;
     double *D1s = smem;                                   // [Mp][FT_S1]
-    double *D2s = D1s + (size_t)Mp * FT_S1;               // [2][Mp][FT_S2]
-    double *colq = D2s + (size_t)2 * Mp * FT_S2;          // [2][5][FT_TJ]  z, beta, kappa, gamma, zu
-    double *w2l = colq + 2 * 5 * FT_TJ;                   // [Mp] plan of fascicle 2 (fascicle 1 during build)
+    double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS][Mp][FT_S2]
+    double *colq = D2s + (size_t)FT_NS * Mp * FT_S2;      // [FT_NS][5][FT_TJ]  z, beta, kappa, gamma, zu
+    double *w1l = colq + FT_NS * 5 * FT_TJ;               // [Mp] plan of fascicle 1
+    double *w1h = w1l + Mp;
+    double *w2l = w1h + Mp;                               // [Mp] plan of fascicle 2
     double *w2h = w2l + Mp;
     double *cs = w2h + Mp;                                // [Mp] csf column
     double *red = cs + Mp;                                // [64]
-    int *r2l = (int *)(red + 64);
+    int *r1l = (int *)(red + 64);
+    int *r1h = r1l + Mp;
+    int *r2l = r1h + Mp;
     int *r2h = r2l + Mp;
     __shared__ unsigned long long s_thr;                  // CTA-wide lower bound on the winning gain
+    __shared__ unsigned long long s_full[FT_NS], s_empty[FT_NS];
     __shared__ double s_tolG;
     __shared__ int s_flag;
 
@@ -240,34 +279,88 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const int tI = blockIdx.x;
     const int i0 = tI * FT_TI;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t4 = lane & 3;
     const double *vp = a.voxp + v * 8;
     const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
-    const double y_sq = vp[0];
     const double gpre = fmax(vp[5], vp[6]);
-    // pairs with det >= kIllDet have a screening error below c0 / kIllDet; two such pairs
-    // further apart than `wide` are ordered with certainty
-    const double wide = 4.0 * c0 / kIllDet;
-    const double negc0 = -c0;
     const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
     const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
+    const int ntJ = a.Npad / FT_TJ;
 
-    auto load_plan = [&](int k) {
-        for (int m = tid; m < Mp; m += FT_THREADS) {
-            if (m < M) {
-                int64_t o = ((v * 2 + k) * M + m) * 2;
-                r2l[m] = a.ip_rows[o]; r2h[m] = a.ip_rows[o + 1];
-                w2l[m] = a.ip_w[o]; w2h[m] = a.ip_w[o + 1];
-                cs[m] = CSF ? p.sig_csf[m] : 0.0;
-            } else {
-                r2l[m] = 0; r2h[m] = 0; w2l[m] = 0.0; w2h[m] = 0.0; cs[m] = 0.0;
-            }
+    for (int m = tid; m < Mp; m += FT_THREADS) {
+        if (m < M) {
+            int64_t o = ((v * 2 + 0) * M + m) * 2, o2 = ((v * 2 + 1) * M + m) * 2;
+            r1l[m] = a.ip_rows[o]; r1h[m] = a.ip_rows[o + 1];
+            w1l[m] = a.ip_w[o]; w1h[m] = a.ip_w[o + 1];
+            r2l[m] = a.ip_rows[o2]; r2h[m] = a.ip_rows[o2 + 1];
+            w2l[m] = a.ip_w[o2]; w2h[m] = a.ip_w[o2 + 1];
+            cs[m] = CSF ? p.sig_csf[m] : 0.0;
+        } else {
+            r1l[m] = r1h[m] = r2l[m] = r2h[m] = 0;
+            w1l[m] = w1h[m] = w2l[m] = w2h[m] = 0.0; cs[m] = 0.0;
         }
-    };
-    // ---- resident i1 tile: rotate, project out the CSF column, normalise ----
-    load_plan(0);
-    if (tid == 0) { s_thr = (unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0)); s_flag = 0; }
+    }
+    if (tid == 0) {
+        s_thr = (unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0));
+        s_flag = 0;
+        for (int st = 0; st < FT_NS; st++) { mbar_init(&s_full[st], FT_PROD); mbar_init(&s_empty[st], FT_CONS); }
+    }
     __syncthreads();
+
+    if (tid >= FT_CONS) {
+        // =========================== producers ===========================
+        const int pt = tid - FT_CONS;
+        const int jj = pt & (FT_TJ - 1);
+        const int mrow0 = pt / FT_TJ;                     // 0..FT_PROD/32-1
+        constexpr int RS = FT_PROD / FT_TJ;               // rows per pass
+        constexpr int UB = 14;                            // (lo, hi) pairs in flight per thread
+        for (int jt = 0; jt < ntJ; jt++) {
+            const int st = jt % FT_NS;
+            if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
+            const int j = jt * FT_TJ + jj;
+            const bool ok = j < N;
+            const double csc = ok ? __ldg(cp2 + j) : 0.0;
+            const double cal = (CSF && ok) ? __ldg(cp2 + (size_t)a.Npad + j) : 0.0;
+            const double *Tc = p.table + (ok ? j : 0);
+            double *dst = D2s + (size_t)st * Mp * FT_S2 + jj;
+            for (int mb = mrow0; mb < Mp; mb += RS * UB) {
+                double lo[UB], hi[UB];
+#pragma unroll
+                for (int q = 0; q < UB; q++) {
+                    const int m = min(mb + RS * q, Mp - 1);   // rows >= M carry zero weights
+                    lo[q] = __ldg(Tc + (size_t)r2l[m] * N);
+                    hi[q] = __ldg(Tc + (size_t)r2h[m] * N);
+                }
+                // three passes of independent FP64 ops (the FP64 pipe is shared with the
+                // consumers' DMMA stream: dependent chains would serialise on its latency)
+#pragma unroll
+                for (int q = 0; q < UB; q++) lo[q] *= w2l[min(mb + RS * q, Mp - 1)];
+#pragma unroll
+                for (int q = 0; q < UB; q++) {
+                    const int m = min(mb + RS * q, Mp - 1);
+                    hi[q] = fma(w2h[m], hi[q], lo[q]);
+                    if (CSF) hi[q] = fma(-cal, cs[m], hi[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < UB; q++) hi[q] *= csc;
+#pragma unroll
+                for (int q = 0; q < UB; q++) {
+                    const int m = mb + RS * q;
+                    if (m < Mp) dst[(size_t)m * FT_S2] = hi[q];
+                }
+            }
+            for (int e = pt; e < 5 * FT_TJ; e += FT_PROD)
+                colq[(st * 5 + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
+                    __ldg(cp2 + (size_t)(e / FT_TJ + 2) * a.Npad + jt * FT_TJ + (e % FT_TJ));
+            mbar_arrive(&s_full[st]);
+        }
+        return;
+    }
+
+    // =============================== consumers ===============================
+    const int g = lane >> 2, t4 = lane & 3;
+    const double wide = 4.0 * c0 / kIllDet;
+    const double negc0 = -c0;
+    // ---- resident i1 tile: rotate, project out the CSF column, normalise ----
     {
         const int ii = tid & (FT_TI - 1);
         const int i = i0 + ii;
@@ -275,7 +368,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         const double sc = ok ? cp1[i] : 0.0;
         const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
         const double *Tc = p.table + (ok ? i : 0);
-        constexpr int RS = FT_THREADS / FT_TI;            // rows per pass (2)
+        constexpr int RS = FT_CONS / FT_TI;               // rows per pass (2)
         constexpr int UB = 9;                              // loads in flight per thread: 2*UB
         for (int mb = tid / FT_TI; mb < Mp; mb += RS * UB) {
             double lo[UB], hi[UB];
@@ -284,24 +377,22 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 const int m = mb + RS * q;
                 lo[q] = 0.0; hi[q] = 0.0;
                 if (ok && m < M) {
-                    lo[q] = __ldg(Tc + (size_t)r2l[m] * N);
-                    hi[q] = __ldg(Tc + (size_t)r2h[m] * N);
+                    lo[q] = __ldg(Tc + (size_t)r1l[m] * N);
+                    hi[q] = __ldg(Tc + (size_t)r1h[m] * N);
                 }
             }
 #pragma unroll
             for (int q = 0; q < UB; q++) {
                 const int m = mb + RS * q;
                 if (m < Mp) {
-                    double d = fma(w2h[m], hi[q], w2l[m] * lo[q]);
+                    double d = fma(w1h[m], hi[q], w1l[m] * lo[q]);
                     if (CSF) d = fma(-al, cs[m], d);
                     D1s[(size_t)m * FT_S1 + ii] = d * sc;
                 }
             }
         }
     }
-    __syncthreads();
-    load_plan(1);
-    __syncthreads();
+    consumer_sync();
 
     // ---- per-thread row constants (rows g and g+8 of the warp's 16-row slab) ----
     const int wrow = warp * 16;
@@ -321,52 +412,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     double gb = -1.0, tb = 0.0, thr = fmax(gpre - c0, 0.0), gill = -1.0;
     int bidx = -1, flag = 0;
 
-    // ---- i2 tile gather: thread -> column jj = tid % 32, rows m = tid/32 + 8*q ----
-    const int jj = tid & (FT_TJ - 1);
-    const int mrow0 = tid / FT_TJ;             // 0..7
-    constexpr int NQ = 14;                     // 8*14 = 112 >= Mp (Mp <= 112 checked on host)
-    double plo[NQ], phi[NQ];
-    double csc = 0.0, cal = 0.0, cpar = 0.0;
-    const int ntJ = a.Npad / FT_TJ;
-
-    auto gather_issue = [&](int jt) {
-        const int j = jt * FT_TJ + jj;
-        const bool ok = j < N;
-        csc = ok ? __ldg(cp2 + j) : 0.0;
-        cal = (CSF && ok) ? __ldg(cp2 + (size_t)a.Npad + j) : 0.0;
-        if (tid < 5 * FT_TJ)  // column parameter (q = tid / 32) of column tid % 32
-            cpar = __ldg(cp2 + (size_t)(tid / FT_TJ + 2) * a.Npad + jt * FT_TJ + jj);
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const int m = mrow0 + 8 * q;
-            plo[q] = 0.0; phi[q] = 0.0;
-            if (ok && m < M) {
-                plo[q] = __ldg(p.table + (size_t)r2l[m] * N + j);
-                phi[q] = __ldg(p.table + (size_t)r2h[m] * N + j);
-            }
-        }
-    };
-    auto gather_store = [&](int buf) {
-        double *dst = D2s + (size_t)buf * Mp * FT_S2;
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const int m = mrow0 + 8 * q;
-            if (m < Mp) {
-                double d = fma(w2h[m], phi[q], w2l[m] * plo[q]);
-                if (CSF) d = fma(-cal, cs[m], d);
-                dst[(size_t)m * FT_S2 + jj] = d * csc;
-            }
-        }
-        if (tid < 5 * FT_TJ) colq[(buf * 5 + tid / FT_TJ) * FT_TJ + jj] = cpar;
-    };
-
-    gather_issue(0);
-    gather_store(0);
-    __syncthreads();
-
     for (int jt = 0; jt < ntJ; jt++) {
-        const int buf = jt & 1;
-        if (jt + 1 < ntJ) gather_issue(jt + 1);
+        const int st = jt % FT_NS;
+        mbar_wait(&s_full[st], (unsigned)(jt / FT_NS) & 1u);
         thr = fmax(thr, __longlong_as_double((long long)s_thr));
 
         // ---- correlation tile: 16 x 32 per warp, DMMA m8n8k4 over k ----
@@ -376,7 +424,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
         const double *A_ = D1s + (size_t)t4 * FT_S1 + wrow + g;
-        const double *B_ = D2s + (size_t)buf * Mp * FT_S2 + (size_t)t4 * FT_S2 + g;
+        const double *B_ = D2s + (size_t)st * Mp * FT_S2 + (size_t)t4 * FT_S2 + g;
 #pragma unroll 3
         for (int ks = 0; ks < Mp / 4; ks++) {
             double af[2], bf[4];
@@ -395,30 +443,73 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 
         // ---- closed-form NNLS screening, branch-free over the thread's 16 pairs ----
         // (num + c0)/det >= thr  <=>  fma(-thr, det, num) >= -c0
-        const double *cq = colq + buf * 5 * FT_TJ;
+        const double *cq = colq + st * 5 * FT_TJ;
         unsigned hit = 0;
+        if (!CSF) {
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            const int c = 8 * nt + 2 * t4;
-            const double2 z2v = *reinterpret_cast<const double2 *>(cq + c);
-            double2 b2v = z2v, k2v = z2v, g2v = z2v, zu2v = z2v;
-            if (CSF) {
-                b2v = *reinterpret_cast<const double2 *>(cq + FT_TJ + c);
-                k2v = *reinterpret_cast<const double2 *>(cq + 2 * FT_TJ + c);
-                g2v = *reinterpret_cast<const double2 *>(cq + 3 * FT_TJ + c);
-                zu2v = *reinterpret_cast<const double2 *>(cq + 4 * FT_TJ + c);
+            for (int nt = 0; nt < 4; nt++) {
+                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x;
+                        const double w1 = fma(-rho, z2, z1[mt]);
+                        const double w2 = fma(-rho, z1[mt], z2);
+                        const double det = fma(-rho, rho, 1.0);
+                        const double num = fma(z1[mt], w1, z2 * w2);
+                        const bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
+                        if (pos && fma(-thr, det, num) >= negc0) hit |= 1u << (nt * 4 + e * 2 + mt);
+                    }
             }
+        } else {
+            // pass 1: three-compartment closed form (fascicle pair projected off the CSF column)
+            unsigned fb = 0;   // pairs whose 3-variable solution has a non-positive weight
 #pragma unroll
-            for (int e = 0; e < 2; e++)
+            for (int nt = 0; nt < 4; nt++) {
+                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+                const double2 b2v = *reinterpret_cast<const double2 *>(cq + FT_TJ + 8 * nt + 2 * t4);
 #pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
-                    double num, det;
-                    const bool pos = pair_gain<CSF>(acc[mt][nt][e], z1[mt], e ? z2v.y : z2v.x, b1[mt],
-                                                    e ? b2v.y : b2v.x, k1[mt], e ? k2v.y : k2v.x, g1[mt],
-                                                    e ? g2v.y : g2v.x, zu1[mt], e ? zu2v.y : zu2v.x, Y3,
-                                                    gain_c, num, det);
-                    if (pos && fma(-thr, det, num) >= negc0) hit |= 1u << (nt * 4 + e * 2 + mt);
+                for (int e = 0; e < 2; e++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x, b2 = e ? b2v.y : b2v.x;
+                        const double w1 = fma(-rho, z2, z1[mt]);
+                        const double w2 = fma(-rho, z1[mt], z2);
+                        const double det = fma(-rho, rho, 1.0);
+                        const double w3 = fma(-b2, w2, fma(-b1[mt], w1, Y3 * det));
+                        const double num = fma(gain_c, det, fma(z1[mt], w1, z2 * w2));
+                        const bool pos = min(min(__double2hiint(w1), __double2hiint(w2)), __double2hiint(w3)) > 0;
+                        const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
+                        if (!pos) fb |= bit;
+                        else if (fma(-thr, det, num) >= negc0) hit |= bit;
+                    }
+            }
+            // pass 2: best 2-column sub-problem of the pairs that fell back (only the fascicle
+            // pair depends on (i1, i2); the atom + CSF ones are pair-independent, in gpre)
+            if (__any_sync(0xffffffffu, fb != 0)) {
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    const double2 k2v = *reinterpret_cast<const double2 *>(cq + 2 * FT_TJ + 8 * nt + 2 * t4);
+                    const double2 g2v = *reinterpret_cast<const double2 *>(cq + 3 * FT_TJ + 8 * nt + 2 * t4);
+                    const double2 zu2v = *reinterpret_cast<const double2 *>(cq + 4 * FT_TJ + 8 * nt + 2 * t4);
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) {
+                            const double rho = acc[mt][nt][e];
+                            const double zu2 = e ? zu2v.y : zu2v.x;
+                            const double r = fma(rho * k1[mt], e ? k2v.y : k2v.x, g1[mt] * (e ? g2v.y : g2v.x));
+                            const double v1 = fma(-r, zu2, zu1[mt]);
+                            const double v2 = fma(-r, zu1[mt], zu2);
+                            const double det = fma(-r, r, 1.0);
+                            const double num = fma(zu1[mt], v1, zu2 * v2);
+                            const bool pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
+                            const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
+                            if ((fb & bit) && pos && fma(-thr, det, num) >= negc0) hit |= bit;
+                        }
                 }
+            }
         }
         // ---- rare: some lane of the warp has a competitive pair ----
         if (__any_sync(0xffffffffu, hit != 0)) {
@@ -454,12 +545,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 if (lane == 0) atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
             }
         }
-
-        if (jt + 1 < ntJ) gather_store(buf ^ 1);
-        __syncthreads();
+        mbar_arrive(&s_empty[st]);
     }
 
-    // ---- CTA reduction: best gain, tie -> lower index; near-tie bookkeeping ----
+    // ---- reduction over the consumer threads: best gain, tie -> lower index ----
     const double gt = bidx >= 0 ? gb : -1.0;
     const double tolt = bidx >= 0 ? tb : 0.0;
     double gm = gt;
@@ -473,22 +562,22 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     double *redg = red, *redl = red + 16;
     int *redi = (int *)(red + 8);
     if (lane == 0) { redg[warp] = gm; redi[warp] = im; redl[warp] = gill; }
-    __syncthreads();
+    consumer_sync();
     double G = redg[0], Gill = redl[0];
     int I = redi[0];
-    for (int w = 1; w < FT_THREADS / 32; w++) {
+    for (int w = 1; w < FT_CONS / 32; w++) {
         if (redg[w] > G || (redg[w] == G && redi[w] < I)) { G = redg[w]; I = redi[w]; }
         Gill = fmax(Gill, redl[w]);
     }
     if (bidx >= 0 && bidx == I) s_tolG = tolt;
-    __syncthreads();
+    consumer_sync();
     const double tolG = I != INT_MAX ? s_tolG : 0.0;
     if (bidx >= 0) {
         const bool winner = bidx == I;
         const bool close = gt + tolt >= G - tolG;
         if ((winner && flag) || (!winner && close)) atomicOr(&s_flag, 1);
     }
-    __syncthreads();
+    consumer_sync();
     if (tid == 0) {
         const int64_t o = v * a.ntI + tI;
         a.cta_gain[o] = G;
@@ -588,8 +677,8 @@ int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_
     const size_t smem_prep = sizeof(double) * (4 * p.M + 32) + sizeof(int) * 2 * p.M;
     MFB_LAUNCH(k_fast_prep, dim3((unsigned)V, 2), 256, smem_prep, st, a);
 
-    const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)2 * a.Mp * FT_S2 + 2 * 5 * FT_TJ +
-                                          3 * a.Mp + 64) + sizeof(int) * 2 * a.Mp;
+    const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_NS * 5 * FT_TJ +
+                                          5 * a.Mp + 64) + sizeof(int) * 4 * a.Mp;
     if (smem + 64 > 227 * 1024) {
         set_error("fast tier: tile does not fit in shared memory");
         return MFB_EUNSUPPORTED;

@@ -279,3 +279,19 @@ def test_fast_tier_degenerate_voxels():
     exact = ph.gpu_rows(flags=1)
     assert np.array_equal(fast, exact)
     compare_rows(fast, oracle_rows(ph), ph, exact_bits=True)
+
+
+def test_fast_tier_large_validation():
+    """20k voxels at the benchmark shape (N = 1000, M = 105): the screening tier and the
+    reference-order tier must produce bit-identical rows; only a small fraction of voxels
+    may need the exact tier."""
+    from microstructure_fingerprinting_b200 import mf_utils as mfu
+    ph = make_phantom(n_atoms=1000, n_vox=20000, seed=2024, frac_k=(0.0, 0.0, 1.0), csf_frac=0.3)
+    msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, None)
+    fast = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, None, 2, True, False, flags=0)
+    st = plan.stats()
+    exact = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, None, 2, True, False, flags=1)
+    plan.close()
+    assert np.array_equal(fast, exact)
+    assert st[0] + st[1] == 20000 and st[1] < 0.02 * 20000, st
