@@ -94,7 +94,7 @@ def run_reference(args):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
-    sample = max(cores, int(args.cpu_voxels) if args.cpu_voxels else 2 * cores)
+    sample = max(cores, int(args.cpu_voxels) if args.cpu_voxels else 8 * cores)
     ph = make_workload(sample, args.atoms, seed=1234)
     tab = orc.init_table(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
     plan = orc.plan_scheme(tab, ph.sch)
@@ -117,7 +117,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": workload_config(args, sample),
+            "config": workload_config(args, args.voxels),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d voxels per step (same workload generator, seed 1234), "
                                        "C oracle port of the reference's _fit_voxel, one thread "

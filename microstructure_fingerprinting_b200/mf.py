@@ -18,6 +18,13 @@ from . import mf_utils as mfu
 from . import nifti
 
 
+def shard_bounds(n_items, n_shards):
+    """Contiguous, balanced split of range(n_items) into n_shards spans: returns the
+    n_shards + 1 boundaries.  Used for the per-GPU ROI shards (no data-path collective:
+    voxels are independent given the replicated plan)."""
+    return np.linspace(0, n_items, n_shards + 1).astype(np.int64)
+
+
 def _as_array(x):
     """Array or path to a NIfTI file -> (ndarray, affine or None)."""
     if isinstance(x, str):
@@ -277,7 +284,7 @@ class MFModel():
         st_est = time.time()
         if VRB >= 2:
             print("Starting estimation in %d voxel(s) on %d GPU(s)." % (ROI_size, len(devices)))
-        bounds = np.linspace(0, ROI_size, len(devices) + 1).astype(np.int64)
+        bounds = shard_bounds(ROI_size, len(devices))
         errors = []
 
         def work(rank, dev):

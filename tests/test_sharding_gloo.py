@@ -1,0 +1,62 @@
+"""N > 1 host logic on CPU: two gloo ranks shard a ROI the way bench.py / MFModel.fit do
+(contiguous spans, no data-path collective), gather the rows on rank 0 and max-reduce the
+step time."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from microstructure_fingerprinting_b200.mf import shard_bounds
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, V, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = shard_bounds(V, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    # stand-in for the per-rank fit: row i of the result is a function of the voxel index
+    rows = torch.arange(lo, hi, dtype=torch.float64)[:, None] * torch.tensor([[1.0, 2.0, 3.0]])
+    parts = [None] * world
+    dist.all_gather_object(parts, (lo, rows.numpy()))   # uneven shards: the final host-side gather
+    gathered = [torch.from_numpy(r) for _, r in sorted(parts, key=lambda t: t[0])]
+    t = torch.tensor([10.0 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)   # bench.py: max over ranks of the step time
+    dist.barrier()
+    if rank == 0:
+        out_q.put((torch.cat(gathered).numpy(), float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    V, world = 1001, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, V, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rows, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert rows.shape == (V, 3)
+    assert np.array_equal(rows[:, 0], np.arange(V, dtype=float))
+    assert tmax == 11.0
+
+
+def test_shard_bounds_cover_everything():
+    for V in (1, 2, 7, 1000, 12345):
+        for w in (1, 2, 3, 8):
+            b = shard_bounds(V, w)
+            assert b[0] == 0 and b[-1] == V and np.all(np.diff(b) >= 0)
+            assert np.max(np.diff(b)) - np.min(np.diff(b)) <= 1
