@@ -21,6 +21,7 @@
 // separated from the runner-up (or from a pair-independent branch) by more than the
 // screening error bound is handed to the exact tier.
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -46,6 +47,7 @@ struct FastArgs {
     int Mp;            // M padded to a multiple of 4
     int Npad;          // N padded to a multiple of FT_TJ
     int ntI;           // i1 tiles per voxel
+    int debug;            // timing experiments only (MFB_FAST_DEBUG): 1 skip epilogue, 2 skip gathers
     const int32_t *vox_list;
     const double *peaks;
     int peaks_ld;
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         for (int jt = 0; jt < ntJ; jt++) {
             const int st = jt % FT_NS;
             if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
+            if ((a.debug & 2) && jt >= FT_NS) { mbar_arrive(&s_full[st]); continue; }
             const int j = jt * FT_TJ + jj;
             const bool ok = j < N;
             const double csc = ok ? __ldg(cp2 + j) : 0.0;
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
         const double *Tc = p.table + (ok ? i : 0);
         constexpr int RS = FT_CONS / FT_TI;               // rows per pass (2)
-        constexpr int UB = 9;                              // loads in flight per thread: 2*UB
+        constexpr int UB = 18;                             // loads in flight per thread: 2*UB
         for (int mb = tid / FT_TI; mb < Mp; mb += RS * UB) {
             double lo[UB], hi[UB];
 #pragma unroll
@@ -408,6 +411,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
     }
 
+    const int mtv = max(0, min(2, (N - (i0 + wrow) + 7) >> 3));   // valid 8-row blocks of this warp
+
     // thread-local best (central gain gb, tolerance tb) and the shared screening threshold
     double gb = -1.0, tb = 0.0, thr = fmax(gpre - c0, 0.0), gill = -1.0;
     int bidx = -1, flag = 0;
@@ -425,27 +430,56 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
         const double *A_ = D1s + (size_t)t4 * FT_S1 + wrow + g;
         const double *B_ = D2s + (size_t)st * Mp * FT_S2 + (size_t)t4 * FT_S2 + g;
+        // 8-atom blocks of this tile that hold real atoms (warp-uniform): the last i1 / i2
+        // tiles of a dictionary whose size is not a multiple of the tile are partly empty
+        const int ntv = min(4, (N - jt * FT_TJ + 7) >> 3);
+        if (ntv == 4 && mtv == 2) {
 #pragma unroll 3
-        for (int ks = 0; ks < Mp / 4; ks++) {
-            double af[2], bf[4];
+            for (int ks = 0; ks < Mp / 4; ks++) {
+                double af[2], bf[4];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
+                for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
+                for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++)
+                for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++)
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                                 : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
-                                 : "d"(af[mt]), "d"(bf[nt]));
+                    for (int nt = 0; nt < 4; nt++)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                     : "d"(af[mt]), "d"(bf[nt]));
+            }
+        } else {
+#pragma unroll 1
+            for (int ks = 0; ks < Mp / 4; ks++) {
+                double af[2], bf[4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+                        if (mt < mtv && nt < ntv)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                         : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                         : "d"(af[mt]), "d"(bf[nt]));
+            }
         }
 
         // ---- closed-form NNLS screening, branch-free over the thread's 16 pairs ----
         // (num + c0)/det >= thr  <=>  fma(-thr, det, num) >= -c0
         const double *cq = colq + st * 5 * FT_TJ;
         unsigned hit = 0;
-        if (!CSF) {
+        if (a.debug & 1) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) sacc += acc[mt][nt][0] + acc[mt][nt][1];
+            if (sacc == 1.2345e300) hit = 1;
+        } else if (!CSF) {
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
                 const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
@@ -514,29 +548,36 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         // ---- rare: some lane of the warp has a competitive pair ----
         if (__any_sync(0xffffffffu, hit != 0)) {
             if (hit) {
+                // off the hot path: one instantiation of the closed form, accumulators read
+                // back through a (local-memory) copy indexed at run time
+                double rcopy[16];
 #pragma unroll
                 for (int nt = 0; nt < 4; nt++)
 #pragma unroll
                     for (int e = 0; e < 2; e++)
 #pragma unroll
-                        for (int mt = 0; mt < 2; mt++) {
-                            if (!(hit & (1u << (nt * 4 + e * 2 + mt)))) continue;
-                            const int c = 8 * nt + 2 * t4 + e;
-                            double num, det;
-                            pair_gain<CSF>(acc[mt][nt][e], z1[mt], cq[c], b1[mt], cq[FT_TJ + c], k1[mt],
-                                           cq[2 * FT_TJ + c], g1[mt], cq[3 * FT_TJ + c], zu1[mt],
-                                           cq[4 * FT_TJ + c], Y3, gain_c, num, det);
-                            if (!(det > 1e-12)) { gill = INFINITY; continue; }   // numerically singular
-                            const double gq = num / det, tq = c0 / det;
-                            if (det < kIllDet) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
-                            if (gq > gb) {
-                                flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
-                                gb = gq; tb = tq;
-                                bidx = (i0 + wrow + 8 * mt + g) * N + jt * FT_TJ + c;
-                            } else if (!(gb > gq + wide)) {
-                                flag = 1;
-                            }
-                        }
+                        for (int mt = 0; mt < 2; mt++) rcopy[nt * 4 + e * 2 + mt] = acc[mt][nt][e];
+#pragma unroll 1
+                for (int q = 0; q < 16; q++) {
+                    if (!(hit & (1u << q))) continue;
+                    const int nt = q >> 2, e = (q >> 1) & 1, mt = q & 1;
+                    const int c = 8 * nt + 2 * t4 + e;
+                    double num, det;
+                    pair_gain<CSF>(rcopy[q], mt ? z1[1] : z1[0], cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
+                                   mt ? k1[1] : k1[0], cq[2 * FT_TJ + c], mt ? g1[1] : g1[0],
+                                   cq[3 * FT_TJ + c], mt ? zu1[1] : zu1[0], cq[4 * FT_TJ + c], Y3, gain_c,
+                                   num, det);
+                    if (!(det > 1e-12)) { gill = INFINITY; continue; }   // numerically singular
+                    const double gq = num / det, tq = c0 / det;
+                    if (det < kIllDet) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
+                    if (gq > gb) {
+                        flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
+                        gb = gq; tb = tq;
+                        bidx = (i0 + wrow + 8 * mt + g) * N + jt * FT_TJ + c;
+                    } else if (!(gb > gq + wide)) {
+                        flag = 1;
+                    }
+                }
             }
             double lb = bidx >= 0 ? gb - tb : 0.0;               // certified lower bound
             for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
@@ -661,6 +702,10 @@ int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_
     a.Mp = (p.M + 3) & ~3;
     a.Npad = (p.N + FT_TJ - 1) / FT_TJ * FT_TJ;
     a.ntI = (p.N + FT_TI - 1) / FT_TI;
+    {
+        const char *d = getenv("MFB_FAST_DEBUG");
+        a.debug = d ? atoi(d) : 0;
+    }
     a.vox_list = vox_list; a.peaks = peaks; a.peaks_ld = peaks_ld; a.y = y;
     char *q = (char *)scratch;
     a.ip_rows = (int *)q; q += al256(sizeof(int) * V * 2 * p.M * 2);
