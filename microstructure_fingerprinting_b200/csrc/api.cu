@@ -349,6 +349,12 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             MFB_CUDA_TRY(cudaStreamSynchronize(st));
             pl->stats[0] += (double)(cnt - n_redo);
             if (n_redo > 0) MFB_TRY(run_exact(redo_list, n_redo, false));
+        } else if (!(flags & 1) && single_fascicle_supported(dp, Kt, ct, et) && list) {
+            // one fascicle: fused rotation + closed forms in the reference's arithmetic
+            MFB_TRY(launch_single_fascicle(dp, cnt, list, peaks, pld, y, ct, et, pl->tuple.as<long long>(), st));
+            MFB_TRY(launch_gather_from_table(dp, cnt, Kt, ct, et, peaks, pld, pl->tuple.as<long long>(),
+                                             list, pl->asmall.as<double>(), pl->idx5.as<int32_t>(), st));
+            pl->stats[5] += (double)cnt;
         } else {
             MFB_TRY(run_exact(list, cnt, timed));
         }

@@ -118,6 +118,12 @@ int launch_classify(int64_t V, const int32_t *K, const uint8_t *csf, const uint8
                     int maxfasc, uint8_t *type, uint8_t *nbv, int32_t *lists /*12*V*/,
                     int32_t *counts /*12*/, cudaStream_t st);
 
+// One-fascicle voxels: rotation + Gram terms + closed forms fused (reference arithmetic).
+bool single_fascicle_supported(const DevPlan &p, int K, int csf, int ear);
+int launch_single_fascicle(const DevPlan &p, int64_t nvox, const int32_t *vox_list,
+                           const double *peaks, int peaks_ld, const double *y, int csf, int ear,
+                           long long *tuple, cudaStream_t st);
+
 // ------------------------- fast tier (fast.cu) -------------------------------------
 // DMMA screening for 2-fascicle voxels ([N,N] and [N,N,1]); voxels whose winner is not
 // certain are appended to redo_list (exact tier).

@@ -10,6 +10,7 @@
 //   scipy interp1d._call_linear two-weight lerp).
 // Loop-order tie-breaks ("first strict minimum") are reproduced by reducing on the pair
 // (residual, loop index).
+#include <algorithm>
 #include <climits>
 
 #include "common.cuh"
@@ -631,6 +632,170 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
     }
     MFB_LAUNCH(k_reduce_tiles, (unsigned)((V + 3) / 4), 128, 0, st, V, a.ntiles, a.tile_res,
                a.tile_idx, vox_list, tuple_out);
+    return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// one-fascicle voxels ([N], [N,1], [N,E], [N,1,E]): rotation, Gram terms and closed forms
+// fused in one kernel, nothing materialised.  One CTA per voxel, one thread per atom; the
+// atom's rotated column is produced on the fly from the lookup table (two coalesced row
+// reads per measurement) and every sum runs in the reference's order.
+// ---------------------------------------------------------------------------------
+#define SF_MAXISO 12
+
+struct SfArgs {
+    DevPlan p;
+    const int32_t *vox_list;
+    const double *peaks;
+    int peaks_ld;
+    const double *y;
+    int csf, ear;
+    long long *tuple;
+};
+
+__global__ void __launch_bounds__(256) k_single_fascicle(SfArgs a)
+{
+    extern __shared__ double sm[];
+    const DevPlan &p = a.p;
+    const int M = p.M, N = p.N;
+    const int nIso = a.csf + a.ear * p.E;
+    double *wl = sm, *wh = sm + M, *wl2 = sm + 2 * M, *wh2 = sm + 3 * M, *ys = sm + 4 * M;
+    double *iso = ys + M;                       // [nIso][M] iso columns (csf first)
+    double *isoSq = iso + (size_t)nIso * M;     // [nIso]
+    double *isoY = isoSq + SF_MAXISO;           // [nIso]
+    double *isoX = isoY + SF_MAXISO;            // [nIso] csf . ear[e]
+    int *rl = (int *)(isoX + SF_MAXISO), *rh = rl + M, *rl2 = rh + M, *rh2 = rl2 + M;
+    __shared__ Best red[32];
+    __shared__ double s_ysq;
+    const int64_t v = blockIdx.x;
+    const int64_t row = a.vox_list ? a.vox_list[v] : v;
+    const double ux = a.peaks[row * a.peaks_ld], uy = a.peaks[row * a.peaks_ld + 1],
+                 uz = a.peaks[row * a.peaks_ld + 2];
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        double x = dir_dot(p, m, ux, uy, uz);
+        Lerp l1 = shell_lerp(p, p.shell_lo[m], x);
+        rl[m] = l1.rl; rh[m] = l1.rh; wl[m] = l1.wl; wh[m] = l1.wh;
+        if (p.shell_hi[m] != p.shell_lo[m]) {
+            Lerp l2 = shell_lerp(p, p.shell_hi[m], x);
+            rl2[m] = l2.rl; rh2[m] = l2.rh; wl2[m] = l2.wl; wh2[m] = l2.wh;
+        } else {
+            rl2[m] = -1;
+        }
+        ys[m] = a.y[row * M + m];
+        for (int e = 0; e < nIso; e++)
+            iso[(size_t)e * M + m] = (a.csf && e == 0) ? p.sig_csf[m] : p.sig_ear[(size_t)m * p.E + (e - a.csf)];
+    }
+    __syncthreads();
+    if (threadIdx.x < nIso) {  // statistics of the iso columns, reference order
+        const int e = threadIdx.x;
+        double sq = 0.0, dy = 0.0, cx = 0.0;
+        for (int k = 0; k < M; k++) {
+            double c = iso[(size_t)e * M + k];
+            sq = DA(sq, DM(c, c));
+            dy = DA(dy, DM(ys[k], c));
+            if (a.csf && e > 0) cx = DA(cx, DM(iso[k], c));   // A23 = csf . ear (mfu:528-531)
+        }
+        isoSq[e] = sq; isoY[e] = dy; isoX[e] = cx;
+    }
+    if (threadIdx.x == 32) {
+        double s = 0.0;
+        for (int k = 0; k < M; k++) s = DA(s, DM(ys[k], ys[k]));
+        s_ysq = s;
+    }
+    __syncthreads();
+    const double y_sq = s_ysq;
+    const int nb = 1 + a.csf + a.ear;
+
+    auto column = [&](int m, int i) -> double {
+        Lerp la, lb;
+        la.rl = rl[m]; la.rh = rh[m]; la.wl = wl[m]; la.wh = wh[m];
+        const bool between = rl2[m] >= 0;
+        double gwl = 0.0, gwh = 0.0;
+        lb = la;
+        if (between) { lb.rl = rl2[m]; lb.rh = rh2[m]; lb.wl = wl2[m]; lb.wh = wh2[m]; gwl = p.gw_lo[m]; gwh = p.gw_hi[m]; }
+        return rot_entry(p, la, lb, between, gwl, gwh, i);
+    };
+
+    Best b;
+    b.res = INFINITY; b.idx = LLONG_MAX;
+    for (int i1 = threadIdx.x; i1 < N; i1 += blockDim.x) {
+        double sq = 0.0, dy = 0.0, cr[SF_MAXISO];
+#pragma unroll
+        for (int e = 0; e < SF_MAXISO; e++) cr[e] = 0.0;
+        for (int k = 0; k < M; k++) {
+            const double d = column(k, i1);
+            sq = DA(sq, DM(d, d));
+            dy = DA(dy, DM(ys[k], d));
+#pragma unroll
+            for (int e = 0; e < SF_MAXISO; e++)
+                if (e < nIso) cr[e] = DA(cr[e], DM(d, iso[(size_t)e * M + k]));
+        }
+        if (nb == 1) {  // mfu:252-273
+            if (dy >= 0) {
+                double w = DD(dy, sq);
+                double res = DS(y_sq, DM(w, dy));
+                if (res < y_sq) best_take(b, res, i1);
+            }
+        } else if (nb == 2) {  // mfu:329-386, second block = the iso columns
+#pragma unroll
+            for (int e = 0; e < SF_MAXISO; e++)
+                if (e < nIso) {
+                    double w0, w1;
+                    double res = lsq2(y_sq, sq, cr[e], isoSq[e], dy, isoY[e], w0, w1);
+                    if (res < y_sq) best_take(b, res, (long long)i1 * nIso + e);
+                }
+        } else {  // [N, 1, E]: loop order i3 (EAR), i1, i2 = 0 (mfu:540-601)
+#pragma unroll
+            for (int e = 1; e < SF_MAXISO; e++)
+                if (e < nIso) {
+                    const int i3 = e - 1;
+                    double w0, w1, w2, res;
+                    if (cramer3(sq, cr[0], cr[e], isoSq[0], isoX[e], isoSq[e], dy, isoY[0], isoY[e], w0, w1, w2)) {
+                        res = 0.0;
+                        for (int k = 0; k < M; k++) {
+                            double dd = DS(DA(DA(DM(w0, column(k, i1)), DM(w1, iso[k])),
+                                              DM(w2, iso[(size_t)e * M + k])), ys[k]);
+                            res = DA(res, DM(dd, dd));
+                        }
+                    } else {
+                        res = fallback3(y_sq, sq, cr[0], cr[e], isoSq[0], isoX[e], isoSq[e], dy, isoY[0],
+                                        isoY[e], w0, w1, w2);
+                    }
+                    if (res < y_sq) best_take(b, res, (long long)i3 * N + i1);
+                }
+        }
+    }
+    b = best_block_reduce(b, red);
+    if (threadIdx.x == 0) a.tuple[row] = (b.idx == LLONG_MAX) ? kNoTuple : b.idx;
+}
+
+bool single_fascicle_supported(const DevPlan &p, int K, int csf, int ear)
+{
+    return K == 1 && csf + ear * p.E <= SF_MAXISO;
+}
+
+int launch_single_fascicle(const DevPlan &p, int64_t nvox, const int32_t *vox_list,
+                           const double *peaks, int peaks_ld, const double *y, int csf, int ear,
+                           long long *tuple, cudaStream_t st)
+{
+    if (nvox == 0) return MFB_OK;
+    SfArgs a;
+    a.p = p; a.vox_list = vox_list; a.peaks = peaks; a.peaks_ld = peaks_ld; a.y = y;
+    a.csf = csf; a.ear = ear; a.tuple = tuple;
+    const int nIso = csf + ear * p.E;
+    size_t smem = sizeof(double) * ((size_t)5 * p.M + (size_t)nIso * p.M + 3 * SF_MAXISO) + sizeof(int) * 4 * p.M;
+    if (smem > 200 * 1024) { set_error("single-fascicle kernel: protocol too long for shared memory"); return MFB_EUNSUPPORTED; }
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        MFB_CUDA_TRY(cudaFuncSetAttribute(k_single_fascicle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int64_t maxgrid = 1 << 20;
+    for (int64_t v0 = 0; v0 < nvox; v0 += maxgrid) {
+        SfArgs b = a;
+        b.vox_list = vox_list + v0;
+        MFB_LAUNCH(k_single_fascicle, (unsigned)std::min<int64_t>(maxgrid, nvox - v0), 256, smem, st, b);
+    }
     return MFB_OK;
 }
 
