@@ -201,10 +201,6 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
         if (sizes[b] <= 0) { set_error("mfb_solve_batch: sizes must be > 0"); return MFB_EINVAL; }
     BlockSpec bs = make_spec(nblocks, sizes);
     if (lda < bs.ntot) { set_error("mfb_solve_batch: lda < sum(sizes)"); return MFB_EINVAL; }
-    if (nblocks > 3) {
-        set_error("mfb_solve_batch: 4-5 blocks not implemented yet");
-        return MFB_EUNSUPPORTED;
-    }
     if (V == 0) return MFB_OK;
     MFB_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -286,11 +282,6 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             return MFB_EINVAL;
         }
         const BlockSpec bs = fit_spec(dp.N, dp.E, Kt, ct, et);
-        if (bs.nb > 3) {
-            set_error("mfb_fit: voxels with 4 or more compartments (2 fascicles + CSF + EAR) are "
-                      "not implemented yet");
-            return MFB_EUNSUPPORTED;
-        }
         const int32_t *list = pl->lists.as<int32_t>() + (int64_t)t * nv;
         const bool timed = (flags & 2) && bs.nb >= 2 && Kt == 2;
         auto next_events = [&]() -> cudaEvent_t * {

@@ -543,6 +543,180 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// 4 and 5 blocks (mfu:612-657 solve_exhaustive_posweights_4up).  The reference calls
+// scipy.optimize.nnls on every index tuple (itertools.product order) and keeps the first
+// strict minimum of rnorm^2.  Here the tiny NNLS is solved in closed form from the Gram
+// entries by enumerating the 2^nb - 1 supports (normal equations on the support, all
+// weights > 0, best gain): same optimum as Lawson-Hanson up to rounding, so
+// parity for these shapes is to rounding, not bitwise.
+// ---------------------------------------------------------------------------------
+__device__ double nnls_enum(int nb, const double *G /* 5x5 */, const double *Y, double *wbest)
+{
+    double best = 0.0;
+    for (int b = 0; b < kMaxBlocks; b++) wbest[b] = 0.0;
+    for (int mask = 1; mask < (1 << nb); mask++) {
+        int id[kMaxBlocks], n = 0;
+        for (int b = 0; b < nb; b++)
+            if (mask & (1 << b)) id[n++] = b;
+        // Cholesky of the support's Gram block
+        double L[kMaxBlocks][kMaxBlocks], z[kMaxBlocks], w[kMaxBlocks];
+        bool ok = true;
+        for (int i = 0; i < n && ok; i++) {
+            for (int j = 0; j <= i; j++) {
+                double sacc = G[id[i] * kMaxBlocks + id[j]];
+                for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+                if (i == j) {
+                    if (!(sacc > 0.0)) { ok = false; break; }
+                    L[i][i] = sqrt(sacc);
+                } else {
+                    L[i][j] = sacc / L[j][j];
+                }
+            }
+        }
+        if (!ok) continue;
+        for (int i = 0; i < n; i++) {
+            double sacc = Y[id[i]];
+            for (int k = 0; k < i; k++) sacc -= L[i][k] * z[k];
+            z[i] = sacc / L[i][i];
+        }
+        for (int i = n - 1; i >= 0; i--) {
+            double sacc = z[i];
+            for (int k = i + 1; k < n; k++) sacc -= L[k][i] * w[k];
+            w[i] = sacc / L[i][i];
+        }
+        bool pos = true;
+        double gain = 0.0;
+        for (int i = 0; i < n; i++) { pos = pos && (w[i] > 0.0); gain += Y[id[i]] * w[i]; }
+        if (pos && gain > best) {
+            best = gain;
+            for (int b = 0; b < kMaxBlocks; b++) wbest[b] = 0.0;
+            for (int i = 0; i < n; i++) wbest[id[i]] = w[i];
+        }
+    }
+    return best;
+}
+
+struct MultiArgs {
+    ExactArgs e;
+    int S;                 // total columns of blocks 3..nb
+    long long T;           // number of trailing tuples = prod(size[2:])
+    const double *crossS;  // [V][N1+N2][S]   (a_i . a_s) for i in blocks 1-2, s in blocks 3..
+    const double *crossSS; // [V][S][S]
+};
+
+// grid (ceil((N1+N2+S)*S/128), V): cross terms with the trailing blocks, reference-style sums
+__global__ void __launch_bounds__(128) k_cross_small(MultiArgs ma, double *crossS, double *crossSS)
+{
+    const ExactArgs &a = ma.e;
+    const int64_t v = blockIdx.y;
+    const int N12 = a.bs.size[0] + a.bs.size[1], S = ma.S;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)(N12 + S) * S) return;
+    const int i = (int)(t / S), sidx = (int)(t % S);
+    const double *A = a.A + v * a.strideA;
+    const int cs = a.bs.start[2] + sidx;
+    const int c = i < N12 ? i : a.bs.start[2] + (i - N12);
+    double acc = 0.0;
+    for (int k = 0; k < a.M; k++) acc = DA(acc, DM(A[(size_t)k * a.lda + c], A[(size_t)k * a.lda + cs]));
+    if (i < N12) crossS[(v * N12 + i) * S + sidx] = acc;
+    else crossSS[(v * S + (i - N12)) * S + sidx] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_pairs_multi(MultiArgs ma)
+{
+    const ExactArgs &a = ma.e;
+    __shared__ double s1[EX_KC][EX_T];
+    __shared__ double s2[EX_KC][EX_T];
+    __shared__ Best red[32];
+    const int64_t v = blockIdx.z;
+    const int N1 = a.bs.size[0], N2 = a.bs.size[1], nb = a.bs.nb, S = ma.S;
+    const int tI = blockIdx.y * EX_T, tJ = blockIdx.x * EX_T;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double *A = a.A + v * a.strideA;
+    const double *B1 = A + a.bs.start[0], *B2 = A + a.bs.start[1];
+    const int M = a.M;
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
+    for (int k0 = 0; k0 < M; k0 += EX_KC) {
+        const int kc = min(EX_KC, M - k0);
+        for (int e = threadIdx.x; e < EX_KC * EX_T; e += 256) {
+            int kk = e / EX_T, cc = e % EX_T;
+            double x1 = 0.0, x2 = 0.0;
+            if (kk < kc) {
+                if (tI + cc < N1) x1 = B1[(size_t)(k0 + kk) * a.lda + tI + cc];
+                if (tJ + cc < N2) x2 = B2[(size_t)(k0 + kk) * a.lda + tJ + cc];
+            }
+            s1[kk][cc] = x1;
+            s2[kk][cc] = x2;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < kc; kk++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) av[r] = s1[kk][ty + 16 * r];
+#pragma unroll
+            for (int c = 0; c < 4; c++) bv[c] = s2[kk][tx + 16 * c];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = DA(acc[r][c], DM(av[r], bv[c]));
+        }
+        __syncthreads();
+    }
+    const double y_sq = a.ysq[v];
+    const double *colsq = a.colsq + v * a.bs.ntot, *ady = a.ady + v * a.bs.ntot;
+    const double *cS = ma.crossS + v * (int64_t)(N1 + N2) * S;
+    const double *cSS = ma.crossSS + v * (int64_t)S * S;
+    Best b;
+    b.res = INFINITY; b.idx = LLONG_MAX;
+#pragma unroll 1
+    for (int q = 0; q < 16; q++) {
+        const int r = q >> 2, c = q & 3;
+        const int i1 = tI + ty + 16 * r, i2 = tJ + tx + 16 * c;
+        if (i1 >= N1 || i2 >= N2) continue;
+        double a12 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++)
+                if (rr == r && cc == c) a12 = acc[rr][cc];
+        double G[kMaxBlocks * kMaxBlocks], Y[kMaxBlocks], w[kMaxBlocks];
+        G[0] = colsq[a.bs.start[0] + i1]; Y[0] = ady[a.bs.start[0] + i1];
+        G[kMaxBlocks + 1] = colsq[a.bs.start[1] + i2]; Y[1] = ady[a.bs.start[1] + i2];
+        G[1] = G[kMaxBlocks] = a12;
+        for (long long t = 0; t < ma.T; t++) {
+            int idx[kMaxBlocks];
+            long long rem = t;
+            for (int bb = nb - 1; bb >= 2; bb--) { idx[bb] = (int)(rem % a.bs.size[bb]); rem /= a.bs.size[bb]; }
+            for (int bb = 2; bb < nb; bb++) {
+                const int sb = a.bs.start[bb] - a.bs.start[2] + idx[bb];   // column among the trailing ones
+                G[bb * kMaxBlocks + bb] = colsq[a.bs.start[bb] + idx[bb]];
+                Y[bb] = ady[a.bs.start[bb] + idx[bb]];
+                G[bb] = G[bb * kMaxBlocks] = cS[(int64_t)i1 * S + sb];
+                G[kMaxBlocks + bb] = G[bb * kMaxBlocks + 1] = cS[(int64_t)(N1 + i2) * S + sb];
+                for (int b2 = 2; b2 < bb; b2++) {
+                    const int sb2 = a.bs.start[b2] - a.bs.start[2] + idx[b2];
+                    G[b2 * kMaxBlocks + bb] = G[bb * kMaxBlocks + b2] = cSS[(int64_t)sb2 * S + sb];
+                }
+            }
+            const double gain = nnls_enum(nb, G, Y, w);
+            const double res = y_sq - gain;
+            if (gain > 0.0 && res < y_sq)
+                best_take(b, res, ((long long)i1 * N2 + i2) * ma.T + t);   // product order
+        }
+    }
+    b = best_block_reduce(b, red);
+    if (threadIdx.x == 0) {
+        int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        a.tile_res[v * a.ntiles + tile] = b.res;
+        a.tile_idx[v * a.ntiles + tile] = b.idx;
+    }
+}
+
 // per voxel: min over tiles; one warp per voxel
 __global__ void __launch_bounds__(128) k_reduce_tiles(int64_t V, int ntiles, const double *tile_res,
                                                       const long long *tile_idx,
@@ -582,6 +756,11 @@ size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs)
         s += align256(sizeof(double) * V * bs.size[0] * bs.size[2]);
         s += align256(sizeof(double) * V * bs.size[1] * bs.size[2]);
     }
+    if (bs.nb >= 4) {
+        const size_t S = bs.ntot - bs.start[2];
+        s += align256(sizeof(double) * V * (bs.size[0] + bs.size[1]) * S);
+        s += align256(sizeof(double) * V * S * S);
+    }
     s += align256(sizeof(double) * V * exact_ntiles(bs));
     s += align256(sizeof(long long) * V * exact_ntiles(bs));
     return s;
@@ -592,8 +771,8 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
                         void *scratch, long long *tuple_out, cudaStream_t st, cudaEvent_t *ev)
 {
     if (V == 0) return MFB_OK;
-    if (bs.nb < 1 || bs.nb > 3) {
-        set_error("exact search supports 1-3 blocks");
+    if (bs.nb < 1 || bs.nb > kMaxBlocks) {
+        set_error("exact search supports 1-5 blocks");
         return MFB_EUNSUPPORTED;
     }
     if (V > 65535) {
@@ -613,6 +792,12 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
         a.cross13 = (double *)p; p += align256(sizeof(double) * V * bs.size[0] * bs.size[2]);
         a.cross23 = (double *)p; p += align256(sizeof(double) * V * bs.size[1] * bs.size[2]);
     }
+    double *crossS = nullptr, *crossSS = nullptr;
+    if (bs.nb >= 4) {
+        const size_t S = bs.ntot - bs.start[2];
+        crossS = (double *)p; p += align256(sizeof(double) * V * (bs.size[0] + bs.size[1]) * S);
+        crossSS = (double *)p; p += align256(sizeof(double) * V * S * S);
+    }
     a.tile_res = (double *)p; p += align256(sizeof(double) * V * a.ntiles);
     a.tile_idx = (long long *)p;
 
@@ -625,9 +810,20 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
             long long n = (long long)(bs.size[0] + bs.size[1]) * bs.size[2];
             MFB_LAUNCH(k_cross3, dim3((unsigned)((n + 127) / 128), (unsigned)V), 128, 0, st, a);
         }
+        MultiArgs ma;
+        if (bs.nb >= 4) {
+            ma.e = a;
+            ma.S = bs.ntot - bs.start[2];
+            ma.T = 1;
+            for (int b = 2; b < bs.nb; b++) ma.T *= bs.size[b];
+            ma.crossS = crossS; ma.crossSS = crossSS;
+            long long n = (long long)(bs.size[0] + bs.size[1] + ma.S) * ma.S;
+            MFB_LAUNCH(k_cross_small, dim3((unsigned)((n + 127) / 128), (unsigned)V), 128, 0, st, ma, crossS, crossSS);
+        }
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
         if (bs.nb == 2) MFB_LAUNCH(k_pairs<2>, grid, 256, 0, st, a);
-        else MFB_LAUNCH(k_pairs<3>, grid, 256, 0, st, a);
+        else if (bs.nb == 3) MFB_LAUNCH(k_pairs<3>, grid, 256, 0, st, a);
+        else MFB_LAUNCH(k_pairs_multi, grid, 256, 0, st, ma);
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     }
     MFB_LAUNCH(k_reduce_tiles, (unsigned)((V + 3) / 4), 128, 0, st, V, a.ntiles, a.tile_res,
@@ -932,6 +1128,31 @@ __device__ void eval_tuple(int M, int nb, const double *As /* M x kMaxBlocks */,
                             w1, w2);
         }
         if (res < y_sq) { w[0] = w0; w[1] = w1; w[2] = w2; obj = res; }
+    } else {
+        // 4-5 blocks: NNLS by support enumeration on the tuple's Gram matrix; the objective is
+        // the direct residual, like scipy's rnorm^2 (mfu:640-641)
+        double G[kMaxBlocks * kMaxBlocks], Y[kMaxBlocks], ww[kMaxBlocks];
+        for (int i = 0; i < nb; i++) {
+            double dyi = 0.0;
+            for (int k = 0; k < M; k++) dyi = DA(dyi, DM(y[k * ys], As[(size_t)k * kMaxBlocks + i]));
+            Y[i] = dyi;
+            for (int j = 0; j <= i; j++) {
+                double g = 0.0;
+                for (int k = 0; k < M; k++)
+                    g = DA(g, DM(As[(size_t)k * kMaxBlocks + i], As[(size_t)k * kMaxBlocks + j]));
+                G[i * kMaxBlocks + j] = G[j * kMaxBlocks + i] = g;
+            }
+        }
+        const double gain = nnls_enum(nb, G, Y, ww);
+        if (gain > 0.0) {
+            double res = 0.0;
+            for (int k = 0; k < M; k++) {
+                double r = -y[k * ys];
+                for (int i = 0; i < nb; i++) r += As[(size_t)k * kMaxBlocks + i] * ww[i];
+                res += r * r;
+            }
+            if (res < y_sq) { for (int i = 0; i < nb; i++) w[i] = ww[i]; obj = res; }
+        }
     }
 }
 

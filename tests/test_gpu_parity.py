@@ -148,8 +148,6 @@ def test_mfmodel_fit_matches_reference_maps(ukbb, tag):
         ear = None
     elif tag == "C":
         numfasc = np.minimum(numfasc, 1)
-    if tag == "D":
-        pytest.xfail("2 fascicles + CSF + EAR (4 blocks) not implemented yet")
     model = _ukbb_model(ukbb)
     fit = model.fit(ukbb["data"], ukbb["mask"], numfasc, peaks=ukbb["peaks"], bvals=ukbb["bvals"],
                     bvecs=ukbb["bvecs"], csf_mask=csf, ear_mask=ear, verbose=0)
@@ -295,3 +293,22 @@ def test_fast_tier_large_validation():
     plan.close()
     assert np.array_equal(fast, exact)
     assert st[0] + st[1] == 20000 and st[1] < 0.02 * 20000, st
+
+
+@pytest.mark.parametrize("name", [n for n in SOLVER_CASE_NAMES if n[1] in "45"])
+def test_solver_4up_matches_reference(solver_cases, name):
+    """4-5 blocks: the reference runs scipy.optimize.nnls per tuple; the GPU enumerates the
+    supports in closed form -> same tuple, weights and objective to rounding (1e-9)."""
+    A, Y, sizes = solver_cases[name + "_A"], solver_cases[name + "_Y"], solver_cases[name + "_sizes"]
+    ysq = np.sum(Y ** 2, axis=1)
+    for v in range(Y.shape[0]):
+        w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(A, Y[v].copy(), sizes)
+        assert sub.dtype == np.int64
+        rsub, rw = solver_cases[name + "_sub"][v], solver_cases[name + "_w"][v]
+        # a block whose optimal weight is 0 leaves its index undetermined (every atom of that
+        # block ties to rounding in the reference): indices must agree wherever weight > 0
+        active = (rw > 1e-9 * rw.max()) | (w > 1e-9 * max(w.max(), 1e-300))
+        assert np.array_equal(sub[active], rsub[active]), (name, v)
+        assert np.allclose(w, rw, rtol=1e-9, atol=1e-9 * rw.max()), (name, v)
+        assert abs(obj - solver_cases[name + "_obj"][v]) <= 1e-12 * ysq[v] + 1e-9 * abs(obj)
+        assert np.allclose(yrec, solver_cases[name + "_yrec"][v], rtol=1e-9, atol=1e-9 * np.sqrt(ysq[v]))
