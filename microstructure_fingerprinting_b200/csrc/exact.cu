@@ -981,11 +981,8 @@ int launch_single_fascicle(const DevPlan &p, int64_t nvox, const int32_t *vox_li
     const int nIso = csf + ear * p.E;
     size_t smem = sizeof(double) * ((size_t)5 * p.M + (size_t)nIso * p.M + 3 * SF_MAXISO) + sizeof(int) * 4 * p.M;
     if (smem > 200 * 1024) { set_error("single-fascicle kernel: protocol too long for shared memory"); return MFB_EUNSUPPORTED; }
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
+    if (smem > 48 * 1024)  // per device / context attribute
         MFB_CUDA_TRY(cudaFuncSetAttribute(k_single_fascicle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
     const int64_t maxgrid = 1 << 20;
     for (int64_t v0 = 0; v0 < nvox; v0 += maxgrid) {
         SfArgs b = a;

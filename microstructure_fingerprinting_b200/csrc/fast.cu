@@ -728,12 +728,9 @@ int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_
         set_error("fast tier: tile does not fit in shared memory");
         return MFB_EUNSUPPORTED;
     }
-    static size_t attr_set[2] = {0, 0};
-    if (attr_set[csf ? 1 : 0] < smem) {
-        if (csf) MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[csf ? 1 : 0] = smem;
-    }
+    // per device / context attribute: set on every launch (microseconds)
+    if (csf) MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
     dim3 grid(a.ntI, (unsigned)V);
     if (csf) MFB_LAUNCH(k_fast_pairs<1>, grid, FT_THREADS, smem, st, a);

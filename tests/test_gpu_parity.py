@@ -312,3 +312,21 @@ def test_solver_4up_matches_reference(solver_cases, name):
         assert np.allclose(w, rw, rtol=1e-9, atol=1e-9 * rw.max()), (name, v)
         assert abs(obj - solver_cases[name + "_obj"][v]) <= 1e-12 * ysq[v] + 1e-9 * abs(obj)
         assert np.allclose(yrec, solver_cases[name + "_yrec"][v], rtol=1e-9, atol=1e-9 * np.sqrt(ysq[v]))
+
+
+def test_fit_parallel_multi_gpu(ukbb):
+    """parallel=True shards the ROI over all visible GPUs (contiguous spans, no collective):
+    the maps must be identical to the single-GPU fit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ph = make_phantom(n_atoms=200, n_vox=3001, seed=31, csf_frac=0.3)
+    dic = ph.dic
+    model = MFModel(dic)
+    shape = (3001,)
+    one = model.fit(ph.Y, np.ones(shape), ph.K.astype(float), peaks=ph.peaks, pgse_scheme=ph.sch,
+                    csf_mask=ph.csf.astype(float), verbose=0, parallel=False)
+    many = model.fit(ph.Y, np.ones(shape), ph.K.astype(float), peaks=ph.peaks, pgse_scheme=ph.sch,
+                     csf_mask=ph.csf.astype(float), verbose=0, parallel=True)
+    for p in one.param_names:
+        assert np.array_equal(getattr(one, p), getattr(many, p)), p
