@@ -90,6 +90,20 @@ int mfb_rotate_multishell(mfb_plan *plan, int64_t V, const double *dirs,
                           double *D_out, int64_t ldd, void *stream);
 
 /*
+ * Row-lerp primitive behind mfu.rotate_atom (mf_utils.py:1205-1437) and
+ * mfu.rotate_atom_2Dprotocol (mf_utils.py:1440-1690): the per-shell / per-line
+ * scipy interp1d calls (mf_utils.py:1423-1426, 1678-1684) evaluated for a batch of
+ * directions from an explicit interpolation plan.  Device pointers:
+ *   table R*N row-major; row_lo,row_hi,w_lo,w_hi V*M; scale V*M or NULL
+ *   out[v][m][0..N) = scale * (w_hi*table[row_hi] + w_lo*table[row_lo]),
+ *   separately rounded products and sum (scipy's two-weight form); rows of ldd doubles.
+ */
+int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *table,
+                  const int32_t *row_lo, const int32_t *row_hi, const double *w_lo,
+                  const double *w_hi, const double *scale, double *out, int64_t ldd,
+                  void *stream);
+
+/*
  * Batched solve_exhaustive_posweights on explicit dictionaries.
  *   nblocks in [1,5]; sizes[nblocks] (host) > 0, Ntot = sum(sizes)
  *   A       device; voxel v's dictionary is the row-major (M, lda) matrix at

@@ -27,6 +27,8 @@ SYMBOLS = {
                                ctypes.c_int]),
     "mfb_plan_destroy": (None, [c_vp]),
     "mfb_rotate_multishell": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, ctypes.c_int64, c_vp]),
+    "mfb_lerp_rows": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp]),
     "mfb_solve_batch": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_vp,
                                        c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp, c_vp,
                                        c_vp, c_vp]),

@@ -185,6 +185,19 @@ extern "C" int mfb_rotate_multishell(mfb_plan *pl, int64_t V, const double *dirs
                                   (int64_t)pl->dp.M * ldd, (cudaStream_t)stream);
 }
 
+extern "C" int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *table,
+                             const int32_t *row_lo, const int32_t *row_hi, const double *w_lo,
+                             const double *w_hi, const double *scale, double *out, int64_t ldd,
+                             void *stream)
+{
+    if (V < 0 || M < 0 || N <= 0 || ldd < N || (V > 0 && M > 0 && (!table || !row_lo || !row_hi || !w_lo || !w_hi || !out))) {
+        set_error("mfb_lerp_rows: invalid argument");
+        return MFB_EINVAL;
+    }
+    MFB_CUDA_TRY(cudaSetDevice(device));
+    return launch_lerp_rows(V, M, N, table, row_lo, row_hi, w_lo, w_hi, scale, out, ldd, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------------------------
 // batched solve on explicit dictionaries
 // ---------------------------------------------------------------------------------

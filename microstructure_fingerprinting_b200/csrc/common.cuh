@@ -79,6 +79,10 @@ int launch_rotate_assemble(const DevPlan &p, int64_t nvox, const int32_t *vox_li
                            const double *peaks, int peaks_ld, int K, int csf, int ear,
                            double *A, int64_t lda, int64_t strideA, cudaStream_t st);
 
+int launch_lerp_rows(int64_t V, int M, int N, const double *table, const int32_t *row_lo,
+                     const int32_t *row_hi, const double *w_lo, const double *w_hi,
+                     const double *scale, double *out, int64_t ldd, cudaStream_t st);
+
 size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs);
 
 // Exhaustive search in the reference's arithmetic on explicit dictionaries.

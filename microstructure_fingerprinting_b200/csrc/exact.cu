@@ -168,6 +168,41 @@ int launch_rotate_assemble(const DevPlan &p, int64_t nvox, const int32_t *vox_li
 }
 
 // ---------------------------------------------------------------------------------
+// explicit-plan row lerp (rotate_atom / rotate_atom_2Dprotocol): grid (M, V)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_lerp_rows(int M, int N, const double *table, const int32_t *row_lo, const int32_t *row_hi,
+            const double *w_lo, const double *w_hi, const double *scale, double *out, int64_t ldd)
+{
+    const int64_t v = blockIdx.y;
+    const int m = blockIdx.x;
+    const int64_t o = v * M + m;
+    const double *tl = table + (size_t)row_lo[o] * N, *th = table + (size_t)row_hi[o] * N;
+    const double wl = w_lo[o], wh = w_hi[o];
+    double *dst = out + (v * M + m) * ldd;
+    if (scale) {
+        const double sc = scale[o];
+        for (int j = threadIdx.x; j < N; j += blockDim.x) dst[j] = DM(sc, DA(DM(wh, th[j]), DM(wl, tl[j])));
+    } else {
+        for (int j = threadIdx.x; j < N; j += blockDim.x) dst[j] = DA(DM(wh, th[j]), DM(wl, tl[j]));
+    }
+}
+
+int launch_lerp_rows(int64_t V, int M, int N, const double *table, const int32_t *row_lo,
+                     const int32_t *row_hi, const double *w_lo, const double *w_hi,
+                     const double *scale, double *out, int64_t ldd, cudaStream_t st)
+{
+    if (V == 0 || M == 0) return MFB_OK;
+    for (int64_t v0 = 0; v0 < V; v0 += 65535) {
+        const int64_t nv = std::min<int64_t>(65535, V - v0);
+        MFB_LAUNCH(k_lerp_rows, dim3((unsigned)M, (unsigned)nv), 256, 0, st, M, N, table, row_lo + v0 * M,
+                   row_hi + v0 * M, w_lo + v0 * M, w_hi + v0 * M, scale ? scale + v0 * M : nullptr,
+                   out + v0 * M * ldd, ldd);
+    }
+    return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // closed forms
 // ---------------------------------------------------------------------------------
 // mfu:404-459 lsqnonneg_2var_opt (also inlined at mfu:331-381)

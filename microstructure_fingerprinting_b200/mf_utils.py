@@ -9,6 +9,9 @@ Mirrors (same names, argument meaning, return types and error behaviour):
   get_gyromagnetic_ratio            reference mf_utils.py:1138-1150
   DT_vec_to_2Darray                 reference mf_utils.py:901-957
   loadmat                           reference mf_utils.py:3026-3087
+  rotate_atom                       reference mf_utils.py:1205-1437
+  rotate_atom_2Dprotocol            reference mf_utils.py:1440-1690
+  rotate_scheme_mat, vrrotvec2mat   reference mf_utils.py:1153-1202, 842-858
 The numerical work (rotation, exhaustive search) runs in libmfb200.so on the GPU; this
 module only validates, marshals and keeps the small per-study tables on the host.
 There is no CPU fallback.
@@ -23,6 +26,7 @@ __all__ = ["solve_exhaustive_posweights", "solve_exhaustive_posweights_batch",
            "init_PGSE_multishell_interp", "interp_PGSE_from_multishell",
            "import_PGSE_scheme", "get_PGSE_scheme_from_bval_bvec_dense",
            "get_gyromagnetic_ratio", "DT_vec_to_2Darray", "loadmat", "from_ipython",
+           "rotate_atom", "rotate_atom_2Dprotocol", "rotate_scheme_mat", "vrrotvec2mat",
            "MultiShellTable", "SchemePlan", "GpuPlan"]
 
 
@@ -528,3 +532,302 @@ def solve_exhaustive_posweights(A, y, dicsizes, printmsg=None):
         A.astype(np.float64), y.astype(np.float64).reshape(1, -1), dicsizes)
     idt = np.int64 if dicsizes.size >= 4 else np.int32
     return (w[0], sub[0].astype(idt), tot[0].astype(idt), float(obj[0]), yrec[0])
+
+
+# ----------------------------------------------------------------------------------
+# HARDI / AxCaliber rotations of an M-row dictionary (low-level API)
+# ----------------------------------------------------------------------------------
+
+def _lerp_rows(table, row_lo, row_hi, w_lo, w_hi, scale=None, device=0):
+    """out[v, m, :] = scale * (w_hi * table[row_hi] + w_lo * table[row_lo]) on the GPU
+    (mfb_lerp_rows).  Plan arrays are (V, M); returns a NumPy array (V, M, N)."""
+    torch = _lib.require_cuda()
+    dev = torch.device('cuda', device)
+    table = np.ascontiguousarray(table, dtype=np.float64)
+    V, M = row_lo.shape
+    N = table.shape[1]
+
+    def up(x, dt):
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=dt)).to(dev)
+    d_t = up(table, np.float64)
+    d_rl, d_rh = up(row_lo, np.int32), up(row_hi, np.int32)
+    d_wl, d_wh = up(w_lo, np.float64), up(w_hi, np.float64)
+    d_sc = None if scale is None else up(scale, np.float64)
+    out = torch.empty((V, M, N), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = _lib.load().mfb_lerp_rows(device, V, M, N, d_t.data_ptr(), d_rl.data_ptr(), d_rh.data_ptr(),
+                                       d_wl.data_ptr(), d_wh.data_ptr(),
+                                       None if d_sc is None else d_sc.data_ptr(), out.data_ptr(), N, st)
+    _lib.check(rc, "mfb_lerp_rows")
+    return out.cpu().numpy()
+
+
+def _lerp_plan(xs, x_new):
+    """scipy interp1d._call_linear bookkeeping for sorted nodes xs: interval index clipped
+    to [1, n-1] (linear extrapolation outside) and the two separately rounded weights."""
+    j = np.clip(np.searchsorted(xs, x_new), 1, xs.size - 1)
+    x_lo, x_hi = xs[j - 1], xs[j]
+    return j - 1, j, (x_hi - x_new) / (x_hi - x_lo), (x_new - x_lo) / (x_hi - x_lo)
+
+
+def rotate_atom(sig, sch_mat, ordir, newdir, DIFF, S0, warnings=True):
+    """Rotate HARDI signals of single fascicles from `ordir` to `newdir`
+    (reference mf_utils.py:1205-1437).
+
+    Per (G, Delta, delta) shell of `sch_mat`: nodes = sorted unique |g.ordir| (first
+    occurrences), the free-diffusion point (1, exp(-b*DIFF)*S0) appended unless a node
+    equals 1, the near-perpendicular cluster merged into its mean, linear interpolation /
+    extrapolation at |g.newdir|; b0 rows are copied.  Returns an array shaped like `sig`.
+    Extension: `newdir` of shape (V, 3) returns (V,) + sig.shape.
+    """
+    assert isinstance(sig, np.ndarray), "Input sig should be a NumPy ndarray"
+    assert isinstance(sch_mat, np.ndarray), "Input sch_mat should be a NumPy ndarray"
+    assert isinstance(ordir, np.ndarray), "Input ordir should be a NumPy ndarray"
+    assert isinstance(newdir, np.ndarray), "Input newdir should be a NumPy ndarray"
+    sig_shape = sig.shape
+    if sig.ndim == 1:
+        sig = sig.reshape((sig.size, 1))
+    if not isinstance(DIFF, np.ndarray):
+        DIFF = np.array([[DIFF]])
+    assert isinstance(S0, np.ndarray), "Input S0 should be a NumPy ndarray"
+    if S0.ndim == 1:
+        S0 = S0[:, np.newaxis]
+    if sch_mat.shape[1] < 6:
+        raise ValueError('sch_mat must be a N-by-6 or7 matrix')
+    if sch_mat.shape[0] != sig.shape[0]:
+        raise ValueError('sch_mat and sig must have the same number of rows')
+    assert sig.shape == S0.shape, "The S0 matrix should have the same size as the signal matrix"
+
+    batched = newdir.ndim == 2 and newdir.shape[1] == 3 and newdir.size > 3
+    dirs = newdir.reshape(-1, 3) if batched else newdir.reshape(1, 3)
+    V, M = dirs.shape[0], sig.shape[0]
+    gam = get_gyromagnetic_ratio('H')
+    gnorm = np.sqrt((sch_mat[:, 0:3] ** 2).sum(axis=1, keepdims=True))
+    gnorm[gnorm == 0] = np.inf
+    gunit = sch_mat[:, 0:3] / gnorm
+    x_or = np.abs(np.dot(gunit, ordir / np.sqrt((ordir ** 2).sum())))
+    x_new = np.stack([np.abs(np.dot(gunit, d / np.sqrt((d ** 2).sum()))) for d in dirs])  # (V, M)
+    bvals = (gam * sch_mat[:, 3] * sch_mat[:, 5]) ** 2 * (sch_mat[:, 4] - sch_mat[:, 5] / 3)
+    shells, shell_of = np.unique(sch_mat[:, 3:6], return_inverse=True, axis=0)
+    shell_of = np.ravel(shell_of)
+
+    rows = [sig]                      # table: the raw rows first (b0 rows are copied), then shells
+    n_rows = M
+    row_lo = np.zeros((V, M), dtype=np.int32)
+    row_hi = np.zeros((V, M), dtype=np.int32)
+    w_lo = np.ones((V, M))
+    w_hi = np.zeros((V, M))
+    for s in range(shells.shape[0]):
+        ind = np.where(shell_of == s)[0]
+        bval = bvals[ind[0]]
+        if bval == 0:
+            row_lo[:, ind] = row_hi[:, ind] = ind
+            continue
+        if ind.size < 2:
+            raise ValueError("Fewer than 2 identical (G, Del, del) triplets "
+                             "detected for triplet %d/%d (%g, %g, %g), b=%g"
+                             " s/mm^2, probably not a HARDI shell." %
+                             (s + 1, shells.shape[0], shells[s, 0], shells[s, 1], shells[s, 2], bval / 1e6))
+        if ind.size < 10 and warnings:
+            print("WARNING: rotate_atom: fewer than 10 data points detected"
+                  " for acquisition parameters (G, Del, del) %d/%d "
+                  "(%g, %g, %g), b=%g s/mm^2.\nQuality of approximation may be poor."
+                  % (s + 1, shells.shape[0], shells[s, 0], shells[s, 1], shells[s, 2], bval / 1e6))
+        same_S0 = np.all(np.isclose(S0[ind, :], S0[ind[0], :]), axis=0)
+        if np.any(~same_S0):
+            bad = np.where(~same_S0)[0]
+            raise ValueError('Distinct values in provided S0 image '
+                             'for shell  %d/%d (b=%g s/mm^2) for %d substrate(s) [%s]' %
+                             (s + 1, shells.shape[0], bval / 1e6, bad.shape[0],
+                              " ".join("{:d}".format(b) for b in bad)))
+        xs, first = np.unique(x_or[ind], return_index=True)
+        ys = sig[ind, :][first, :]
+        if not np.any(xs == 1):
+            xs = np.append(xs, [1])
+            ys = np.append(ys, np.exp(-bval * DIFF) * S0[ind[0], :][np.newaxis, :], axis=0)
+        cluster = np.abs(xs - xs[0]) < 1e-3
+        c = int(np.sum(cluster))
+        if c > 1:
+            xs = np.append(np.mean(xs[cluster]), xs[c:])
+            ys = np.append(np.mean(ys[cluster, :], axis=0, keepdims=True), ys[c:, :], axis=0)
+        lo, hi, wl, wh = _lerp_plan(xs, x_new[:, ind])
+        row_lo[:, ind], row_hi[:, ind] = n_rows + lo, n_rows + hi
+        w_lo[:, ind], w_hi[:, ind] = wl, wh
+        rows.append(ys)
+        n_rows += ys.shape[0]
+    out = _lerp_rows(np.vstack(rows), row_lo, row_hi, w_lo, w_hi)
+    if np.any(np.isnan(out)):
+        raise ValueError('Nan detected after rotation of substrate(s).')
+    if batched:
+        return out.reshape((V,) + sig_shape)
+    return np.reshape(out[0], sig_shape)
+
+
+def vrrotvec2mat(rotax, theta):
+    """Rotation matrix of angle theta about the unit axis rotax (reference mf_utils.py:842-858)."""
+    if rotax.size != 3:
+        raise ValueError("rotation axis should be a 3-element NumPy array")
+    if ~np.isclose(np.sum(rotax ** 2), 1):
+        raise ValueError("rotation axis should have unit norm")
+    s, c = np.sin(theta), np.cos(theta)
+    t = 1 - c
+    x, y, z = rotax[0], rotax[1], rotax[2]
+    return np.array([[t * x * x + c, t * x * y - s * z, t * x * z + s * y],
+                     [t * x * y + s * z, t * y * y + c, t * y * z - s * x],
+                     [t * x * z - s * y, t * y * z + s * x, t * z * z + c]])
+
+
+def rotate_scheme_mat(sch_mat, cyldir1, cyldir2):
+    """Scheme matrix seen from a fascicle rotated from cyldir1 to cyldir2
+    (reference mf_utils.py:1153-1202): DWI(fasc(dir2); sch) = DWI(fasc(dir1); sch_eff)."""
+    if cyldir1.size != 3 or cyldir2.size != 3:
+        raise ValueError("cyldir1 and cyldir2 should be 3-elements NumPy arrays.")
+    if (~np.isclose(np.sum(cyldir1 ** 2), 1) or ~np.isclose(np.sum(cyldir2 ** 2), 1)):
+        raise ValueError("cyldir1 and cyldir2 should have unit norm.")
+    axis = np.cross(cyldir1, cyldir2)
+    n2 = np.sum(axis ** 2)
+    if not n2 > 0:
+        return sch_mat
+    axis = axis / np.sqrt(n2)
+    ang = np.arccos(np.dot(cyldir1, cyldir2))
+    g = sch_mat[:, :3] @ vrrotvec2mat(axis, -ang).T
+    g[np.abs(g) <= np.finfo(float).eps] = 0
+    gn = np.sqrt(np.sum(g ** 2, axis=1, keepdims=True))
+    nz = np.squeeze(gn > 0)
+    g[nz, :] = g[nz, :] / gn[nz, :]
+    return np.hstack((g, sch_mat[:, 3:])) if sch_mat.shape[1] > 3 else g
+
+
+def _perp_frame(sch_mat, fascdir):
+    """Unit in-plane directions, perpendicular and parallel gradient intensities of every
+    sequence in the frame of a fascicle along fascdir (reference mf_utils.py:1502-1517)."""
+    eff = rotate_scheme_mat(sch_mat, np.array([0, 0, 1]), fascdir)
+    # NB: like the reference, the in-plane directions are normalised IN PLACE in `eff`; when
+    # fascdir is the z axis `eff` is `sch_mat` itself, so the (private) scheme copy is
+    # normalised and a later frame computed from it sees unit in-plane norms
+    # (reference mf_utils.py:1503-1508, 1530-1535).  Reproduced for parity.
+    gp = eff[:, 0:2]
+    nrm = np.sqrt(np.sum(gp ** 2, axis=1))
+    nz = nrm > 0
+    gp[nz, :] = eff[nz, 0:2] / nrm[nz][:, np.newaxis]
+    G = sch_mat[:, 3]
+    return gp, nz, G * nrm, np.abs(eff[:, 2]) * G
+
+
+def _opposite_pairs(dirs_un):
+    """Index pairs (i, j) of unique in-plane directions with d_i . d_j ~ -1."""
+    return np.where(np.isclose(dirs_un @ dirs_un.T, -1))
+
+
+def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF):
+    """Rotate signals of a 2D AxCaliber-like protocol (gradients in the xy plane, pairs of
+    opposite polarities along one or two lines) from a fascicle along `refdir` to `newdir`
+    (reference mf_utils.py:1440-1690): signal = parallel free-diffusion factor times the
+    perpendicular signal, the latter interpolated linearly in the signed perpendicular
+    gradient intensity along the closest reference line, per (Delta, delta) pair.
+    """
+    sig_shape = sig.shape
+    if sig.ndim == 1:
+        sig = sig[:, np.newaxis]
+    if np.any(sch_mat[:, 2] != 0):
+        raise ValueError("Use the original schemefile with zeros for gz.\n"
+                         "Specify the reference and new orientations separately.")
+    if sig_shape[0] != sch_mat.shape[0]:
+        raise ValueError("Signal and scheme matrix must have the same "
+                         "number of elements (sequences) along their first"
+                         " dimension. Detected %d and %d." % (sig_shape[0], sch_mat.shape[0]))
+    sch_mat = np.array(sch_mat, dtype=np.float64, copy=True)   # private: never touch the caller's
+    gam = get_gyromagnetic_ratio('H')
+    G, Delta, delta = sch_mat[:, 3], sch_mat[:, 4], sch_mat[:, 5]
+    is_b0, is_b = (G == 0), (G != 0)
+    M = sch_mat.shape[0]
+
+    g_ref, nz_ref, Gperp_ref, Gpar_ref = _perp_frame(sch_mat, refdir)
+    assert np.all(np.isclose(G ** 2, Gperp_ref ** 2 + Gpar_ref ** 2)), \
+        "Inconsistency in parallel and perpendicular gradient components for reference fasicle."
+    S_par_ref = np.exp(-(gam * delta * Gpar_ref) ** 2 * (Delta - delta / 3) * DIFF)
+    assert np.all(np.isclose(S_par_ref[is_b0], 1)), \
+        "Reference fascicle: parallel signal should  be one in b0 sequences."
+    S_perp_ref = sig / S_par_ref[:, np.newaxis]          # lookup-table rows 0..M-1
+
+    g_new, nz_new, Gperp_new, Gpar_new = _perp_frame(sch_mat, newdir)
+    assert np.all(np.isclose(G ** 2, Gperp_new ** 2 + Gpar_new ** 2)), \
+        "Inconsistency in parallel and perpendicular gradient components for new fascicle."
+    S_par_new = np.exp(-(gam * delta * Gpar_new) ** 2 * (Delta - delta / 3) * DIFF)
+    assert np.all(np.isclose(S_par_new[is_b0], 1)), \
+        "New fascicle: parallel signal should  be equal to 1 in b0 sequences."
+
+    # interpolation plan: b0 sequences copy their own row
+    row_lo = np.arange(M, dtype=np.int32)
+    row_hi = np.arange(M, dtype=np.int32)
+    w_lo, w_hi = np.ones(M), np.zeros(M)
+    extra_rows = []
+    covered = is_b0.copy()
+
+    pairs, pair_of = np.unique(sch_mat[:, 4:6], return_inverse=True, axis=0)
+    pair_of = np.ravel(pair_of)
+    for ip in range(pairs.shape[0]):
+        in_pair = pair_of == ip
+        ind = np.where(in_pair)[0]
+        ref_un, ref_id = np.unique(g_ref[ind, :], return_inverse=True, axis=0)
+        ref_id = np.ravel(ref_id)
+        assert ref_un.shape[0] in (3, 5), (
+            "Problem at delta pair %d/%d: found %d unique gradient directions in plane perpendicular"
+            " to reference fascicle (including b0 zero dirs)." % (ip + 1, pairs.shape[0], ref_un.shape[0]))
+        ig, ig_op = _opposite_pairs(ref_un)
+        assert ig.size in (2, 4), (
+            "Problem at delta pair %d/%d: found %d instead of 4 (2x2, redundant) pairs of opposite "
+            "directions in plane perpendicular to reference fascicle." % (ip + 1, pairs.shape[0], ig.size))
+        new_un, new_id = np.unique(g_new[ind, :], return_inverse=True, axis=0)
+        new_id = np.ravel(new_id)
+        assert new_un.shape[0] in (3, 5), (
+            "Problem at delta pair %d/%d: found %d unique gradient directions in plane perpendicular to "
+            "new fascicle (including b0 zero dirs)." % (ip + 1, pairs.shape[0], new_un.shape[0]))
+        pn, pn_op = _opposite_pairs(new_un)
+        upper = pn < pn_op
+        pn, pn_op = pn[upper], pn_op[upper]
+        assert pn.size in (1, 2), (
+            "Problem at delta pair %d/%d: found %d instead of 2 pairs of opposite directions, in plane "
+            " perpendicular to new fascicle." % (ip + 1, pairs.shape[0], pn.size))
+
+        # gradients that became parallel to the new fascicle: mean b0 signal of the shell
+        vanished = ~nz_new & is_b & in_pair
+        shell_b0 = is_b0 & in_pair
+        if np.sum(vanished) > 0:
+            assert np.sum(shell_b0) > 0, (
+                "Shell %d/%d: some new line directions are completely parallel to new fascicle, "
+                "implying free diffusion. However, no b0 measurements in the reference signal are "
+                "available for this shell. We therefore can't properly scale the new signal."
+                % (ip + 1, pairs.shape[0]))
+            if np.sum(shell_b0) == 1:
+                row_lo[vanished] = row_hi[vanished] = np.where(shell_b0)[0][0]
+            else:
+                extra_rows.append(np.mean(sig[shell_b0, :], axis=0))
+                row_lo[vanished] = row_hi[vanished] = M + len(extra_rows) - 1
+            w_lo[vanished], w_hi[vanished] = 1.0, 0.0
+            covered |= vanished
+
+        for il in range(pn.size):
+            line_new = new_un[pn[il], :]
+            sel_new = ind[(new_id == pn[il]) | (new_id == pn_op[il])]
+            assert np.all(is_b[sel_new]), (
+                "Problem at delta pair %d/%d, new line direction %d/%d: trying to interpolate b0 "
+                "sequences." % (ip + 1, pairs.shape[0], il, pn.size))
+            Gs_new = Gperp_new[sel_new] * np.sign(g_new[sel_new, :] @ line_new)
+            i_max = np.argmax(ref_un @ line_new)     # closest reference line
+            line_ref = ref_un[i_max, :]
+            k = np.where(i_max == ig)[0]
+            sel_ref = ind[(ref_id == ig[k]) | (ref_id == ig_op[k])]
+            Gs_ref = Gperp_ref[sel_ref] * np.sign(g_ref[sel_ref, :] @ line_ref)
+            order = np.argsort(Gs_ref, kind="mergesort")   # interp1d(assume_sorted=False)
+            lo, hi, wl, wh = _lerp_plan(Gs_ref[order], Gs_new)
+            row_lo[sel_new], row_hi[sel_new] = sel_ref[order][lo], sel_ref[order][hi]
+            w_lo[sel_new], w_hi[sel_new] = wl, wh
+            covered[sel_new] = True
+    table = S_perp_ref if not extra_rows else np.vstack([S_perp_ref] + extra_rows)
+    # sequences no rule reached keep a zero perpendicular signal, like the reference
+    scale = np.where(covered, S_par_new, 0.0)
+    out = _lerp_rows(table, row_lo[None, :], row_hi[None, :], w_lo[None, :], w_hi[None, :],
+                     scale[None, :])[0]
+    return np.reshape(out, sig_shape)

@@ -211,7 +211,71 @@ def reference_test_vectors():
     print("ref_synthetic written")
 
 
+def lowlevel_rotation_cases():
+    """rotate_atom on a subset of the HCP Monte-Carlo dictionary (the reference's
+    test_hcp_dict pipeline, tests/integration/test_exhaustive_fingerprinting.py:163-249) and
+    rotate_atom_2Dprotocol on the AxCaliber fixture scheme with analytic atoms."""
+    rng = np.random.default_rng(99)
+    ld = mfu.loadmat(os.path.join(FIX, "MC_dictionary_hcp.mat"))
+    dic = ld["dic_fascicle_refdir"]
+    cols = np.sort(rng.choice(dic.shape[1], 16, replace=False))
+    cols[3] = 86                                   # the atom test_hcp_dict plants
+    cols = np.unique(cols)
+    sig, S0 = np.ascontiguousarray(dic[:, cols]), np.ascontiguousarray(ld["S0_fascicle"][:, cols])
+    sch = mfu.import_PGSE_scheme(os.path.join(FIX, "hcp_mgh_1003.scheme1"))
+    sch_b0 = np.vstack((np.zeros((40, sch.shape[1])), sch))
+    sch_b0[:40, 4:] = sch[0, 4:]
+    refdir = np.array([0.0, 0.0, 1.0])
+    dirs = rng.standard_normal((4, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs[0] = [0.0, 0.0, 1.0]
+    rot = np.stack([mfu.rotate_atom(sig, sch_b0, refdir, d, ld["WM_DIFF"], S0) for d in dirs])
+    rot1d = mfu.rotate_atom(sig[:, 2], sch_b0, refdir, dirs[1], ld["WM_DIFF"], S0[:, 2])
+    # the joint pipeline of test_hcp_dict on the subset: 2 fascicles + CSF, noiseless
+    i_gt = int(np.where(cols == 86)[0][0])
+    fd = dirs[1:3]
+    nu_gt = np.array([0.5, 0.3, 0.2])
+    D = np.zeros((sch_b0.shape[0], 2 * cols.size + 1))
+    y = np.zeros(sch_b0.shape[0])
+    for k in range(2):
+        D[:, k * cols.size:(k + 1) * cols.size] = mfu.rotate_atom(sig, sch_b0, refdir, fd[k],
+                                                                  ld["WM_DIFF"], S0)
+        y += 500 * nu_gt[k] * D[:, k * cols.size + i_gt]
+    D[:, -1] = ld["sig_csf"]
+    y += 500 * nu_gt[2] * ld["sig_csf"]
+    w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(D, y, np.array([cols.size, cols.size, 1]))
+
+    # ---- 2D protocol ----
+    sch2 = mfu.import_PGSE_scheme(os.path.join(FIX, "2D_qspace_clean_rot_xy.scheme"))
+    gam = mfu.get_gyromagnetic_ratio("H")
+    DIFF2 = 2.0e-9
+    G, Del, dl = sch2[:, 3], sch2[:, 4], sch2[:, 5]
+    ref2 = np.array([0.0, 0.0, 1.0])
+    eff = mfu.rotate_scheme_mat(sch2.copy(), np.array([0, 0, 1.0]), ref2)
+    gperp = np.sqrt(np.sum(eff[:, :2] ** 2, axis=1))
+    bperp = (gam * dl * G * gperp) ** 2 * (Del - dl / 3)
+    bpar = (gam * dl * np.abs(eff[:, 2]) * G) ** 2 * (Del - dl / 3)
+    dperp = np.array([0.05e-9, 0.2e-9, 0.45e-9, 0.8e-9, 1.3e-9])
+    sig2 = np.exp(-bpar[:, None] * DIFF2) * np.exp(-bperp[:, None] * dperp[None, :])
+    sig2 *= (1.0 + 0.01 * rng.standard_normal(sig2.shape))       # MC-like variability
+    dirs2 = rng.standard_normal((4, 3))
+    dirs2 /= np.linalg.norm(dirs2, axis=1, keepdims=True)
+    dirs2[0] = [0.0, 0.0, 1.0]
+    # the reference normalises its sch_mat argument in place when refdir is the z axis: hand it a
+    # fresh copy per call so that every golden comes from the pristine fixture scheme
+    rot2 = np.stack([mfu.rotate_atom_2Dprotocol(sig2, sch2.copy(), ref2, d, DIFF2) for d in dirs2])
+    rot2_1d = mfu.rotate_atom_2Dprotocol(sig2[:, 1], sch2.copy(), ref2, dirs2[2], DIFF2)
+    np.savez_compressed(
+        os.path.join(OUT, "lowlevel_rotation.npz"),
+        hcp_sig=sig, hcp_S0=S0, hcp_sch=sch_b0, hcp_dirs=dirs, hcp_rot=rot, hcp_rot1d=rot1d,
+        hcp_DIFF=ld["WM_DIFF"], hcp_sig_csf=ld["sig_csf"], hcp_y=y, hcp_w=w, hcp_sub=sub,
+        hcp_obj=obj, hcp_igt=i_gt,
+        ax_sig=sig2, ax_sch=sch2, ax_dirs=dirs2, ax_rot=rot2, ax_rot1d=rot2_1d, ax_DIFF=DIFF2)
+    print("lowlevel_rotation written; hcp solve:", sub, w / w.sum())
+
+
 if __name__ == "__main__":
+    lowlevel_rotation_cases()
     solver_cases()
     reference_test_vectors()
     rotation_and_fit_cases()

@@ -277,3 +277,13 @@ def fit_rows(tab, plan, Y, Kv, csf, ear, peaks, sig_csf=None, sig_ear=None):
         out[i] = fit_voxel(tab, plan, Y[i], Kv[i], csf[i], ear[i], peaks[i], maxfasc,
                            csf_on, ear_on, sig_csf, sig_ear)
     return out
+
+
+def lerp_rows(table, row_lo, row_hi, w_lo, w_hi, scale=None):
+    """The scipy interp1d two-weight lerp over explicit rows, as used by rotate_atom
+    (mfu:1423-1426) and rotate_atom_2Dprotocol (mfu:1678-1684): NumPy restatement of the
+    mfb_lerp_rows kernel, (V, M) plan arrays -> (V, M, N)."""
+    out = w_hi[..., None] * table[row_hi] + w_lo[..., None] * table[row_lo]
+    if scale is not None:
+        out = scale[..., None] * out
+    return out

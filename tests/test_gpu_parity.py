@@ -330,3 +330,75 @@ def test_fit_parallel_multi_gpu(ukbb):
                      csf_mask=ph.csf.astype(float), verbose=0, parallel=True)
     for p in one.param_names:
         assert np.array_equal(getattr(one, p), getattr(many, p)), p
+
+
+@pytest.fixture(scope="module")
+def lowlevel():
+    import os
+    from tests.conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "lowlevel_rotation.npz"))
+
+
+def test_lerp_rows_kernel_vs_oracle():
+    rng = np.random.default_rng(3)
+    R, N, V, M = 57, 33, 4, 19
+    table = rng.standard_normal((R, N))
+    rl, rh = rng.integers(0, R, (V, M)), rng.integers(0, R, (V, M))
+    wl, wh, sc = rng.standard_normal((V, M)), rng.standard_normal((V, M)), rng.random((V, M))
+    got = mfu._lerp_rows(table, rl, rh, wl, wh, sc)
+    assert np.array_equal(got, orc.lerp_rows(table, rl, rh, wl, wh, sc))
+    got = mfu._lerp_rows(table, rl, rh, wl, wh)
+    assert np.array_equal(got, orc.lerp_rows(table, rl, rh, wl, wh))
+
+
+def test_rotate_atom_matches_reference(lowlevel):
+    """mfu.rotate_atom on a subset of the reference's HCP Monte-Carlo dictionary."""
+    g = lowlevel
+    ref = np.array([0.0, 0.0, 1.0])
+    for d, want in zip(g["hcp_dirs"], g["hcp_rot"]):
+        got = mfu.rotate_atom(g["hcp_sig"], g["hcp_sch"], ref, d, float(g["hcp_DIFF"]), g["hcp_S0"],
+                              warnings=False)
+        assert got.shape == want.shape
+        assert np.allclose(got, want, rtol=1e-13, atol=0)
+    got1 = mfu.rotate_atom(g["hcp_sig"][:, 2], g["hcp_sch"], ref, g["hcp_dirs"][1], float(g["hcp_DIFF"]),
+                           g["hcp_S0"][:, 2], warnings=False)
+    assert got1.shape == g["hcp_rot1d"].shape and np.allclose(got1, g["hcp_rot1d"], rtol=1e-13, atol=0)
+    batch = mfu.rotate_atom(g["hcp_sig"], g["hcp_sch"], ref, g["hcp_dirs"], float(g["hcp_DIFF"]),
+                            g["hcp_S0"], warnings=False)
+    assert np.allclose(batch, g["hcp_rot"], rtol=1e-13, atol=0)
+    with pytest.raises(ValueError):
+        mfu.rotate_atom(g["hcp_sig"], g["hcp_sch"][:-1], ref, ref, 2e-9, g["hcp_S0"])
+
+
+def test_hcp_pipeline(lowlevel):
+    """The reference's test_hcp_dict (tests/integration/test_exhaustive_fingerprinting.py:163-249)
+    on a dictionary subset: rotate_atom x2 + CSF column + 3-block exhaustive solve, noiseless."""
+    g = lowlevel
+    ref = np.array([0.0, 0.0, 1.0])
+    n = g["hcp_sig"].shape[1]
+    D = np.zeros((g["hcp_sch"].shape[0], 2 * n + 1))
+    for k in range(2):
+        D[:, k * n:(k + 1) * n] = mfu.rotate_atom(g["hcp_sig"], g["hcp_sch"], ref, g["hcp_dirs"][1 + k],
+                                                  float(g["hcp_DIFF"]), g["hcp_S0"], warnings=False)
+    D[:, -1] = g["hcp_sig_csf"]
+    w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(D, g["hcp_y"].copy(), np.array([n, n, 1]))
+    i_gt = int(g["hcp_igt"])
+    assert np.all(sub[:2] == i_gt) and np.array_equal(sub, g["hcp_sub"])
+    assert np.allclose(w / w.sum(), [0.5, 0.3, 0.2])
+    assert np.allclose(w, g["hcp_w"], rtol=1e-9)
+
+
+def test_rotate_atom_2d_matches_reference(lowlevel):
+    g = lowlevel
+    ref = np.array([0.0, 0.0, 1.0])
+    for d, want in zip(g["ax_dirs"], g["ax_rot"]):
+        got = mfu.rotate_atom_2Dprotocol(g["ax_sig"], g["ax_sch"], ref, d, float(g["ax_DIFF"]))
+        assert got.shape == want.shape
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-300)
+    got1 = mfu.rotate_atom_2Dprotocol(g["ax_sig"][:, 1], g["ax_sch"], ref, g["ax_dirs"][2],
+                                      float(g["ax_DIFF"]))
+    assert got1.shape == g["ax_rot1d"].shape and np.allclose(got1, g["ax_rot1d"], rtol=1e-12)
+    bad = g["ax_sch"].copy()
+    bad[5, 2] = 0.1
+    with pytest.raises(ValueError, match="zeros for gz"):
+        mfu.rotate_atom_2Dprotocol(g["ax_sig"], bad, ref, ref, 2e-9)
