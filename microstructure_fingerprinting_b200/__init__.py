@@ -10,7 +10,8 @@ hand-written CUDA kernels (libmfb200.so, C ABI in include/mfb200.h); there is no
 fallback.
 """
 from .mf import MFModel, MFModelFit
+from .peaks import cleanup_2fascicles
 from . import mf_utils
 
 __version__ = "0.1.0"
-__all__ = ["MFModel", "MFModelFit", "mf_utils"]
+__all__ = ["MFModel", "MFModelFit", "cleanup_2fascicles", "mf_utils"]

@@ -274,7 +274,45 @@ def lowlevel_rotation_cases():
     print("lowlevel_rotation written; hcp solve:", sub, w / w.sum())
 
 
+def cleanup_cases():
+    """cleanup_2fascicles (mf.py:36-335) on random inputs in its three peak modes."""
+    rng = np.random.default_rng(404)
+    shape = (6, 5, 4)
+    mask = (rng.random(shape) < 0.85).astype(float)
+    f1 = rng.random(shape) * 0.8
+    f2 = rng.random(shape) * 0.6
+    f1.flat[:6] = [0.5, 0.05, 0.3, 0.1, 0.0, 0.19]
+    f2.flat[:6] = [0.5, 0.05, 0.1, 0.3, 0.0, 0.5]
+    u1 = rng.standard_normal(shape + (3,)); u1 /= np.linalg.norm(u1, axis=-1, keepdims=True)
+    u2 = rng.standard_normal(shape + (3,)); u2 /= np.linalg.norm(u2, axis=-1, keepdims=True)
+    near = rng.random(shape) < 0.25                    # nearly parallel pairs (merge branch)
+    u2[near] = u1[near] * rng.choice([-1.0, 1.0], size=near.sum())[:, None] + 0.05 * rng.standard_normal((near.sum(), 3))
+    u2 /= np.linalg.norm(u2, axis=-1, keepdims=True)
+    out = {"mask": mask, "f1": f1, "f2": f2, "u1": u1, "u2": u2}
+    pk, nf = refmf.cleanup_2fascicles(f1, f2, "peaks", u1, u2, mask)
+    out["peaks_pk"], out["peaks_nf"] = pk, nf
+    cl1 = np.stack([np.arccos(np.clip(u1[..., 2], -1, 1)), np.arctan2(u1[..., 1], u1[..., 0])], -1)
+    cl2 = np.stack([np.arccos(np.clip(u2[..., 2], -1, 1)), np.arctan2(u2[..., 1], u2[..., 0])], -1)
+    pk, nf = refmf.cleanup_2fascicles(None, None, "colat_longit", cl1, cl2, mask,
+                                      frac12=np.stack([f1, f2], -1))
+    out["cl1"], out["cl2"], out["colat_pk"], out["colat_nf"] = cl1, cl2, pk, nf
+
+    def tens(u):
+        DT = 1e-4 * np.eye(3) + 1.9e-3 * u[..., :, None] * u[..., None, :]
+        T = np.zeros(u.shape[:-1] + (1, 6))
+        T[..., 0, 0], T[..., 0, 1], T[..., 0, 2] = DT[..., 0, 0], DT[..., 0, 1], DT[..., 1, 1]
+        T[..., 0, 3], T[..., 0, 4], T[..., 0, 5] = DT[..., 0, 2], DT[..., 1, 2], DT[..., 2, 2]
+        return T
+    t1, t2 = tens(u1), tens(u2)
+    t2[0, 0, 0] = 0
+    pk, nf = refmf.cleanup_2fascicles(f1, f2, "tensor", t1, t2, mask)
+    out["t1"], out["t2"], out["tensor_pk"], out["tensor_nf"] = t1, t2, pk, nf
+    np.savez_compressed(os.path.join(OUT, "cleanup_cases.npz"), **out)
+    print("cleanup_cases written", np.unique(out["peaks_nf"], return_counts=True))
+
+
 if __name__ == "__main__":
+    cleanup_cases()
     lowlevel_rotation_cases()
     solver_cases()
     reference_test_vectors()

@@ -125,3 +125,21 @@ def test_reads_reference_style_nifti(tmp_path):
     vol, aff = nifti.load(p)
     assert vol.shape == (2, 2, 2) and vol[1, 0, 0] == 1.0 and vol[0, 1, 0] == 2.0
     assert np.allclose(aff, [[2, 0, 0, 5], [0, 2, 0, 6], [0, 0, 2, 7], [0, 0, 0, 1]])
+
+
+def test_cleanup_2fascicles_matches_reference():
+    from microstructure_fingerprinting_b200 import cleanup_2fascicles
+    from tests.conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "cleanup_cases.npz"))
+    pk, nf = cleanup_2fascicles(g["f1"], g["f2"], "peaks", g["u1"], g["u2"], g["mask"])
+    assert np.array_equal(pk, g["peaks_pk"]) and np.array_equal(nf, g["peaks_nf"])
+    pk, nf = cleanup_2fascicles(None, None, "colat_longit", g["cl1"], g["cl2"], g["mask"],
+                                frac12=np.stack([g["f1"], g["f2"]], -1))
+    assert np.array_equal(pk, g["colat_pk"]) and np.array_equal(nf, g["colat_nf"])
+    pk, nf = cleanup_2fascicles(g["f1"], g["f2"], "tensor", g["t1"], g["t2"], g["mask"])
+    assert np.array_equal(pk, g["tensor_pk"]) and np.array_equal(nf, g["tensor_nf"])
+    assert set(np.unique(nf)) <= {0.0, 1.0, 2.0}
+    with pytest.raises(ValueError):
+        cleanup_2fascicles(None, None, "peaks", g["u1"], g["u2"], g["mask"])
+    with pytest.raises(ValueError, match="Unknown peak mode"):
+        cleanup_2fascicles(g["f1"], g["f2"], "bogus", g["u1"], g["u2"], g["mask"])
