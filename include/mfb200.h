@@ -126,23 +126,26 @@ int mfb_solve_batch(int device, int64_t V, int M, int nblocks,
  *   y V*M, peaks V*3*maxfasc, K V (0..maxfasc), csf V, ear V (0/1 bytes)
  *   params_out V*P with P = 1 + 2*maxfasc + csf_on + 2*ear_on + 2, row layout of
  *   mf:375-381: [M0 | nu_k | ID_k | nu_csf | nu_ear ID_ear | MSE | R2].
- * flags: bit 0 = force the exact (reference-order) tier for every voxel.
+ * flags: bit 0 = force the exact (reference-order) tier for every voxel;
+ *        bit 1 = bracket the dominant kernel with CUDA events (mfb_fit_stats).
  */
 int mfb_fit(mfb_plan *plan, int64_t V, const double *y, const double *peaks,
             const int32_t *K, const uint8_t *csf, const uint8_t *ear,
             int maxfasc, int csf_on, int ear_on, double *params_out,
             int flags, void *stream);
 
-/* Same with HOST buffers: chunked, double-buffered H2D / compute / D2H on the
- * plan's own streams.  This is the call a non-PyTorch host would bind. */
+/* Same with HOST buffers: chunked H2D / compute / D2H on the plan's own stream
+ * (copies are < 1 % of the fit time).  This is the call a non-PyTorch host binds. */
 int mfb_fit_host(mfb_plan *plan, int64_t V, const double *y, const double *peaks,
                  const int32_t *K, const uint8_t *csf, const uint8_t *ear,
                  int maxfasc, int csf_on, int ear_on, double *params_out,
                  int flags);
 
-/* Per-plan counters of the last mfb_fit call: voxels solved by the fast
- * (DMMA screening) tier, voxels re-solved by the exact tier, per-stage device
- * milliseconds when timing was enabled.  out[8]. */
+/* Per-plan counters of the last mfb_fit / mfb_fit_host call, out[8]:
+ *   [0] voxels accepted by the fast (DMMA screening) tier, [1] voxels solved by the exact
+ *   tier, [2] ms in the dominant kernel (flags bit 1), [3] its launches, [4] voxels it
+ *   covered, [5] one-fascicle voxels (fused kernel), [6] fast-tier hand-overs caused by an
+ *   ill-conditioned competitor, [7] by a near tie. */
 int mfb_fit_stats(mfb_plan *plan, double *out, int n);
 
 #ifdef __cplusplus

@@ -335,23 +335,27 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             // fast tier: DMMA screening; uncertain voxels are redone by the exact tier
             const int64_t fsub = std::min<int64_t>(cnt, 8192);
             MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(dp, fsub)));
-            MFB_TRY(pl->redo.ensure(sizeof(int32_t) * (nv + 1)));
-            int32_t *redo_count = pl->redo.as<int32_t>();
-            int32_t *redo_list = redo_count + 1;
-            MFB_CUDA_TRY(cudaMemsetAsync(redo_count, 0, sizeof(int32_t), st));
+            MFB_TRY(pl->redo.ensure(sizeof(int32_t) * (nv + 8)));
+            int32_t *redo_count = pl->redo.as<int32_t>();   // [count, reasons[4], -, -, -, list...]
+            int32_t *reasons = redo_count + 1;
+            int32_t *redo_list = redo_count + 8;
+            MFB_CUDA_TRY(cudaMemsetAsync(redo_count, 0, 8 * sizeof(int32_t), st));
             for (int64_t s0 = 0; s0 < cnt; s0 += fsub) {
                 const int64_t ns = std::min(fsub, cnt - s0);
                 cudaEvent_t *ev = timed ? next_events() : nullptr;
                 MFB_TRY(launch_fast_search(dp, ns, ct, list + s0, peaks, pld, y, pl->fscratch.p,
-                                           pl->tuple.as<long long>(), redo_list, redo_count, st, ev));
+                                           pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev));
                 if (ev) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
             }
             MFB_TRY(launch_gather_from_table(dp, cnt, Kt, ct, et, peaks, pld, pl->tuple.as<long long>(),
                                              list, pl->asmall.as<double>(), pl->idx5.as<int32_t>(), st));
-            int32_t n_redo = 0;
-            MFB_CUDA_TRY(cudaMemcpyAsync(&n_redo, redo_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            int32_t head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            MFB_CUDA_TRY(cudaMemcpyAsync(head, redo_count, sizeof(head), cudaMemcpyDeviceToHost, st));
             MFB_CUDA_TRY(cudaStreamSynchronize(st));
+            const int32_t n_redo = head[0];
             pl->stats[0] += (double)(cnt - n_redo);
+            pl->stats[6] += head[2];          // ill-conditioned competitor
+            pl->stats[7] += head[3] + 1e-6 * head[4] ;  // near ties (+ 1e-6 * pair-independent branch)
             if (n_redo > 0) MFB_TRY(run_exact(redo_list, n_redo, false));
         } else if (!(flags & 1) && single_fascicle_supported(dp, Kt, ct, et) && list) {
             // one fascicle: fused rotation + closed forms in the reference's arithmetic

@@ -135,8 +135,8 @@ bool fast_supported(const DevPlan &p, int K, int csf, int ear);
 size_t fast_scratch_bytes(const DevPlan &p, int64_t V);
 int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_list,
                        const double *peaks, int peaks_ld, const double *y, void *scratch,
-                       long long *tuple, int32_t *redo_list, int32_t *redo_count, cudaStream_t st,
-                       cudaEvent_t *ev);
+                       long long *tuple, int32_t *redo_list, int32_t *redo_count, int32_t *reasons,
+                       cudaStream_t st, cudaEvent_t *ev);
 
 // solve_batch helpers
 int launch_unpack_solution(int64_t V, int nb, const double *w5, const int32_t *idx5,

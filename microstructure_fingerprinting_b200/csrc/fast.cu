@@ -64,6 +64,7 @@ struct FastArgs {
     long long *tuple;  // [row]
     int32_t *redo_list;  // voxels handed to the exact tier
     int32_t *redo_count;
+    int32_t *reasons;    // [4] why voxels were handed over: no pair, ill-conditioned, near tie, pair-independent branch
 };
 
 __device__ __forceinline__ int search_left(const double *xs, int n, double x)
@@ -648,14 +649,16 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
         }
     }
     bool certain = I >= 0;
+    int reason = certain ? -1 : 0;
     for (int t = 0; t < a.ntI && certain; t++) {
         const int64_t o = v * a.ntI + t;
-        if (a.cta_ill[o] >= G - tolG) certain = false;
-        if (t == best_t) { if (a.cta_flag[o]) certain = false; continue; }
-        if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] >= G - tolG) certain = false;
+        if (a.cta_ill[o] >= G - tolG) { certain = false; reason = 1; }
+        if (t == best_t) { if (a.cta_flag[o]) { certain = false; reason = 2; } continue; }
+        if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] >= G - tolG) { certain = false; reason = 2; }
     }
     // pair-independent branches (single atoms, atom + CSF, CSF alone) must be clearly worse
-    if (certain && !(G - tolG > gpre + 16.0 * c0)) certain = false;
+    if (certain && !(G - tolG > gpre + 16.0 * c0)) { certain = false; reason = 3; }
+    if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
     const int64_t row = a.vox_list[v];
     if (certain) {
         a.tuple[row] = (long long)I;
@@ -693,7 +696,8 @@ size_t fast_scratch_bytes(const DevPlan &p, int64_t V)
 
 int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_list,
                        const double *peaks, int peaks_ld, const double *y, void *scratch,
-                       long long *tuple, int32_t *redo_list, int32_t *redo_count, cudaStream_t st,
+                       long long *tuple, int32_t *redo_list, int32_t *redo_count, int32_t *reasons,
+                       cudaStream_t st,
                        cudaEvent_t *ev)
 {
     if (V == 0) return MFB_OK;
@@ -717,7 +721,7 @@ int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_
     a.cta_ill = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_idx = (int *)q; q += al256(sizeof(int) * V * a.ntI);
     a.cta_flag = (int *)q;
-    a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count;
+    a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count; a.reasons = reasons;
 
     const size_t smem_prep = sizeof(double) * (4 * p.M + 32) + sizeof(int) * 2 * p.M;
     MFB_LAUNCH(k_fast_prep, dim3((unsigned)V, 2), 256, smem_prep, st, a);
