@@ -218,24 +218,53 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     MFB_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     // sub-batches keep the scratch bounded
+    const bool fast = fast_supported_explicit(M, bs) && !getenv("MFB_SOLVE_EXACT");
     size_t per_vox = exact_scratch_bytes(1, bs) + 4096;
-    int64_t sub = std::max<int64_t>(1, std::min<int64_t>(65535, ((size_t)1 << 30) / per_vox));
+    if (fast) per_vox = std::max(per_vox, fast_scratch_bytes(M, bs.size[0], bs.size[1], 1) + 4096);
+    int64_t sub = std::max<int64_t>(1, std::min<int64_t>(fast ? 8192 : 65535, ((size_t)1 << 30) / per_vox));
     sub = std::min(sub, V);
-    Buf scratch, tuple, asmall, idx5, w5;
+    Buf scratch, tuple, asmall, idx5, w5, redo;
     int rc = MFB_OK;
-    auto cleanup = [&]() { scratch.release(); tuple.release(); asmall.release(); idx5.release(); w5.release(); };
-    if ((rc = scratch.ensure(exact_scratch_bytes(sub, bs))) || (rc = tuple.ensure(sizeof(long long) * sub)) ||
+    auto cleanup = [&]() { scratch.release(); tuple.release(); asmall.release(); idx5.release(); w5.release(); redo.release(); };
+    size_t sbytes = exact_scratch_bytes(sub, bs);
+    if (fast) sbytes = std::max(sbytes, fast_scratch_bytes(M, bs.size[0], bs.size[1], sub));
+    if ((rc = scratch.ensure(sbytes)) || (rc = tuple.ensure(sizeof(long long) * sub)) ||
         (rc = asmall.ensure(sizeof(double) * sub * M * kMaxBlocks)) ||
-        (rc = idx5.ensure(sizeof(int32_t) * sub * kMaxBlocks)) || (rc = w5.ensure(sizeof(double) * sub * kMaxBlocks))) {
+        (rc = idx5.ensure(sizeof(int32_t) * sub * kMaxBlocks)) || (rc = w5.ensure(sizeof(double) * sub * kMaxBlocks)) ||
+        (rc = redo.ensure(sizeof(int32_t) * (sub + 8)))) {
         cleanup();
         return rc;
     }
+    DevPlan dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    dummy.M = M;
     for (int64_t v0 = 0; v0 < V && rc == MFB_OK; v0 += sub) {
         int64_t nv = std::min(sub, V - v0);
         const double *Av = A + v0 * strideA;
         const double *yv = y + v0 * M;
-        rc = launch_exact_search(nv, M, bs, Av, lda, strideA, yv, M, nullptr, scratch.p,
-                                 tuple.as<long long>(), st);
+        if (fast) {
+            // DMMA screening on the explicit dictionaries; uncertain voxels fall through to the
+            // reference-order search below
+            FastProblem fp;
+            fp.src = 1; fp.N1 = bs.size[0]; fp.N2 = bs.size[1]; fp.A = Av; fp.lda = lda; fp.strideA = strideA;
+            fp.start1 = bs.start[0]; fp.start2 = bs.start[1]; fp.start3 = bs.nb == 3 ? bs.start[2] : 0;
+            fp.csf = bs.nb == 3;
+            int32_t *redo_count = redo.as<int32_t>(), *reasons = redo_count + 1, *redo_list = redo_count + 8;
+            if (cudaMemsetAsync(redo_count, 0, 8 * sizeof(int32_t), st) != cudaSuccess ||
+                cudaMemsetAsync(tuple.p, 0xff, sizeof(long long) * nv, st) != cudaSuccess) { rc = MFB_ECUDA; break; }
+            rc = launch_fast_search(dummy, fp, nv, nullptr, nullptr, 0, yv, scratch.p, tuple.as<long long>(),
+                                    redo_list, redo_count, reasons, st, nullptr);
+            if (rc) break;
+            int32_t n_redo = 0;
+            if (cudaMemcpyAsync(&n_redo, redo_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) { rc = MFB_ECUDA; break; }
+            if (n_redo > 0)
+                rc = launch_exact_search(n_redo, M, bs, Av, lda, strideA, yv, M, redo_list, scratch.p,
+                                         tuple.as<long long>(), st, nullptr, 1);
+        } else {
+            rc = launch_exact_search(nv, M, bs, Av, lda, strideA, yv, M, nullptr, scratch.p,
+                                     tuple.as<long long>(), st);
+        }
         if (rc) break;
         rc = launch_gather_from_A(nv, M, bs, Av, lda, strideA, tuple.as<long long>(), nullptr,
                                   asmall.as<double>(), idx5.as<int32_t>(), st);
@@ -334,7 +363,10 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
         if (!(flags & 1) && fast_supported(dp, Kt, ct, et)) {
             // fast tier: DMMA screening; uncertain voxels are redone by the exact tier
             const int64_t fsub = std::min<int64_t>(cnt, 8192);
-            MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(dp, fsub)));
+            MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(dp.M, dp.N, dp.N, fsub)));
+            FastProblem fp;
+            memset(&fp, 0, sizeof(fp));
+            fp.src = 0; fp.N1 = fp.N2 = dp.N; fp.csf = ct;
             MFB_TRY(pl->redo.ensure(sizeof(int32_t) * (nv + 8)));
             int32_t *redo_count = pl->redo.as<int32_t>();   // [count, reasons[4], -, -, -, list...]
             int32_t *reasons = redo_count + 1;
@@ -343,7 +375,7 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             for (int64_t s0 = 0; s0 < cnt; s0 += fsub) {
                 const int64_t ns = std::min(fsub, cnt - s0);
                 cudaEvent_t *ev = timed ? next_events() : nullptr;
-                MFB_TRY(launch_fast_search(dp, ns, ct, list + s0, peaks, pld, y, pl->fscratch.p,
+                MFB_TRY(launch_fast_search(dp, fp, ns, list + s0, peaks, pld, y, pl->fscratch.p,
                                            pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev));
                 if (ev) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
             }

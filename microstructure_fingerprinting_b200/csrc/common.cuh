@@ -91,7 +91,7 @@ size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs);
 int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, int64_t lda,
                         int64_t strideA, const double *y, int64_t y_ld,
                         const int32_t *vox_list, void *scratch, long long *tuple_out,
-                        cudaStream_t st, cudaEvent_t *ev = nullptr);
+                        cudaStream_t st, cudaEvent_t *ev = nullptr, int a_by_row = 0);
 
 // Copy the winning tuple's columns into Asmall[row(v)] (M x kMaxBlocks, row-major) and
 // decode the per-block indices into idx_sub[row(v)*kMaxBlocks + b].
@@ -131,9 +131,18 @@ int launch_single_fascicle(const DevPlan &p, int64_t nvox, const int32_t *vox_li
 // ------------------------- fast tier (fast.cu) -------------------------------------
 // DMMA screening for 2-fascicle voxels ([N,N] and [N,N,1]); voxels whose winner is not
 // certain are appended to redo_list (exact tier).
+struct FastProblem {
+    int src;            // 0: rotate from the plan's lookup table; 1: explicit dictionaries
+    int N1, N2;         // atoms of the two searched blocks
+    const double *A;    // explicit: voxel row r reads A + r*strideA, (M, lda) row-major
+    int64_t lda, strideA;
+    int start1, start2, start3;
+    int csf;            // a third, single-column block is present
+};
 bool fast_supported(const DevPlan &p, int K, int csf, int ear);
-size_t fast_scratch_bytes(const DevPlan &p, int64_t V);
-int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_list,
+bool fast_supported_explicit(int M, const BlockSpec &bs);
+size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V);
+int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const int32_t *vox_list,
                        const double *peaks, int peaks_ld, const double *y, void *scratch,
                        long long *tuple, int32_t *redo_list, int32_t *redo_count, int32_t *reasons,
                        cudaStream_t st, cudaEvent_t *ev);

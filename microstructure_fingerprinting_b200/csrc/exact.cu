@@ -322,7 +322,14 @@ struct ExactArgs {
     double *colsq, *ady, *ysq, *cross13, *cross23, *tile_res;
     long long *tile_idx;
     int ntiles;
+    int a_by_row;   // dictionaries indexed by the voxel's row (vox_list) instead of its local index
 };
+
+__device__ __forceinline__ const double *ex_A(const ExactArgs &a, int64_t v)
+{
+    const int64_t r = (a.a_by_row && a.vox_list) ? (int64_t)a.vox_list[v] : v;
+    return a.A + r * a.strideA;
+}
 
 // grid (ceil(ntot/128), V); dynamic smem M doubles (y)
 __global__ void __launch_bounds__(128) k_colstats(ExactArgs a)
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(128) k_colstats(ExactArgs a)
     for (int k = threadIdx.x; k < a.M; k += blockDim.x) ys[k] = y[k];
     __syncthreads();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const double *A = a.A + v * a.strideA;
+    const double *A = ex_A(a, v);
     if (c < a.bs.ntot) {
         double sq = 0.0, dy = 0.0;
         for (int k = 0; k < a.M; k++) {
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(128) k_cross3(ExactArgs a)
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)(N1 + N2) * N3) return;
     const int i = (int)(t / N3), i3 = (int)(t % N3);
-    const double *A = a.A + v * a.strideA;
+    const double *A = ex_A(a, v);
     const int c3 = a.bs.start[2] + i3;
     const int c = i < N1 ? a.bs.start[0] + i : a.bs.start[1] + (i - N1);
     double s = 0.0;
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
     const int N1 = a.bs.size[0], N2 = a.bs.size[1];
     const int tI = blockIdx.y * EX_T, tJ = blockIdx.x * EX_T;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const double *A = a.A + v * a.strideA;
+    const double *A = ex_A(a, v);
     const double *B1 = A + a.bs.start[0], *B2 = A + a.bs.start[1];
     const double *yv = a.y + row * a.y_ld;
     const int M = a.M;
@@ -649,7 +656,7 @@ __global__ void __launch_bounds__(128) k_cross_small(MultiArgs ma, double *cross
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)(N12 + S) * S) return;
     const int i = (int)(t / S), sidx = (int)(t % S);
-    const double *A = a.A + v * a.strideA;
+    const double *A = ex_A(a, v);
     const int cs = a.bs.start[2] + sidx;
     const int c = i < N12 ? i : a.bs.start[2] + (i - N12);
     double acc = 0.0;
@@ -668,7 +675,7 @@ __global__ void __launch_bounds__(256) k_pairs_multi(MultiArgs ma)
     const int N1 = a.bs.size[0], N2 = a.bs.size[1], nb = a.bs.nb, S = ma.S;
     const int tI = blockIdx.y * EX_T, tJ = blockIdx.x * EX_T;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const double *A = a.A + v * a.strideA;
+    const double *A = ex_A(a, v);
     const double *B1 = A + a.bs.start[0], *B2 = A + a.bs.start[1];
     const int M = a.M;
     double acc[4][4];
@@ -803,7 +810,8 @@ size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs)
 
 int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, int64_t lda,
                         int64_t strideA, const double *y, int64_t y_ld, const int32_t *vox_list,
-                        void *scratch, long long *tuple_out, cudaStream_t st, cudaEvent_t *ev)
+                        void *scratch, long long *tuple_out, cudaStream_t st, cudaEvent_t *ev,
+                        int a_by_row)
 {
     if (V == 0) return MFB_OK;
     if (bs.nb < 1 || bs.nb > kMaxBlocks) {
@@ -817,6 +825,7 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
     ExactArgs a;
     a.M = M; a.bs = bs; a.A = A; a.lda = lda; a.strideA = strideA; a.y = y; a.y_ld = y_ld;
     a.vox_list = vox_list;
+    a.a_by_row = a_by_row;
     a.ntiles = exact_ntiles(bs);
     char *p = (char *)scratch;
     a.colsq = (double *)p; p += align256(sizeof(double) * V * bs.ntot);

@@ -42,10 +42,16 @@ namespace mfb {
 static constexpr double kIllDet = 1e-4;
 
 struct FastArgs {
-    DevPlan p;
+    DevPlan p;         // table source: rotation plan; explicit source: only p.M is used
+    int src;           // 0: sub-dictionaries rotated from the lookup table (fit path)
+                       // 1: explicit dictionaries A (mfb_solve_batch)
+    int N1, N2;        // atoms of the two searched blocks
+    const double *A;   // explicit source: voxel row r reads A + r*strideA, (M, lda) row-major
+    int64_t lda, strideA;
+    int start1, start2, start3;  // first column of block 1, block 2 and of the third (1-column) block
     int csf;
     int Mp;            // M padded to a multiple of 4
-    int Npad;          // N padded to a multiple of FT_TJ
+    int Npad;          // max(N1, N2) padded to a multiple of FT_TJ
     int ntI;           // i1 tiles per voxel
     int debug;            // timing experiments only (MFB_FAST_DEBUG): 1 skip epilogue, 2 skip gathers
     const int32_t *vox_list;
@@ -107,33 +113,39 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
 {
     extern __shared__ double sm[];
     const DevPlan &p = a.p;
-    const int M = p.M, N = p.N;
+    const int M = p.M;
     double *wl = sm, *wh = sm + M, *ys = sm + 2 * M, *cs = sm + 3 * M, *red = sm + 4 * M;
     int *rl = (int *)(red + 32), *rh = rl + M;
     const int64_t v = blockIdx.x;
     const int k = blockIdx.y;
-    const int64_t row = a.vox_list[v];
-    const double *u = a.peaks + row * a.peaks_ld + 3 * k;
-    const double ux = u[0], uy = u[1], uz = u[2];
+    const int Nk = k ? a.N2 : a.N1;
+    const int64_t row = a.vox_list ? a.vox_list[v] : v;
+    const double *Ar = a.src ? a.A + row * a.strideA : nullptr;
+    if (!a.src) {
+        const double *u = a.peaks + row * a.peaks_ld + 3 * k;
+        const double ux = u[0], uy = u[1], uz = u[2];
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            // same expression order as the exact tier (exact.cu dir_dot / shell_lerp)
+            double x = fabs(__dadd_rn(__dadd_rn(__dmul_rn(p.gdir[3 * m], ux), __dmul_rn(p.gdir[3 * m + 1], uy)),
+                                      __dmul_rn(p.gdir[3 * m + 2], uz)));
+            int s = p.shell_lo[m];
+            const double *xs = p.nodes + p.off[s];
+            int n = p.off[s + 1] - p.off[s];
+            int j = search_left(xs, n, x);
+            j = j < 1 ? 1 : (j > n - 1 ? n - 1 : j);
+            double den = __dsub_rn(xs[j], xs[j - 1]);
+            rl[m] = p.off[s] + j - 1;
+            rh[m] = p.off[s] + j;
+            wh[m] = __ddiv_rn(__dsub_rn(x, xs[j - 1]), den);
+            wl[m] = __ddiv_rn(__dsub_rn(xs[j], x), den);
+            int64_t o = ((v * 2 + k) * M + m) * 2;
+            a.ip_rows[o] = rl[m]; a.ip_rows[o + 1] = rh[m];
+            a.ip_w[o] = wl[m]; a.ip_w[o + 1] = wh[m];
+        }
+    }
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        // same expression order as the exact tier (exact.cu dir_dot / shell_lerp)
-        double x = fabs(__dadd_rn(__dadd_rn(__dmul_rn(p.gdir[3 * m], ux), __dmul_rn(p.gdir[3 * m + 1], uy)),
-                                  __dmul_rn(p.gdir[3 * m + 2], uz)));
-        int s = p.shell_lo[m];
-        const double *xs = p.nodes + p.off[s];
-        int n = p.off[s + 1] - p.off[s];
-        int j = search_left(xs, n, x);
-        j = j < 1 ? 1 : (j > n - 1 ? n - 1 : j);
-        double den = __dsub_rn(xs[j], xs[j - 1]);
-        rl[m] = p.off[s] + j - 1;
-        rh[m] = p.off[s] + j;
-        wh[m] = __ddiv_rn(__dsub_rn(x, xs[j - 1]), den);
-        wl[m] = __ddiv_rn(__dsub_rn(xs[j], x), den);
         ys[m] = a.y[row * M + m];
-        cs[m] = a.csf ? p.sig_csf[m] : 0.0;
-        int64_t o = ((v * 2 + k) * M + m) * 2;
-        a.ip_rows[o] = rl[m]; a.ip_rows[o + 1] = rh[m];
-        a.ip_w[o] = wl[m]; a.ip_w[o + 1] = wh[m];
+        cs[m] = !a.csf ? 0.0 : (a.src ? Ar[(size_t)m * a.lda + a.start3] : p.sig_csf[m]);
     }
     __syncthreads();
     double y_sq = 0.0, A33 = 0.0, Y3 = 0.0;
@@ -147,10 +159,12 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     double gbest = 0.0;
     for (int i = threadIdx.x; i < a.Npad; i += blockDim.x) {
         double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0};
-        if (i < N) {
+        if (i < Nk) {
             double sq = 0.0, dy = 0.0, d3 = 0.0;
+            const double *Ac = a.src ? Ar + (k ? a.start2 : a.start1) + i : nullptr;
             for (int m = 0; m < M; m++) {
-                double d = fma(wh[m], p.table[(size_t)rh[m] * N + i], wl[m] * p.table[(size_t)rl[m] * N + i]);
+                double d = a.src ? Ac[(size_t)m * a.lda]
+                                 : fma(wh[m], p.table[(size_t)rh[m] * p.N + i], wl[m] * p.table[(size_t)rl[m] * p.N + i]);
                 sq = fma(d, d, sq);
                 dy = fma(d, ys[m], dy);
                 d3 = fma(d, cs[m], d3);
@@ -260,6 +274,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     extern __shared__ __align__(16) double smem[];
     const DevPlan &p = a.p;
     const int M = p.M, N = p.N, Mp = a.Mp;
+    const int N1 = a.N1, N2 = a.N2;
     double *D1s = smem;                                   // [Mp][FT_S1]
     double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS][Mp][FT_S2]
     double *colq = D2s + (size_t)FT_NS * Mp * FT_S2;      // [FT_NS][5][FT_TJ]  z, beta, kappa, gamma, zu
@@ -287,10 +302,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const double gpre = fmax(vp[5], vp[6]);
     const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
     const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
-    const int ntJ = a.Npad / FT_TJ;
+    const int ntJ = (N2 + FT_TJ - 1) / FT_TJ;
+    const int64_t row = a.vox_list ? a.vox_list[v] : v;
+    const double *Ar = a.src ? a.A + row * a.strideA : nullptr;
 
     for (int m = tid; m < Mp; m += FT_THREADS) {
-        if (m < M) {
+        if (m < M && a.src) {
+            // explicit dictionaries: rows are read directly (weights 1 / 0, row index = m)
+            r1l[m] = r1h[m] = r2l[m] = r2h[m] = m;
+            w1l[m] = w2l[m] = 0.0; w1h[m] = w2h[m] = 1.0;
+            cs[m] = CSF ? Ar[(size_t)m * a.lda + a.start3] : 0.0;
+        } else if (m < M) {
             int64_t o = ((v * 2 + 0) * M + m) * 2, o2 = ((v * 2 + 1) * M + m) * 2;
             r1l[m] = a.ip_rows[o]; r1h[m] = a.ip_rows[o + 1];
             w1l[m] = a.ip_w[o]; w1h[m] = a.ip_w[o + 1];
@@ -321,18 +343,20 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
             if ((a.debug & 2) && jt >= FT_NS) { mbar_arrive(&s_full[st]); continue; }
             const int j = jt * FT_TJ + jj;
-            const bool ok = j < N;
+            const bool ok = j < N2;
             const double csc = ok ? __ldg(cp2 + j) : 0.0;
             const double cal = (CSF && ok) ? __ldg(cp2 + (size_t)a.Npad + j) : 0.0;
-            const double *Tc = p.table + (ok ? j : 0);
+            // source rows: lookup table (stride N) or this voxel's dictionary (stride lda)
+            const double *Tc = a.src ? Ar + a.start2 + (ok ? j : 0) : p.table + (ok ? j : 0);
+            const size_t rs = a.src ? (size_t)a.lda : (size_t)N;
             double *dst = D2s + (size_t)st * Mp * FT_S2 + jj;
             for (int mb = mrow0; mb < Mp; mb += RS * UB) {
                 double lo[UB], hi[UB];
 #pragma unroll
                 for (int q = 0; q < UB; q++) {
                     const int m = min(mb + RS * q, Mp - 1);   // rows >= M carry zero weights
-                    lo[q] = __ldg(Tc + (size_t)r2l[m] * N);
-                    hi[q] = __ldg(Tc + (size_t)r2h[m] * N);
+                    lo[q] = __ldg(Tc + (size_t)r2l[m] * rs);
+                    hi[q] = __ldg(Tc + (size_t)r2h[m] * rs);
                 }
                 // three passes of independent FP64 ops (the FP64 pipe is shared with the
                 // consumers' DMMA stream: dependent chains would serialise on its latency)
@@ -368,10 +392,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     {
         const int ii = tid & (FT_TI - 1);
         const int i = i0 + ii;
-        const bool ok = i < N;
+        const bool ok = i < N1;
         const double sc = ok ? cp1[i] : 0.0;
         const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
-        const double *Tc = p.table + (ok ? i : 0);
+        const double *Tc = a.src ? Ar + a.start1 + (ok ? i : 0) : p.table + (ok ? i : 0);
+        const size_t rs = a.src ? (size_t)a.lda : (size_t)N;
         constexpr int RS = FT_CONS / FT_TI;               // rows per pass (2)
         constexpr int UB = 18;                             // loads in flight per thread: 2*UB
         for (int mb = tid / FT_TI; mb < Mp; mb += RS * UB) {
@@ -381,8 +406,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 const int m = mb + RS * q;
                 lo[q] = 0.0; hi[q] = 0.0;
                 if (ok && m < M) {
-                    lo[q] = __ldg(Tc + (size_t)r1l[m] * N);
-                    hi[q] = __ldg(Tc + (size_t)r1h[m] * N);
+                    lo[q] = __ldg(Tc + (size_t)r1l[m] * rs);
+                    hi[q] = __ldg(Tc + (size_t)r1h[m] * rs);
                 }
             }
 #pragma unroll
@@ -404,7 +429,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 #pragma unroll
     for (int mt = 0; mt < 2; mt++) {
         const int i = i0 + wrow + 8 * mt + g;
-        const bool ok = i < N;
+        const bool ok = i < N1;
         z1[mt] = ok ? cp1[(size_t)2 * a.Npad + i] : 0.0;
         b1[mt] = (CSF && ok) ? cp1[(size_t)3 * a.Npad + i] : 0.0;
         k1[mt] = (CSF && ok) ? cp1[(size_t)4 * a.Npad + i] : 0.0;
@@ -412,7 +437,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
     }
 
-    const int mtv = max(0, min(2, (N - (i0 + wrow) + 7) >> 3));   // valid 8-row blocks of this warp
+    const int mtv = max(0, min(2, (N1 - (i0 + wrow) + 7) >> 3));   // valid 8-row blocks of this warp
 
     // thread-local best (central gain gb, tolerance tb) and the shared screening threshold
     double gb = -1.0, tb = 0.0, thr = fmax(gpre - c0, 0.0), gill = -1.0;
@@ -433,7 +458,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         const double *B_ = D2s + (size_t)st * Mp * FT_S2 + (size_t)t4 * FT_S2 + g;
         // 8-atom blocks of this tile that hold real atoms (warp-uniform): the last i1 / i2
         // tiles of a dictionary whose size is not a multiple of the tile are partly empty
-        const int ntv = min(4, (N - jt * FT_TJ + 7) >> 3);
+        const int ntv = min(4, (N2 - jt * FT_TJ + 7) >> 3);
         if (ntv == 4 && mtv == 2) {
 #pragma unroll 3
             for (int ks = 0; ks < Mp / 4; ks++) {
@@ -574,7 +599,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                     if (gq > gb) {
                         flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
                         gb = gq; tb = tq;
-                        bidx = (i0 + wrow + 8 * mt + g) * N + jt * FT_TJ + c;
+                        bidx = (i0 + wrow + 8 * mt + g) * N2 + jt * FT_TJ + c;
                     } else if (!(gb > gq + wide)) {
                         flag = 1;
                     }
@@ -659,7 +684,7 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
     // pair-independent branches (single atoms, atom + CSF, CSF alone) must be clearly worse
     if (certain && !(G - tolG > gpre + 16.0 * c0)) { certain = false; reason = 3; }
     if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
-    const int64_t row = a.vox_list[v];
+    const int64_t row = a.vox_list ? a.vox_list[v] : v;
     if (certain) {
         a.tuple[row] = (long long)I;
     } else {
@@ -680,13 +705,25 @@ bool fast_supported(const DevPlan &p, int K, int csf, int ear)
            (csf == 0 || p.sig_csf);
 }
 
-size_t fast_scratch_bytes(const DevPlan &p, int64_t V)
+// Explicit dictionaries (mfb_solve_batch): two searched blocks, optionally a third block of
+// exactly one column (the CSF-like compartment).
+bool fast_supported_explicit(int M, const BlockSpec &bs)
 {
-    const int Npad = (p.N + FT_TJ - 1) / FT_TJ * FT_TJ;
-    const int ntI = (p.N + FT_TI - 1) / FT_TI;
+    const int Mp = (M + 3) & ~3;
+    if (Mp > 112 || bs.nb < 2 || bs.nb > 3) return false;
+    if (bs.nb == 3 && bs.size[2] != 1) return false;
+    if (bs.size[0] < 8 || bs.size[1] < 8) return false;
+    return (long long)bs.size[0] * bs.size[1] < 2000000000LL;
+}
+
+size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V)
+{
+    const int Nmax = N1 > N2 ? N1 : N2;
+    const int Npad = (Nmax + FT_TJ - 1) / FT_TJ * FT_TJ;
+    const int ntI = (N1 + FT_TI - 1) / FT_TI;
     size_t s = 0;
-    s += al256(sizeof(int) * V * 2 * p.M * 2);
-    s += al256(sizeof(double) * V * 2 * p.M * 2);
+    s += al256(sizeof(int) * V * 2 * M * 2);
+    s += al256(sizeof(double) * V * 2 * M * 2);
     s += al256(sizeof(double) * V * 2 * FT_NPAR * Npad);
     s += al256(sizeof(double) * V * 8);
     s += 3 * al256(sizeof(double) * V * ntI);
@@ -694,18 +731,21 @@ size_t fast_scratch_bytes(const DevPlan &p, int64_t V)
     return s;
 }
 
-int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_list,
+int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const int32_t *vox_list,
                        const double *peaks, int peaks_ld, const double *y, void *scratch,
                        long long *tuple, int32_t *redo_list, int32_t *redo_count, int32_t *reasons,
-                       cudaStream_t st,
-                       cudaEvent_t *ev)
+                       cudaStream_t st, cudaEvent_t *ev)
 {
     if (V == 0) return MFB_OK;
     FastArgs a;
-    a.p = p; a.csf = csf;
+    a.p = p; a.csf = fp.csf;
+    a.src = fp.src; a.N1 = fp.N1; a.N2 = fp.N2;
+    a.A = fp.A; a.lda = fp.lda; a.strideA = fp.strideA;
+    a.start1 = fp.start1; a.start2 = fp.start2; a.start3 = fp.start3;
     a.Mp = (p.M + 3) & ~3;
-    a.Npad = (p.N + FT_TJ - 1) / FT_TJ * FT_TJ;
-    a.ntI = (p.N + FT_TI - 1) / FT_TI;
+    const int Nmax = fp.N1 > fp.N2 ? fp.N1 : fp.N2;
+    a.Npad = (Nmax + FT_TJ - 1) / FT_TJ * FT_TJ;
+    a.ntI = (fp.N1 + FT_TI - 1) / FT_TI;
     {
         const char *d = getenv("MFB_FAST_DEBUG");
         a.debug = d ? atoi(d) : 0;
@@ -733,12 +773,24 @@ int launch_fast_search(const DevPlan &p, int64_t V, int csf, const int32_t *vox_
         return MFB_EUNSUPPORTED;
     }
     // per device / context attribute: set on every launch (microseconds)
-    if (csf) MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (fp.csf) MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
-    dim3 grid(a.ntI, (unsigned)V);
-    if (csf) MFB_LAUNCH(k_fast_pairs<1>, grid, FT_THREADS, smem, st, a);
-    else MFB_LAUNCH(k_fast_pairs<0>, grid, FT_THREADS, smem, st, a);
+    const int64_t maxy = 65535;
+    for (int64_t v0 = 0; v0 < V; v0 += maxy) {
+        FastArgs b = a;
+        const int64_t nv = V - v0 < maxy ? V - v0 : maxy;
+        // kernels index their scratch by the local voxel: shift every per-voxel pointer
+        b.ip_rows += v0 * 2 * p.M * 2; b.ip_w += v0 * 2 * p.M * 2;
+        b.colp += v0 * 2 * FT_NPAR * a.Npad; b.voxp += v0 * 8;
+        b.cta_gain += v0 * a.ntI; b.cta_tol += v0 * a.ntI; b.cta_ill += v0 * a.ntI;
+        b.cta_idx += v0 * a.ntI; b.cta_flag += v0 * a.ntI;
+        if (vox_list) b.vox_list = vox_list + v0;
+        else { b.y = y + v0 * p.M; b.A = fp.A ? fp.A + v0 * fp.strideA : nullptr; b.tuple = tuple + v0; }
+        dim3 grid(a.ntI, (unsigned)nv);
+        if (fp.csf) MFB_LAUNCH(k_fast_pairs<1>, grid, FT_THREADS, smem, st, b);
+        else MFB_LAUNCH(k_fast_pairs<0>, grid, FT_THREADS, smem, st, b);
+    }
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     MFB_LAUNCH(k_fast_select, (unsigned)((V + 127) / 128), 128, 0, st, a, V);
     return MFB_OK;

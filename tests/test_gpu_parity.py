@@ -402,3 +402,30 @@ def test_rotate_atom_2d_matches_reference(lowlevel):
     bad[5, 2] = 0.1
     with pytest.raises(ValueError, match="zeros for gz"):
         mfu.rotate_atom_2Dprotocol(g["ax_sig"], bad, ref, ref, 2e-9)
+
+
+@pytest.mark.parametrize("sizes", [[800, 800], [800, 800, 1], [300, 520]])
+def test_solve_batch_fast_equals_exact(sizes, monkeypatch):
+    """BASELINE config 2 shape (M = 100, ~800 atoms per fascicle, explicit per-voxel
+    dictionaries): the DMMA screening path of mfb_solve_batch must return exactly what the
+    reference-order search returns."""
+    rng = np.random.default_rng(sum(sizes))
+    V, M, nt = 48, 100, int(np.sum(sizes))
+    base = rng.random((M, nt)) * np.exp(-3.0 * rng.random((1, nt)) * np.linspace(0, 1, M)[:, None])
+    A = base[None] * (1.0 + 0.05 * rng.standard_normal((V, M, nt)))
+    st = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    Y = np.stack([A[v][:, st + np.array([rng.integers(0, n) for n in sizes])] @ rng.random(len(sizes))
+                  for v in range(V)])
+    Y += 0.02 * rng.standard_normal(Y.shape)
+    fast = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
+    exact = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+    for f, e in zip(fast, exact):
+        assert np.array_equal(f, e)
+    # shared dictionary (strideA = 0)
+    monkeypatch.delenv("MFB_SOLVE_EXACT")
+    fast = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))
+    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
+    exact = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))
+    for f, e in zip(fast, exact):
+        assert np.array_equal(f, e)
