@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfb200.so")
+LIB_PATH = os.environ.get("MFB_LIB") or os.path.join(_HERE, "libmfb200.so")   # MFB_LIB: A/B builds
 
 MFB_OK, MFB_EINVAL, MFB_ECUDA, MFB_ENOMEM, MFB_EUNSUPPORTED = 0, -1, -2, -3, -4
 

@@ -268,7 +268,7 @@ __device__ __forceinline__ void consumer_sync()
 // table, rotate / project / normalise them and fill a 3-stage shared-memory ring.  full[] /
 // empty[] mbarriers are the only synchronisation inside the tile loop, so consumer warps
 // drift apart and one warp's scalar epilogue overlaps another warp's DMMA stream.
-template <int CSF>
+template <int CSF, int SRC>
 __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
     const int ntJ = (N2 + FT_TJ - 1) / FT_TJ;
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
-    const double *Ar = a.src ? a.A + row * a.strideA : nullptr;
+    const double *Ar = SRC ? a.A + row * a.strideA : nullptr;
 
     for (int m = tid; m < Mp; m += FT_THREADS) {
-        if (m < M && a.src) {
+        if (m < M && SRC) {
             // explicit dictionaries: rows are read directly (weights 1 / 0, row index = m)
             r1l[m] = r1h[m] = r2l[m] = r2h[m] = m;
             w1l[m] = w2l[m] = 0.0; w1h[m] = w2h[m] = 1.0;
@@ -347,25 +347,32 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             const double csc = ok ? __ldg(cp2 + j) : 0.0;
             const double cal = (CSF && ok) ? __ldg(cp2 + (size_t)a.Npad + j) : 0.0;
             // source rows: lookup table (stride N) or this voxel's dictionary (stride lda)
-            const double *Tc = a.src ? Ar + a.start2 + (ok ? j : 0) : p.table + (ok ? j : 0);
-            const size_t rs = a.src ? (size_t)a.lda : (size_t)N;
+            const double *Tc = SRC ? Ar + a.start2 + (ok ? j : 0) : p.table + (ok ? j : 0);
+            const size_t rs = SRC ? (size_t)a.lda : (size_t)N;
             double *dst = D2s + (size_t)st * Mp * FT_S2 + jj;
             for (int mb = mrow0; mb < Mp; mb += RS * UB) {
                 double lo[UB], hi[UB];
 #pragma unroll
                 for (int q = 0; q < UB; q++) {
                     const int m = min(mb + RS * q, Mp - 1);   // rows >= M carry zero weights
-                    lo[q] = __ldg(Tc + (size_t)r2l[m] * rs);
-                    hi[q] = __ldg(Tc + (size_t)r2h[m] * rs);
+                    if (SRC) {                                 // explicit dictionary: row m itself
+                        lo[q] = 0.0;
+                        hi[q] = __ldg(Tc + (size_t)min(m, M - 1) * rs);
+                    } else {
+                        lo[q] = __ldg(Tc + (size_t)r2l[m] * rs);
+                        hi[q] = __ldg(Tc + (size_t)r2h[m] * rs);
+                    }
                 }
                 // three passes of independent FP64 ops (the FP64 pipe is shared with the
                 // consumers' DMMA stream: dependent chains would serialise on its latency)
+                if (!SRC) {
 #pragma unroll
-                for (int q = 0; q < UB; q++) lo[q] *= w2l[min(mb + RS * q, Mp - 1)];
+                    for (int q = 0; q < UB; q++) lo[q] *= w2l[min(mb + RS * q, Mp - 1)];
+                }
 #pragma unroll
                 for (int q = 0; q < UB; q++) {
                     const int m = min(mb + RS * q, Mp - 1);
-                    hi[q] = fma(w2h[m], hi[q], lo[q]);
+                    hi[q] = SRC ? w2h[m] * hi[q] : fma(w2h[m], hi[q], lo[q]);   // w2h = 0 on padding rows
                     if (CSF) hi[q] = fma(-cal, cs[m], hi[q]);
                 }
 #pragma unroll
@@ -395,8 +402,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         const bool ok = i < N1;
         const double sc = ok ? cp1[i] : 0.0;
         const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
-        const double *Tc = a.src ? Ar + a.start1 + (ok ? i : 0) : p.table + (ok ? i : 0);
-        const size_t rs = a.src ? (size_t)a.lda : (size_t)N;
+        const double *Tc = SRC ? Ar + a.start1 + (ok ? i : 0) : p.table + (ok ? i : 0);
+        const size_t rs = SRC ? (size_t)a.lda : (size_t)N;
         constexpr int RS = FT_CONS / FT_TI;               // rows per pass (2)
         constexpr int UB = 18;                             // loads in flight per thread: 2*UB
         for (int mb = tid / FT_TI; mb < Mp; mb += RS * UB) {
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 const int m = mb + RS * q;
                 lo[q] = 0.0; hi[q] = 0.0;
                 if (ok && m < M) {
-                    lo[q] = __ldg(Tc + (size_t)r1l[m] * rs);
+                    if (!SRC) lo[q] = __ldg(Tc + (size_t)r1l[m] * rs);
                     hi[q] = __ldg(Tc + (size_t)r1h[m] * rs);
                 }
             }
@@ -773,8 +780,9 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         return MFB_EUNSUPPORTED;
     }
     // per device / context attribute: set on every launch (microseconds)
-    if (fp.csf) MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_pairs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(FastArgs) = fp.csf ? (fp.src ? k_fast_pairs<1, 1> : k_fast_pairs<1, 0>)
+                                    : (fp.src ? k_fast_pairs<0, 1> : k_fast_pairs<0, 0>);
+    MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
     const int64_t maxy = 65535;
     for (int64_t v0 = 0; v0 < V; v0 += maxy) {
@@ -788,8 +796,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         if (vox_list) b.vox_list = vox_list + v0;
         else { b.y = y + v0 * p.M; b.A = fp.A ? fp.A + v0 * fp.strideA : nullptr; b.tuple = tuple + v0; }
         dim3 grid(a.ntI, (unsigned)nv);
-        if (fp.csf) MFB_LAUNCH(k_fast_pairs<1>, grid, FT_THREADS, smem, st, b);
-        else MFB_LAUNCH(k_fast_pairs<0>, grid, FT_THREADS, smem, st, b);
+        MFB_LAUNCH(kern, grid, FT_THREADS, smem, st, b);
     }
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     MFB_LAUNCH(k_fast_select, (unsigned)((V + 127) / 128), 128, 0, st, a, V);
