@@ -50,6 +50,24 @@ def fp64_peak():
         return 37.0, "fallback: 64 DFMA/clk/SM x 148 SM x 1.965 GHz"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    ncu --set full capture (profiles/ncu_fast_pairs_r01_summary.txt, one launch, 4191 voxels)."""
+    path = os.path.join(ROOT, "profiles", "ncu_fast_pairs_r01_summary.txt")
+    try:
+        tot, seen = 0.0, 0
+        for line in open(path):
+            if line.startswith("---"):
+                break
+            if line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum"):
+                val, unit = line.split("=")[1].split()[:2]
+                tot += float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+                seen += 1
+        return tot if seen == 2 else None
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -262,7 +280,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
+                         "traffic_note": "DRAM bytes of one k_fast_pairs<0> launch over 4191 voxels (ncu capture "
+                                         "in profiles/); algorithmic HBM bytes are ~1 KB per voxel, the kernel is "
+                                         "FP64-pipe bound",
                          "kernel": "pair search (Gram + closed-form NNLS + argmin)",
                          "kernel_ms_per_launch": kern_ms / max(kern_launches, 1),
                          "kernel_share_of_step": kern_ms / (ms * args.steps),
