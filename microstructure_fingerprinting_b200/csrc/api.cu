@@ -217,17 +217,24 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     if (V == 0) return MFB_OK;
     MFB_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
-    // sub-batches keep the scratch bounded
+    // sub-batches keep the scratch bounded (the general-M fast path holds a normalised copy
+    // of every dictionary of the sub-batch)
     const bool fast = fast_supported_explicit(M, bs) && !getenv("MFB_SOLVE_EXACT");
+    const int shared_dict = strideA == 0;
     size_t per_vox = exact_scratch_bytes(1, bs) + 4096;
-    if (fast) per_vox = std::max(per_vox, fast_scratch_bytes(M, bs.size[0], bs.size[1], 1) + 4096);
-    int64_t sub = std::max<int64_t>(1, std::min<int64_t>(fast ? 8192 : 65535, ((size_t)1 << 30) / per_vox));
+    size_t fixed = 0;
+    if (fast) {
+        fixed = shared_dict ? fast_scratch_bytes(M, bs.size[0], bs.size[1], 0, 1, 1) : 0;
+        per_vox = std::max(per_vox, fast_scratch_bytes(M, bs.size[0], bs.size[1], 1, 1, shared_dict) - fixed + 4096);
+    }
+    const size_t budget = per_vox > ((size_t)8 << 20) ? (size_t)6 << 30 : (size_t)1 << 30;
+    int64_t sub = std::max<int64_t>(1, std::min<int64_t>(fast ? 8192 : 65535, budget / per_vox));
     sub = std::min(sub, V);
     Buf scratch, tuple, asmall, idx5, w5, redo;
     int rc = MFB_OK;
     auto cleanup = [&]() { scratch.release(); tuple.release(); asmall.release(); idx5.release(); w5.release(); redo.release(); };
     size_t sbytes = exact_scratch_bytes(sub, bs);
-    if (fast) sbytes = std::max(sbytes, fast_scratch_bytes(M, bs.size[0], bs.size[1], sub));
+    if (fast) sbytes = std::max(sbytes, fast_scratch_bytes(M, bs.size[0], bs.size[1], sub, 1, shared_dict));
     if ((rc = scratch.ensure(sbytes)) || (rc = tuple.ensure(sizeof(long long) * sub)) ||
         (rc = asmall.ensure(sizeof(double) * sub * M * kMaxBlocks)) ||
         (rc = idx5.ensure(sizeof(int32_t) * sub * kMaxBlocks)) || (rc = w5.ensure(sizeof(double) * sub * kMaxBlocks)) ||
@@ -246,6 +253,7 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
             // DMMA screening on the explicit dictionaries; uncertain voxels fall through to the
             // reference-order search below
             FastProblem fp;
+            memset(&fp, 0, sizeof(fp));
             fp.src = 1; fp.N1 = bs.size[0]; fp.N2 = bs.size[1]; fp.A = Av; fp.lda = lda; fp.strideA = strideA;
             fp.start1 = bs.start[0]; fp.start2 = bs.start[1]; fp.start3 = bs.nb == 3 ? bs.start[2] : 0;
             fp.csf = bs.nb == 3;
@@ -260,7 +268,7 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
                 cudaStreamSynchronize(st) != cudaSuccess) { rc = MFB_ECUDA; break; }
             if (n_redo > 0)
                 rc = launch_exact_search(n_redo, M, bs, Av, lda, strideA, yv, M, redo_list, scratch.p,
-                                         tuple.as<long long>(), st, nullptr, 1);
+                                         tuple.as<long long>(), st, nullptr, redo_list);
         } else {
             rc = launch_exact_search(nv, M, bs, Av, lda, strideA, yv, M, nullptr, scratch.p,
                                      tuple.as<long long>(), st);
@@ -363,7 +371,7 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
         if (!(flags & 1) && fast_supported(dp, Kt, ct, et)) {
             // fast tier: DMMA screening; uncertain voxels are redone by the exact tier
             const int64_t fsub = std::min<int64_t>(cnt, 8192);
-            MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(dp.M, dp.N, dp.N, fsub)));
+            MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(dp.M, dp.N, dp.N, fsub, 0, 0)));
             FastProblem fp;
             memset(&fp, 0, sizeof(fp));
             fp.src = 0; fp.N1 = fp.N2 = dp.N; fp.csf = ct;
@@ -389,6 +397,53 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             pl->stats[6] += head[2];          // ill-conditioned competitor
             pl->stats[7] += head[3] + 1e-6 * head[4] ;  // near ties (+ 1e-6 * pair-independent branch)
             if (n_redo > 0) MFB_TRY(run_exact(redo_list, n_redo, false));
+        } else if (!(flags & 1) && fast_supported_materialised(dp, Kt, ct, et)) {
+            // between-shell protocols and M > 112: materialise the rotated dictionaries of a
+            // sub-chunk (k_rotate_assemble), screen them with the explicit-source fast tier,
+            // redo the uncertain voxels on the same dictionaries in reference order
+            const int64_t lda = (bs.ntot + 1) & ~(int64_t)1;
+            const int64_t strideA = (int64_t)M * lda;
+            const size_t per_vox = (size_t)strideA * sizeof(double) + fast_scratch_bytes(M, dp.N, dp.N, 1, 1, 0);
+            int64_t sub = std::max<int64_t>(1, std::min<int64_t>(8192, 2 * pl->exact_budget / per_vox));
+            sub = std::min(sub, cnt);
+            MFB_TRY(pl->abuf.ensure((size_t)strideA * sizeof(double) * sub));
+            MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(M, dp.N, dp.N, sub, 1, 0)));
+            MFB_TRY(pl->redo.ensure(sizeof(int32_t) * (2 * sub + 8)));
+            int32_t *redo_count = pl->redo.as<int32_t>(), *reasons = redo_count + 1;
+            int32_t *redo_list = redo_count + 8, *redo_local = redo_list + sub;
+            FastProblem fp;
+            memset(&fp, 0, sizeof(fp));
+            fp.src = 1; fp.N1 = fp.N2 = dp.N; fp.csf = ct;
+            fp.A = pl->abuf.as<double>(); fp.lda = lda; fp.strideA = strideA;
+            fp.start1 = 0; fp.start2 = dp.N; fp.start3 = ct ? 2 * dp.N : 0;
+            fp.a_by_local = 1; fp.redo_local = redo_local;
+            for (int64_t s0 = 0; s0 < cnt; s0 += sub) {
+                const int64_t ns = std::min(sub, cnt - s0);
+                MFB_CUDA_TRY(cudaMemsetAsync(redo_count, 0, 8 * sizeof(int32_t), st));
+                MFB_TRY(launch_rotate_assemble(dp, ns, list + s0, peaks, pld, Kt, ct, et,
+                                               pl->abuf.as<double>(), lda, strideA, st));
+                cudaEvent_t *ev = timed ? next_events() : nullptr;
+                MFB_TRY(launch_fast_search(dp, fp, ns, list + s0, peaks, pld, y, pl->fscratch.p,
+                                           pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev));
+                if (ev) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
+                int32_t head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                MFB_CUDA_TRY(cudaMemcpyAsync(head, redo_count, sizeof(head), cudaMemcpyDeviceToHost, st));
+                MFB_CUDA_TRY(cudaStreamSynchronize(st));
+                const int32_t n_redo = head[0];
+                pl->stats[0] += (double)(ns - n_redo);
+                pl->stats[1] += (double)n_redo;
+                pl->stats[6] += head[2];
+                pl->stats[7] += head[3] + 1e-6 * head[4];
+                if (n_redo > 0) {
+                    MFB_TRY(pl->scratch.ensure(exact_scratch_bytes(n_redo, bs)));
+                    MFB_TRY(launch_exact_search(n_redo, M, bs, pl->abuf.as<double>(), lda, strideA, y, M,
+                                                redo_list, pl->scratch.p, pl->tuple.as<long long>(), st,
+                                                nullptr, redo_local));
+                }
+                MFB_TRY(launch_gather_from_A(ns, M, bs, pl->abuf.as<double>(), lda, strideA,
+                                             pl->tuple.as<long long>(), list + s0, pl->asmall.as<double>(),
+                                             pl->idx5.as<int32_t>(), st));
+            }
         } else if (!(flags & 1) && single_fascicle_supported(dp, Kt, ct, et) && list) {
             // one fascicle: fused rotation + closed forms in the reference's arithmetic
             MFB_TRY(launch_single_fascicle(dp, cnt, list, peaks, pld, y, ct, et, pl->tuple.as<long long>(), st));

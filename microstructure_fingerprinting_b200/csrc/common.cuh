@@ -91,7 +91,7 @@ size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs);
 int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, int64_t lda,
                         int64_t strideA, const double *y, int64_t y_ld,
                         const int32_t *vox_list, void *scratch, long long *tuple_out,
-                        cudaStream_t st, cudaEvent_t *ev = nullptr, int a_by_row = 0);
+                        cudaStream_t st, cudaEvent_t *ev = nullptr, const int32_t *a_list = nullptr);
 
 // Copy the winning tuple's columns into Asmall[row(v)] (M x kMaxBlocks, row-major) and
 // decode the per-block indices into idx_sub[row(v)*kMaxBlocks + b].
@@ -138,10 +138,14 @@ struct FastProblem {
     int64_t lda, strideA;
     int start1, start2, start3;
     int csf;            // a third, single-column block is present
+    int a_by_local;     // explicit + vox_list: local voxel v reads A + v*strideA (vox_list maps y / tuple rows only)
+    int32_t *redo_local;  // optional: local indices of the voxels handed to the exact tier
 };
 bool fast_supported(const DevPlan &p, int K, int csf, int ear);
 bool fast_supported_explicit(int M, const BlockSpec &bs);
-size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V);
+// fit path through materialised dictionaries (between-shell protocols, M > 112)
+bool fast_supported_materialised(const DevPlan &p, int K, int csf, int ear);
+size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V, int src, int shared_dict);
 int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const int32_t *vox_list,
                        const double *peaks, int peaks_ld, const double *y, void *scratch,
                        long long *tuple, int32_t *redo_list, int32_t *redo_count, int32_t *reasons,

@@ -322,12 +322,12 @@ struct ExactArgs {
     double *colsq, *ady, *ysq, *cross13, *cross23, *tile_res;
     long long *tile_idx;
     int ntiles;
-    int a_by_row;   // dictionaries indexed by the voxel's row (vox_list) instead of its local index
+    const int32_t *a_list;   // optional: dictionary index of voxel v (default: v itself)
 };
 
 __device__ __forceinline__ const double *ex_A(const ExactArgs &a, int64_t v)
 {
-    const int64_t r = (a.a_by_row && a.vox_list) ? (int64_t)a.vox_list[v] : v;
+    const int64_t r = a.a_list ? (int64_t)a.a_list[v] : v;
     return a.A + r * a.strideA;
 }
 
@@ -811,7 +811,7 @@ size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs)
 int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, int64_t lda,
                         int64_t strideA, const double *y, int64_t y_ld, const int32_t *vox_list,
                         void *scratch, long long *tuple_out, cudaStream_t st, cudaEvent_t *ev,
-                        int a_by_row)
+                        const int32_t *a_list)
 {
     if (V == 0) return MFB_OK;
     if (bs.nb < 1 || bs.nb > kMaxBlocks) {
@@ -825,7 +825,7 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
     ExactArgs a;
     a.M = M; a.bs = bs; a.A = A; a.lda = lda; a.strideA = strideA; a.y = y; a.y_ld = y_ld;
     a.vox_list = vox_list;
-    a.a_by_row = a_by_row;
+    a.a_list = a_list;
     a.ntiles = exact_ntiles(bs);
     char *p = (char *)scratch;
     a.colsq = (double *)p; p += align256(sizeof(double) * V * bs.ntot);

@@ -22,6 +22,7 @@
 // screening error bound is handed to the exact tier.
 #include <climits>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -49,6 +50,11 @@ struct FastArgs {
     const double *A;   // explicit source: voxel row r reads A + r*strideA, (M, lda) row-major
     int64_t lda, strideA;
     int start1, start2, start3;  // first column of block 1, block 2 and of the third (1-column) block
+    int a_by_local;    // explicit source: the dictionary of local voxel v is A + v*strideA (rows index y / tuple only)
+    double *Dn;        // k_gemm_pairs: normalised (and CSF-projected) copy, [v][Mp2][ldn], zero padded
+    int64_t dn_stride;
+    int ldn, N1pad, Mp2;
+    int32_t *redo_local;  // local indices of the voxels handed to the exact tier
     int csf;
     int Mp;            // M padded to a multiple of 4
     int Npad;          // max(N1, N2) padded to a multiple of FT_TJ
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     const int k = blockIdx.y;
     const int Nk = k ? a.N2 : a.N1;
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
-    const double *Ar = a.src ? a.A + row * a.strideA : nullptr;
+    const double *Ar = a.src ? a.A + (a.a_by_local ? v : row) * a.strideA : nullptr;
     if (!a.src) {
         const double *u = a.peaks + row * a.peaks_ld + 3 * k;
         const double ux = u[0], uy = u[1], uz = u[2];
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
     const int ntJ = (N2 + FT_TJ - 1) / FT_TJ;
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
-    const double *Ar = SRC ? a.A + row * a.strideA : nullptr;
+    const double *Ar = SRC ? a.A + (a.a_by_local ? v : row) * a.strideA : nullptr;
 
     for (int m = tid; m < Mp; m += FT_THREADS) {
         if (m < M && SRC) {
@@ -663,6 +669,344 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 }
 
 // ---------------------------------------------------------------------------------
+// General-M variant.  When the M x 128 i1 tile does not fit in shared memory (M > 112) the
+// dictionaries are first normalised / CSF-projected into a zero-padded copy Dn (k_normalize),
+// and k_gemm_pairs streams BOTH operands through a k-chunked shared-memory ring filled by
+// TMA bulk copies (cp.async.bulk + mbarrier complete_tx, one producer warp, no FP64 work on
+// the producer side); eight consumer warps accumulate a 16 x 64 correlation tile each over
+// all k chunks with DMMA and then run the same closed-form screening as k_fast_pairs.
+// ---------------------------------------------------------------------------------
+#define GP_TI 128
+#define GP_TJ 64
+#define GP_KC 32
+#define GP_NS 3
+#define GP_S1 (GP_TI + 4)
+#define GP_S2 (GP_TJ + 4)
+#define GP_STAGE (GP_KC * (GP_S1 + GP_S2))
+#define GP_THREADS (FT_CONS + 32)
+#define GP_NROWCHUNK 64
+
+// grid (V or 1, 2, row chunks): block k of voxel v -> Dn[v][:, off_k : off_k + Nkpad]
+__global__ void __launch_bounds__(256) k_normalize(FastArgs a)
+{
+    const int64_t v = blockIdx.x;
+    const int k = blockIdx.y;
+    const int64_t row = a.vox_list ? a.vox_list[v] : v;
+    const double *Ar = a.A + (a.a_by_local ? v : row) * a.strideA;
+    const int Nk = k ? a.N2 : a.N1;
+    const int Nkpad = k ? a.ldn - a.N1pad : a.N1pad;
+    const int coff = k ? a.N1pad : 0, start = k ? a.start2 : a.start1;
+    const double *cp = a.colp + (v * 2 + k) * (int64_t)FT_NPAR * a.Npad;
+    double *dst = a.Dn + v * a.dn_stride + coff;
+    const int M = a.p.M;
+    const int m0 = blockIdx.z * GP_NROWCHUNK, m1 = min(a.Mp2, m0 + GP_NROWCHUNK);
+    for (int i = threadIdx.x; i < Nkpad; i += blockDim.x) {
+        const bool ok = i < Nk;
+        const double sc = ok ? cp[i] : 0.0;
+        const double al = (a.csf && ok) ? cp[(size_t)a.Npad + i] : 0.0;
+#pragma unroll 4
+        for (int m = m0; m < m1; m++) {
+            double val = 0.0;
+            if (ok && m < M) {
+                double d = Ar[(size_t)m * a.lda + start + i];
+                if (a.csf) d = fma(-al, Ar[(size_t)m * a.lda + a.start3], d);
+                val = d * sc;
+            }
+            dst[(size_t)m * a.ldn + i] = val;
+        }
+    }
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(b) : "memory");
+}
+
+template <int CSF>
+__global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    double *stages = smem;                                 // [GP_NS][GP_STAGE]: D1 chunk | D2 chunk
+    double *colq = stages + (size_t)GP_NS * GP_STAGE;      // [8 warps][5][GP_TJ] per-warp copies
+    double *red = colq + 8 * 5 * GP_TJ;                    // [64]
+    __shared__ unsigned long long s_thr;
+    __shared__ unsigned long long s_full[GP_NS], s_empty[GP_NS];
+    __shared__ double s_tolG;
+    __shared__ int s_flag;
+
+    const int N1 = a.N1, N2 = a.N2;
+    const int64_t v = blockIdx.y;
+    const int tI = blockIdx.x;
+    const int i0 = tI * GP_TI;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *vp = a.voxp + v * 8;
+    const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
+    const double gpre = fmax(vp[5], vp[6]);
+    const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
+    const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
+    const int ntJ = (N2 + GP_TJ - 1) / GP_TJ;
+    const int nch = a.Mp2 / GP_KC;
+    const int total = ntJ * nch;
+    const double *Dv = a.Dn + v * a.dn_stride;
+
+    if (tid == 0) {
+        s_thr = (unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0));
+        s_flag = 0;
+        for (int st = 0; st < GP_NS; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], FT_CONS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= FT_CONS) {
+        // ============ producer warp: one D1 row (1 KB) and one D2 row (512 B) per lane ============
+        for (int s = 0; s < total; s++) {
+            const int st = s % GP_NS, jt = s / nch, ch = s - jt * nch;
+            if (s >= GP_NS) mbar_wait(&s_empty[st], (unsigned)((s / GP_NS) - 1) & 1u);
+            double *d1 = stages + (size_t)st * GP_STAGE;
+            double *d2 = d1 + GP_KC * GP_S1;
+            if (lane == 0) mbar_expect_tx(&s_full[st], GP_KC * (GP_TI + GP_TJ) * (unsigned)sizeof(double));
+            __syncwarp();
+            const double *src = Dv + (size_t)(ch * GP_KC + lane) * a.ldn;
+            bulk_g2s(d1 + (size_t)lane * GP_S1, src + i0, GP_TI * sizeof(double), &s_full[st]);
+            bulk_g2s(d2 + (size_t)lane * GP_S2, src + a.N1pad + jt * GP_TJ, GP_TJ * sizeof(double), &s_full[st]);
+        }
+        return;
+    }
+
+    // ===================================== consumers =====================================
+    const int g = lane >> 2, t4 = lane & 3;
+    const double wide = 4.0 * c0 / kIllDet;
+    const double negc0 = -c0;
+    const int wrow = warp * 16;
+    double *cq = colq + warp * 5 * GP_TJ;
+    double z1[2], b1[2], k1[2], g1[2], zu1[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int i = i0 + wrow + 8 * mt + g;
+        const bool ok = i < N1;
+        z1[mt] = ok ? cp1[(size_t)2 * a.Npad + i] : 0.0;
+        b1[mt] = (CSF && ok) ? cp1[(size_t)3 * a.Npad + i] : 0.0;
+        k1[mt] = (CSF && ok) ? cp1[(size_t)4 * a.Npad + i] : 0.0;
+        g1[mt] = (CSF && ok) ? cp1[(size_t)5 * a.Npad + i] : 0.0;
+        zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
+    }
+    const int mtv = max(0, min(2, (N1 - (i0 + wrow) + 7) >> 3));
+    double gb = -1.0, tb = 0.0, thr = fmax(gpre - c0, 0.0), gill = -1.0;
+    int bidx = -1, flag = 0;
+
+    int s = 0;
+    for (int jt = 0; jt < ntJ; jt++) {
+        // this warp's copy of the i2 tile's per-atom parameters (z, beta, kappa, gamma, zu);
+        // Npad is a multiple of GP_TJ here, so the reads stay inside colp
+        __syncwarp();
+        for (int e = lane; e < (CSF ? 5 : 1) * GP_TJ; e += 32)
+            cq[e] = __ldg(cp2 + (size_t)(e / GP_TJ + 2) * a.Npad + jt * GP_TJ + (e % GP_TJ));
+        double acc[2][8][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+        const int ntv = max(0, min(8, (N2 - jt * GP_TJ + 7) >> 3));
+        for (int ch = 0; ch < nch; ch++, s++) {
+            const int st = s % GP_NS;
+            mbar_wait(&s_full[st], (unsigned)(s / GP_NS) & 1u);
+            const double *A_ = stages + (size_t)st * GP_STAGE + (size_t)t4 * GP_S1 + wrow + g;
+            const double *B_ = stages + (size_t)st * GP_STAGE + GP_KC * GP_S1 + (size_t)t4 * GP_S2 + g;
+            if (ntv == 8 && mtv == 2) {
+#pragma unroll 2
+                for (int ks = 0; ks < GP_KC / 4; ks++) {
+                    double af[2], bf[8];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * GP_S1 + 8 * mt];
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) bf[nt] = B_[(size_t)ks * 4 * GP_S2 + 8 * nt];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < 8; nt++)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                         : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                         : "d"(af[mt]), "d"(bf[nt]));
+                }
+            } else {
+#pragma unroll 1
+                for (int ks = 0; ks < GP_KC / 4; ks++) {
+                    double af[2], bf[8];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * GP_S1 + 8 * mt];
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) bf[nt] = B_[(size_t)ks * 4 * GP_S2 + 8 * nt];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < 8; nt++)
+                            if (mt < mtv && nt < ntv)
+                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                             : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                             : "d"(af[mt]), "d"(bf[nt]));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
+        }
+
+        // ---- closed-form screening of the thread's 32 pairs (see k_fast_pairs) ----
+        __syncwarp();
+        thr = fmax(thr, __longlong_as_double((long long)s_thr));
+        unsigned hit = 0;
+        if (!CSF) {
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x;
+                        const double w1 = fma(-rho, z2, z1[mt]);
+                        const double w2 = fma(-rho, z1[mt], z2);
+                        const double det = fma(-rho, rho, 1.0);
+                        const double num = fma(z1[mt], w1, z2 * w2);
+                        const bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
+                        if (pos && fma(-thr, det, num) >= negc0) hit |= 1u << (nt * 4 + e * 2 + mt);
+                    }
+            }
+        } else {
+            unsigned fb = 0;
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+                const double2 b2v = *reinterpret_cast<const double2 *>(cq + GP_TJ + 8 * nt + 2 * t4);
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x, b2 = e ? b2v.y : b2v.x;
+                        const double w1 = fma(-rho, z2, z1[mt]);
+                        const double w2 = fma(-rho, z1[mt], z2);
+                        const double det = fma(-rho, rho, 1.0);
+                        const double w3 = fma(-b2, w2, fma(-b1[mt], w1, Y3 * det));
+                        const double num = fma(gain_c, det, fma(z1[mt], w1, z2 * w2));
+                        const bool pos = min(min(__double2hiint(w1), __double2hiint(w2)), __double2hiint(w3)) > 0;
+                        const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
+                        if (!pos) fb |= bit;
+                        else if (fma(-thr, det, num) >= negc0) hit |= bit;
+                    }
+            }
+            if (__any_sync(0xffffffffu, fb != 0)) {
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    const double2 k2v = *reinterpret_cast<const double2 *>(cq + 2 * GP_TJ + 8 * nt + 2 * t4);
+                    const double2 g2v = *reinterpret_cast<const double2 *>(cq + 3 * GP_TJ + 8 * nt + 2 * t4);
+                    const double2 zu2v = *reinterpret_cast<const double2 *>(cq + 4 * GP_TJ + 8 * nt + 2 * t4);
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) {
+                            const double rho = acc[mt][nt][e];
+                            const double zu2 = e ? zu2v.y : zu2v.x;
+                            const double r = fma(rho * k1[mt], e ? k2v.y : k2v.x, g1[mt] * (e ? g2v.y : g2v.x));
+                            const double v1 = fma(-r, zu2, zu1[mt]);
+                            const double v2 = fma(-r, zu1[mt], zu2);
+                            const double det = fma(-r, r, 1.0);
+                            const double num = fma(zu1[mt], v1, zu2 * v2);
+                            const bool pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
+                            const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
+                            if ((fb & bit) && pos && fma(-thr, det, num) >= negc0) hit |= bit;
+                        }
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, hit != 0)) {
+            if (hit) {
+                double rcopy[32];
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) rcopy[nt * 4 + e * 2 + mt] = acc[mt][nt][e];
+#pragma unroll 1
+                for (int q = 0; q < 32; q++) {
+                    if (!(hit & (1u << q))) continue;
+                    const int nt = q >> 2, e = (q >> 1) & 1, mt = q & 1;
+                    const int c = 8 * nt + 2 * t4 + e;
+                    double num, det;
+                    pair_gain<CSF>(rcopy[q], mt ? z1[1] : z1[0], cq[c], mt ? b1[1] : b1[0],
+                                   CSF ? cq[GP_TJ + c] : 0.0, mt ? k1[1] : k1[0], CSF ? cq[2 * GP_TJ + c] : 0.0,
+                                   mt ? g1[1] : g1[0], CSF ? cq[3 * GP_TJ + c] : 0.0, mt ? zu1[1] : zu1[0],
+                                   CSF ? cq[4 * GP_TJ + c] : 0.0, Y3, gain_c, num, det);
+                    if (!(det > 1e-12)) { gill = INFINITY; continue; }
+                    const double gq = num / det, tq = c0 / det;
+                    if (det < kIllDet) gill = fmax(gill, gq + tq);
+                    if (gq > gb) {
+                        flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
+                        gb = gq; tb = tq;
+                        bidx = (i0 + wrow + 8 * mt + g) * N2 + jt * GP_TJ + c;
+                    } else if (!(gb > gq + wide)) {
+                        flag = 1;
+                    }
+                }
+            }
+            double lb = bidx >= 0 ? gb - tb : 0.0;
+            for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+            if (lb > thr) {
+                thr = lb;
+                if (lane == 0) atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
+            }
+        }
+    }
+
+    // ---- reduction over the consumer threads ----
+    const double gt = bidx >= 0 ? gb : -1.0;
+    const double tolt = bidx >= 0 ? tb : 0.0;
+    double gm = gt;
+    int im = bidx >= 0 ? bidx : INT_MAX;
+    for (int o = 16; o > 0; o >>= 1) {
+        double og = __shfl_xor_sync(0xffffffffu, gm, o);
+        int oi = __shfl_xor_sync(0xffffffffu, im, o);
+        if (og > gm || (og == gm && oi < im)) { gm = og; im = oi; }
+    }
+    for (int o = 16; o > 0; o >>= 1) gill = fmax(gill, __shfl_xor_sync(0xffffffffu, gill, o));
+    double *redg = red, *redl = red + 16;
+    int *redi = (int *)(red + 8);
+    if (lane == 0) { redg[warp] = gm; redi[warp] = im; redl[warp] = gill; }
+    consumer_sync();
+    double G = redg[0], Gill = redl[0];
+    int I = redi[0];
+    for (int w = 1; w < FT_CONS / 32; w++) {
+        if (redg[w] > G || (redg[w] == G && redi[w] < I)) { G = redg[w]; I = redi[w]; }
+        Gill = fmax(Gill, redl[w]);
+    }
+    if (bidx >= 0 && bidx == I) s_tolG = tolt;
+    consumer_sync();
+    const double tolG = I != INT_MAX ? s_tolG : 0.0;
+    if (bidx >= 0) {
+        const bool winner = bidx == I;
+        const bool close = gt + tolt >= G - tolG;
+        if ((winner && flag) || (!winner && close)) atomicOr(&s_flag, 1);
+    }
+    consumer_sync();
+    if (tid == 0) {
+        const int64_t o = v * a.ntI + tI;
+        a.cta_gain[o] = G;
+        a.cta_tol[o] = tolG;
+        a.cta_idx[o] = I == INT_MAX ? -1 : I;
+        a.cta_flag[o] = s_flag;
+        a.cta_ill[o] = Gill;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // select: one thread per voxel
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
@@ -697,6 +1041,7 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
     } else {
         int pos = atomicAdd(a.redo_count, 1);
         a.redo_list[pos] = (int32_t)row;
+        if (a.redo_local) a.redo_local[pos] = (int32_t)v;
     }
 }
 
@@ -712,29 +1057,54 @@ bool fast_supported(const DevPlan &p, int K, int csf, int ear)
            (csf == 0 || p.sig_csf);
 }
 
+bool fast_supported_materialised(const DevPlan &p, int K, int csf, int ear)
+{
+    return K == 2 && !ear && p.N >= 8 && p.N <= 46000 && p.M <= 16384 && (csf == 0 || p.sig_csf);
+}
+
 // Explicit dictionaries (mfb_solve_batch): two searched blocks, optionally a third block of
 // exactly one column (the CSF-like compartment).
 bool fast_supported_explicit(int M, const BlockSpec &bs)
 {
-    const int Mp = (M + 3) & ~3;
-    if (Mp > 112 || bs.nb < 2 || bs.nb > 3) return false;
+    if (M > 16384 || bs.nb < 2 || bs.nb > 3) return false;
     if (bs.nb == 3 && bs.size[2] != 1) return false;
     if (bs.size[0] < 8 || bs.size[1] < 8) return false;
     return (long long)bs.size[0] * bs.size[1] < 2000000000LL;
 }
 
-size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V)
+// Geometry shared by fast_scratch_bytes and launch_fast_search.
+struct FastGeom {
+    int Mp, Mp2, Npad, ntI, N1pad, ldn;
+    bool gemm;      // general-M path (k_normalize + k_gemm_pairs)
+};
+static FastGeom fast_geom(int M, int N1, int N2)
 {
+    FastGeom g;
+    g.Mp = (M + 3) & ~3;
+    g.gemm = g.Mp > 112;
     const int Nmax = N1 > N2 ? N1 : N2;
-    const int Npad = (Nmax + FT_TJ - 1) / FT_TJ * FT_TJ;
-    const int ntI = (N1 + FT_TI - 1) / FT_TI;
+    const int padto = g.gemm ? GP_TI : FT_TJ;
+    g.Npad = (Nmax + padto - 1) / padto * padto;
+    g.ntI = g.gemm ? (N1 + GP_TI - 1) / GP_TI : (N1 + FT_TI - 1) / FT_TI;
+    g.Mp2 = (M + GP_KC - 1) / GP_KC * GP_KC;
+    g.N1pad = (N1 + GP_TI - 1) / GP_TI * GP_TI;
+    g.ldn = g.N1pad + (N2 + GP_TJ - 1) / GP_TJ * GP_TJ;
+    return g;
+}
+
+size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V, int src, int shared_dict)
+{
+    const FastGeom g = fast_geom(M, N1, N2);
     size_t s = 0;
-    s += al256(sizeof(int) * V * 2 * M * 2);
-    s += al256(sizeof(double) * V * 2 * M * 2);
-    s += al256(sizeof(double) * V * 2 * FT_NPAR * Npad);
+    if (!src) {
+        s += al256(sizeof(int) * V * 2 * M * 2);
+        s += al256(sizeof(double) * V * 2 * M * 2);
+    }
+    s += al256(sizeof(double) * V * 2 * FT_NPAR * g.Npad);
     s += al256(sizeof(double) * V * 8);
-    s += 3 * al256(sizeof(double) * V * ntI);
-    s += 2 * al256(sizeof(int) * V * ntI);
+    s += 3 * al256(sizeof(double) * V * g.ntI);
+    s += 2 * al256(sizeof(int) * V * g.ntI);
+    if (g.gemm) s += al256(sizeof(double) * (shared_dict ? 1 : V) * (size_t)g.Mp2 * g.ldn);
     return s;
 }
 
@@ -744,61 +1114,102 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
                        cudaStream_t st, cudaEvent_t *ev)
 {
     if (V == 0) return MFB_OK;
+    const FastGeom g = fast_geom(p.M, fp.N1, fp.N2);
+    if (g.gemm && !fp.src) {
+        set_error("fast tier: M > 112 needs explicit (materialised) dictionaries");
+        return MFB_EUNSUPPORTED;
+    }
     FastArgs a;
+    memset(&a, 0, sizeof(a));
     a.p = p; a.csf = fp.csf;
     a.src = fp.src; a.N1 = fp.N1; a.N2 = fp.N2;
     a.A = fp.A; a.lda = fp.lda; a.strideA = fp.strideA;
     a.start1 = fp.start1; a.start2 = fp.start2; a.start3 = fp.start3;
-    a.Mp = (p.M + 3) & ~3;
-    const int Nmax = fp.N1 > fp.N2 ? fp.N1 : fp.N2;
-    a.Npad = (Nmax + FT_TJ - 1) / FT_TJ * FT_TJ;
-    a.ntI = (fp.N1 + FT_TI - 1) / FT_TI;
+    a.a_by_local = fp.a_by_local; a.redo_local = fp.redo_local;
+    a.Mp = g.Mp; a.Npad = g.Npad; a.ntI = g.ntI;
+    a.Mp2 = g.Mp2; a.N1pad = g.N1pad; a.ldn = g.ldn;
+    const bool shared_dict = fp.src && fp.strideA == 0;
+    a.dn_stride = shared_dict ? 0 : (int64_t)g.Mp2 * g.ldn;
     {
         const char *d = getenv("MFB_FAST_DEBUG");
         a.debug = d ? atoi(d) : 0;
     }
     a.vox_list = vox_list; a.peaks = peaks; a.peaks_ld = peaks_ld; a.y = y;
     char *q = (char *)scratch;
-    a.ip_rows = (int *)q; q += al256(sizeof(int) * V * 2 * p.M * 2);
-    a.ip_w = (double *)q; q += al256(sizeof(double) * V * 2 * p.M * 2);
+    if (!fp.src) {
+        a.ip_rows = (int *)q; q += al256(sizeof(int) * V * 2 * p.M * 2);
+        a.ip_w = (double *)q; q += al256(sizeof(double) * V * 2 * p.M * 2);
+    }
     a.colp = (double *)q; q += al256(sizeof(double) * V * 2 * FT_NPAR * a.Npad);
     a.voxp = (double *)q; q += al256(sizeof(double) * V * 8);
     a.cta_gain = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_tol = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_ill = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_idx = (int *)q; q += al256(sizeof(int) * V * a.ntI);
-    a.cta_flag = (int *)q;
+    a.cta_flag = (int *)q; q += al256(sizeof(int) * V * a.ntI);
+    a.Dn = g.gemm ? (double *)q : nullptr;
     a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count; a.reasons = reasons;
 
     const size_t smem_prep = sizeof(double) * (4 * p.M + 32) + sizeof(int) * 2 * p.M;
-    MFB_LAUNCH(k_fast_prep, dim3((unsigned)V, 2), 256, smem_prep, st, a);
-
-    const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_NS * 5 * FT_TJ +
-                                          5 * a.Mp + 64) + sizeof(int) * 4 * a.Mp;
-    if (smem + 64 > 227 * 1024) {
-        set_error("fast tier: tile does not fit in shared memory");
+    if (smem_prep > 200 * 1024) {
+        set_error("fast tier: too many measurements");
         return MFB_EUNSUPPORTED;
     }
-    // per device / context attribute: set on every launch (microseconds)
-    void (*kern)(FastArgs) = fp.csf ? (fp.src ? k_fast_pairs<1, 1> : k_fast_pairs<1, 0>)
-                                    : (fp.src ? k_fast_pairs<0, 1> : k_fast_pairs<0, 0>);
-    MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
+    if (smem_prep > 48 * 1024)
+        MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+    MFB_LAUNCH(k_fast_prep, dim3((unsigned)V, 2), 256, smem_prep, st, a);
+
     const int64_t maxy = 65535;
-    for (int64_t v0 = 0; v0 < V; v0 += maxy) {
+    // per-voxel scratch is indexed by the local voxel: shift every per-voxel pointer
+    auto shifted = [&](int64_t v0) {
         FastArgs b = a;
-        const int64_t nv = V - v0 < maxy ? V - v0 : maxy;
-        // kernels index their scratch by the local voxel: shift every per-voxel pointer
-        b.ip_rows += v0 * 2 * p.M * 2; b.ip_w += v0 * 2 * p.M * 2;
+        if (!fp.src) { b.ip_rows += v0 * 2 * p.M * 2; b.ip_w += v0 * 2 * p.M * 2; }
         b.colp += v0 * 2 * FT_NPAR * a.Npad; b.voxp += v0 * 8;
         b.cta_gain += v0 * a.ntI; b.cta_tol += v0 * a.ntI; b.cta_ill += v0 * a.ntI;
         b.cta_idx += v0 * a.ntI; b.cta_flag += v0 * a.ntI;
+        if (b.Dn) b.Dn += v0 * a.dn_stride;
         if (vox_list) b.vox_list = vox_list + v0;
-        else { b.y = y + v0 * p.M; b.A = fp.A ? fp.A + v0 * fp.strideA : nullptr; b.tuple = tuple + v0; }
-        dim3 grid(a.ntI, (unsigned)nv);
-        MFB_LAUNCH(kern, grid, FT_THREADS, smem, st, b);
+        else { b.y = y + v0 * p.M; b.tuple = tuple + v0; }
+        if (fp.A && (!vox_list || fp.a_by_local)) b.A = fp.A + v0 * fp.strideA;
+        return b;
+    };
+    if (g.gemm) {
+        const size_t smem = sizeof(double) * ((size_t)GP_NS * GP_STAGE + 8 * 5 * GP_TJ + 64);
+        void (*kern)(FastArgs) = fp.csf ? k_gemm_pairs<1> : k_gemm_pairs<0>;
+        MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned zc = (unsigned)((g.Mp2 + GP_NROWCHUNK - 1) / GP_NROWCHUNK);
+        if (shared_dict) {
+            MFB_LAUNCH(k_normalize, dim3(1, 2, zc), 256, 0, st, a);
+        } else {
+            for (int64_t v0 = 0; v0 < V; v0 += maxy) {
+                const int64_t nv = V - v0 < maxy ? V - v0 : maxy;
+                MFB_LAUNCH(k_normalize, dim3((unsigned)nv, 2, zc), 256, 0, st, shifted(v0));
+            }
+        }
+        if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
+        for (int64_t v0 = 0; v0 < V; v0 += maxy) {
+            const int64_t nv = V - v0 < maxy ? V - v0 : maxy;
+            MFB_LAUNCH(kern, dim3(a.ntI, (unsigned)nv), GP_THREADS, smem, st, shifted(v0));
+        }
+        if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
+    } else {
+        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_NS * 5 * FT_TJ +
+                                              5 * a.Mp + 64) + sizeof(int) * 4 * a.Mp;
+        if (smem + 64 > 227 * 1024) {
+            set_error("fast tier: tile does not fit in shared memory");
+            return MFB_EUNSUPPORTED;
+        }
+        // per device / context attribute: set on every launch (microseconds)
+        void (*kern)(FastArgs) = fp.csf ? (fp.src ? k_fast_pairs<1, 1> : k_fast_pairs<1, 0>)
+                                        : (fp.src ? k_fast_pairs<0, 1> : k_fast_pairs<0, 0>);
+        MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
+        for (int64_t v0 = 0; v0 < V; v0 += maxy) {
+            const int64_t nv = V - v0 < maxy ? V - v0 : maxy;
+            MFB_LAUNCH(kern, dim3(a.ntI, (unsigned)nv), FT_THREADS, smem, st, shifted(v0));
+        }
+        if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     }
-    if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     MFB_LAUNCH(k_fast_select, (unsigned)((V + 127) / 128), 128, 0, st, a, V);
     return MFB_OK;
 }

@@ -69,23 +69,34 @@ def host_table(dic):
     return Gun, shells
 
 
+def _rotate_shell(shells, s, xv, atoms):
+    xs, ys = shells[s]
+    j = np.clip(np.searchsorted(xs, xv), 1, xs.size - 1)
+    w_hi = (xv - xs[j - 1]) / (xs[j] - xs[j - 1])
+    w_lo = (xs[j] - xv) / (xs[j] - xs[j - 1])
+    a = atoms[:, None]
+    return w_hi * ys[j, a] + w_lo * ys[j - 1, a]
+
+
 def rotate_columns(dic, sch, dirs, atoms):
-    """Signals of atom `atoms[v]` rotated to `dirs[v]` for every voxel: (V, M)."""
+    """Signals of atom `atoms[v]` rotated to `dirs[v]` for every voxel: (V, M).  Gradient
+    strengths between two dense shells are blended linearly in G (reference
+    mf_utils.py:1921-1956)."""
     Gun, shells = host_table(dic)
     V, M = dirs.shape[0], sch.shape[0]
     out = np.zeros((V, M))
     x = np.abs(dirs @ sch[:, :3].T)                  # (V, M)
-    for s, G in enumerate(Gun):
+    for G in np.unique(sch[:, 3]):
         cols = np.where(sch[:, 3] == G)[0]
-        if cols.size == 0:
-            continue
-        xs, ys = shells[s]
         xv = x[:, cols]
-        j = np.clip(np.searchsorted(xs, xv), 1, xs.size - 1)
-        w_hi = (xv - xs[j - 1]) / (xs[j] - xs[j - 1])
-        w_lo = (xs[j] - xv) / (xs[j] - xs[j - 1])
-        a = atoms[:, None]
-        out[:, cols] = w_hi * ys[j, a] + w_lo * ys[j - 1, a]
+        hit = np.where(Gun == G)[0]
+        if hit.size:
+            out[:, cols] = _rotate_shell(shells, int(hit[0]), xv, atoms)
+        else:
+            h = int(np.argmax(Gun > G))
+            lo, hi = Gun[h - 1], Gun[h]
+            out[:, cols] = ((G - lo) / (hi - lo)) * _rotate_shell(shells, h, xv, atoms) + \
+                ((hi - G) / (hi - lo)) * _rotate_shell(shells, h - 1, xv, atoms)
     return out
 
 
@@ -94,13 +105,15 @@ class Phantom(object):
 
 
 def make_phantom(n_atoms=96, n_vox=64, seed=0, frac_k=(0.1, 0.4, 0.5), csf_frac=0.3, ear=False,
-                 snr=30.0, n_ear=4, dic=None):
+                 snr=30.0, n_ear=4, dic=None, scheme="exact"):
     """Seeded phantom: numfasc in {0,1,2} with probabilities frac_k, CSF on csf_frac of the
     voxels, optional EAR on ~10%, crossing angle U(15,90) deg, M0 = 800, Gaussian noise."""
     rng = np.random.default_rng(seed)
     ph = Phantom()
     ph.dic = dic if dic is not None else make_dictionary(n_atoms, n_ear)
-    ph.sch = load_schemes()[1]
+    # subject protocol: 105 rows snapped to the dense shells ("exact"), the same rows with
+    # their original gradient strengths ("between"), or the 271-row dense scheme itself
+    ph.sch = {"exact": load_schemes()[1], "between": load_schemes()[2], "dense": load_schemes()[0]}[scheme]
     ph.bvals, ph.bvecs = load_schemes()[3], load_schemes()[4]
     M = ph.sch.shape[0]
     V = n_vox

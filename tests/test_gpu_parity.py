@@ -429,3 +429,53 @@ def test_solve_batch_fast_equals_exact(sizes, monkeypatch):
     exact = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))
     for f, e in zip(fast, exact):
         assert np.array_equal(f, e)
+
+
+@pytest.mark.parametrize("sizes,M", [([300, 260], 150), ([200, 200, 1], 130), ([129, 65], 552),
+                                     ([64, 300, 1], 257)])
+def test_solve_batch_general_M_equals_exact(sizes, M, monkeypatch):
+    """M > 112 (the i1 tile no longer fits in shared memory): the TMA-fed k-chunked DMMA
+    screening path (k_normalize + k_gemm_pairs) must return exactly what the
+    reference-order search returns, for per-voxel and for shared dictionaries."""
+    rng = np.random.default_rng(sum(sizes) + M)
+    V, nt = 24, int(np.sum(sizes))
+    base = rng.random((M, nt)) * np.exp(-3.0 * rng.random((1, nt)) * np.linspace(0, 1, M)[:, None])
+    A = base[None] * (1.0 + 0.05 * rng.standard_normal((V, M, nt)))
+    st = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    Y = np.stack([A[v][:, st + np.array([rng.integers(0, n) for n in sizes])] @ rng.random(len(sizes))
+                  for v in range(V)])
+    Y += 0.02 * rng.standard_normal(Y.shape)
+    for dic in (A, A[0]):
+        monkeypatch.delenv("MFB_SOLVE_EXACT", raising=False)
+        fast = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes))
+        monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
+        exact = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes))
+        for f, e in zip(fast, exact):
+            assert np.array_equal(f, e)
+    # and the single-voxel wrapper against the CPU oracle
+    monkeypatch.delenv("MFB_SOLVE_EXACT")
+    for v in range(3):
+        w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(A[v], Y[v].copy(), np.asarray(sizes))
+        wo, subo, toto, objo, _ = orc.solve(A[v], Y[v], sizes)
+        assert np.array_equal(sub, subo) and np.array_equal(w, wo) and obj == objo
+
+
+@pytest.mark.parametrize("scheme,n_atoms,n_vox", [("between", 200, 1200), ("dense", 150, 500),
+                                                  ("between", 1000, 300)])
+def test_fit_materialised_fast_tier_equals_exact_tier(scheme, n_atoms, n_vox):
+    """Between-shell protocols (gradient strengths that match no dense shell,
+    mf_utils.py:1921-1956) and protocols with M > 112 run the screening tier on materialised
+    dictionaries: rows must be bit-identical to the reference-order tier and to the oracle."""
+    ph = make_phantom(n_atoms=n_atoms, n_vox=n_vox, seed=n_atoms + 5, frac_k=(0.05, 0.15, 0.8),
+                      csf_frac=0.4, scheme=scheme)
+    msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, None)
+    fast = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, None, 2, True, False, flags=0)
+    st = plan.stats()
+    exact = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, None, 2, True, False, flags=1)
+    plan.close()
+    assert np.array_equal(fast, exact)
+    n2 = int(np.sum(ph.K == 2))
+    assert st[0] > 0.9 * n2, st          # the screening tier decided almost every 2-fascicle voxel
+    sub = np.arange(0, 16)
+    compare_rows(fast[sub], oracle_rows(ph, sub), ph, idx=sub, exact_bits=True)
