@@ -121,6 +121,12 @@ int mfb_solve_batch(int device, int64_t V, int M, int nblocks,
                     int32_t *idx_sub, double *min_obj, double *y_rec,
                     void *stream);
 
+/* Process-wide counters of mfb_solve_batch, out[6]: voxels decided by the screening tier,
+ * voxels redone by the reference-order tier, and why they were handed over ([2] no
+ * candidate, [3] ill-conditioned competitor, [4] near tie, [5] a solution with fewer active
+ * columns was competitive).  reset != 0 clears them after reading. */
+int mfb_solve_stats(int64_t *out, int n, int reset);
+
 /*
  * The voxel loop of MFModel.fit.  Device pointers:
  *   y V*M, peaks V*3*maxfasc, K V (0..maxfasc), csf V, ear V (0/1 bytes)

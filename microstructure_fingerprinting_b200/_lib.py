@@ -37,6 +37,7 @@ SYMBOLS = {
     "mfb_fit_host": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int]),
     "mfb_fit_stats": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
+    "mfb_solve_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
 }
 
 _lib = None
@@ -84,6 +85,14 @@ def check(rc, what=""):
     if rc == MFB_EUNSUPPORTED:
         raise NotImplementedError(msg)
     raise MFBError(msg)
+
+
+def solve_stats(reset=False):
+    """Counters of mfb_solve_batch (include/mfb200.h): [screened, redone, no candidate,
+    ill-conditioned, near tie, fewer active columns]."""
+    out = (ctypes.c_int64 * 6)()
+    check(load().mfb_solve_stats(out, 6, 1 if reset else 0), "mfb_solve_stats")
+    return [int(x) for x in out]
 
 
 def launch_count():

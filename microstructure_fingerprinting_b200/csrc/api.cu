@@ -80,7 +80,19 @@ struct mfb_plan {
     size_t exact_budget = (size_t)3 << 30;  // bytes of materialised dictionaries per sub-chunk
 };
 
-extern "C" int mfb_version(void) { return 1; }
+// counters of the mfb_solve_batch calls of this process: voxels decided by the screening
+// tier, voxels redone in reference order, hand-over reasons (no candidate, ill-conditioned
+// competitor, near tie, branch with fewer active columns)
+static std::atomic<long long> g_solve_stats[6];
+
+extern "C" int mfb_version(void) { return 2; }
+extern "C" int mfb_solve_stats(int64_t *out, int n, int reset)
+{
+    if (!out && n > 0) { set_error("mfb_solve_stats: invalid argument"); return MFB_EINVAL; }
+    for (int i = 0; i < n && i < 6; i++) out[i] = (int64_t)g_solve_stats[i].load();
+    if (reset) for (int i = 0; i < 6; i++) g_solve_stats[i] = 0;
+    return MFB_OK;
+}
 extern "C" const char *mfb_last_error(void) { return t_error.c_str(); }
 extern "C" int64_t mfb_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -219,22 +231,28 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     cudaStream_t st = (cudaStream_t)stream;
     // sub-batches keep the scratch bounded (the general-M fast path holds a normalised copy
     // of every dictionary of the sub-batch)
-    const bool fast = fast_supported_explicit(M, bs) && !getenv("MFB_SOLVE_EXACT");
+    const bool no_fast = getenv("MFB_SOLVE_EXACT") != nullptr;
+    const bool fast = fast_supported_explicit(M, bs) && !no_fast;
+    const bool fast3 = !fast && fast3_supported_explicit(M, bs) && !no_fast;
     const int shared_dict = strideA == 0;
     size_t per_vox = exact_scratch_bytes(1, bs) + 4096;
     size_t fixed = 0;
     if (fast) {
         fixed = shared_dict ? fast_scratch_bytes(M, bs.size[0], bs.size[1], 0, 1, 1) : 0;
         per_vox = std::max(per_vox, fast_scratch_bytes(M, bs.size[0], bs.size[1], 1, 1, shared_dict) - fixed + 4096);
+    } else if (fast3) {
+        fixed = shared_dict ? fast3_scratch_bytes(M, bs, 0, 1) : 0;
+        per_vox = std::max(per_vox, fast3_scratch_bytes(M, bs, 1, shared_dict) - fixed + 4096);
     }
-    const size_t budget = per_vox > ((size_t)8 << 20) ? (size_t)6 << 30 : (size_t)1 << 30;
-    int64_t sub = std::max<int64_t>(1, std::min<int64_t>(fast ? 8192 : 65535, budget / per_vox));
+    const size_t budget = per_vox > ((size_t)1 << 20) ? (size_t)6 << 30 : (size_t)1 << 30;
+    int64_t sub = std::max<int64_t>(1, std::min<int64_t>((fast || fast3) ? 8192 : 65535, budget / per_vox));
     sub = std::min(sub, V);
     Buf scratch, tuple, asmall, idx5, w5, redo;
     int rc = MFB_OK;
     auto cleanup = [&]() { scratch.release(); tuple.release(); asmall.release(); idx5.release(); w5.release(); redo.release(); };
     size_t sbytes = exact_scratch_bytes(sub, bs);
     if (fast) sbytes = std::max(sbytes, fast_scratch_bytes(M, bs.size[0], bs.size[1], sub, 1, shared_dict));
+    if (fast3) sbytes = std::max(sbytes, fast3_scratch_bytes(M, bs, sub, shared_dict));
     if ((rc = scratch.ensure(sbytes)) || (rc = tuple.ensure(sizeof(long long) * sub)) ||
         (rc = asmall.ensure(sizeof(double) * sub * M * kMaxBlocks)) ||
         (rc = idx5.ensure(sizeof(int32_t) * sub * kMaxBlocks)) || (rc = w5.ensure(sizeof(double) * sub * kMaxBlocks)) ||
@@ -249,23 +267,31 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
         int64_t nv = std::min(sub, V - v0);
         const double *Av = A + v0 * strideA;
         const double *yv = y + v0 * M;
-        if (fast) {
+        if (fast || fast3) {
             // DMMA screening on the explicit dictionaries; uncertain voxels fall through to the
             // reference-order search below
-            FastProblem fp;
-            memset(&fp, 0, sizeof(fp));
-            fp.src = 1; fp.N1 = bs.size[0]; fp.N2 = bs.size[1]; fp.A = Av; fp.lda = lda; fp.strideA = strideA;
-            fp.start1 = bs.start[0]; fp.start2 = bs.start[1]; fp.start3 = bs.nb == 3 ? bs.start[2] : 0;
-            fp.csf = bs.nb == 3;
             int32_t *redo_count = redo.as<int32_t>(), *reasons = redo_count + 1, *redo_list = redo_count + 8;
             if (cudaMemsetAsync(redo_count, 0, 8 * sizeof(int32_t), st) != cudaSuccess ||
                 cudaMemsetAsync(tuple.p, 0xff, sizeof(long long) * nv, st) != cudaSuccess) { rc = MFB_ECUDA; break; }
-            rc = launch_fast_search(dummy, fp, nv, nullptr, nullptr, 0, yv, scratch.p, tuple.as<long long>(),
-                                    redo_list, redo_count, reasons, st, nullptr);
+            if (fast) {
+                FastProblem fp;
+                memset(&fp, 0, sizeof(fp));
+                fp.src = 1; fp.N1 = bs.size[0]; fp.N2 = bs.size[1]; fp.A = Av; fp.lda = lda; fp.strideA = strideA;
+                fp.start1 = bs.start[0]; fp.start2 = bs.start[1]; fp.start3 = bs.nb == 3 ? bs.start[2] : 0;
+                fp.csf = bs.nb == 3;
+                rc = launch_fast_search(dummy, fp, nv, nullptr, nullptr, 0, yv, scratch.p, tuple.as<long long>(),
+                                        redo_list, redo_count, reasons, st, nullptr);
+            } else {
+                rc = launch_fast_search3(M, bs, Av, lda, strideA, nv, yv, scratch.p, tuple.as<long long>(),
+                                         redo_list, redo_count, reasons, st, nullptr);
+            }
             if (rc) break;
-            int32_t n_redo = 0;
-            if (cudaMemcpyAsync(&n_redo, redo_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            int32_t head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (cudaMemcpyAsync(head, redo_count, sizeof(head), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaStreamSynchronize(st) != cudaSuccess) { rc = MFB_ECUDA; break; }
+            const int32_t n_redo = head[0];
+            g_solve_stats[0] += nv - n_redo; g_solve_stats[1] += n_redo;
+            for (int i = 0; i < 4; i++) g_solve_stats[2 + i] += head[1 + i];
             if (n_redo > 0)
                 rc = launch_exact_search(n_redo, M, bs, Av, lda, strideA, yv, M, redo_list, scratch.p,
                                          tuple.as<long long>(), st, nullptr, redo_list);

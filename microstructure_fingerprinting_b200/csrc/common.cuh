@@ -151,6 +151,15 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
                        long long *tuple, int32_t *redo_list, int32_t *redo_count, int32_t *reasons,
                        cudaStream_t st, cudaEvent_t *ev);
 
+// Triple scan ([N1, N2, N3], reference `_3`) on explicit dictionaries: DMMA correlation
+// matrices + FP64 closed-form enumeration; uncertain voxels are appended to redo_list.
+bool fast3_supported_explicit(int M, const BlockSpec &bs);
+size_t fast3_scratch_bytes(int M, const BlockSpec &bs, int64_t V, int shared_dict);
+int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda, int64_t strideA,
+                        int64_t V, const double *y, void *scratch, long long *tuple,
+                        int32_t *redo_list, int32_t *redo_count, int32_t *reasons, cudaStream_t st,
+                        cudaEvent_t *ev);
+
 // solve_batch helpers
 int launch_unpack_solution(int64_t V, int nb, const double *w5, const int32_t *idx5,
                            double *w, int32_t *idx, cudaStream_t st);

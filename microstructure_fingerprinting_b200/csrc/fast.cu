@@ -55,6 +55,19 @@ struct FastArgs {
     int64_t dn_stride;
     int ldn, N1pad, Mp2;
     int32_t *redo_local;  // local indices of the voxels handed to the exact tier
+    int nblk;          // searched blocks (2, or 3 for the triple scan)
+    int Nb[3], startb[3], dnoff[3];   // atoms, first column in A, first column in Dn of each block
+    int njobs;         // k_gemm_pairs jobs per voxel (1: the pair scan; 3: the correlation matrices of a triple scan)
+    int job_rb[3], job_cb[3];         // row / column block of each job
+    double *R[3];      // job outputs (STORE): [v][rows padded][ldr], normalised correlations
+    int ldr[3];
+    int64_t r_stride[3];
+    // triple scan (k_triples): thread layout, tiles, per-tile results, voxel-wide threshold
+    int tr_txt, tr_tyt, tr_nt1, tr_ntiles;
+    double *t_gain, *t_tol, *t_ill;
+    long long *t_idx;
+    int *t_flag;
+    unsigned long long *vthr;
     int csf;
     int Mp;            // M padded to a multiple of 4
     int Npad;          // max(N1, N2) padded to a multiple of FT_TJ
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     int *rl = (int *)(red + 32), *rh = rl + M;
     const int64_t v = blockIdx.x;
     const int k = blockIdx.y;
-    const int Nk = k ? a.N2 : a.N1;
+    const int Nk = a.Nb[k];
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     const double *Ar = a.src ? a.A + (a.a_by_local ? v : row) * a.strideA : nullptr;
     if (!a.src) {
@@ -161,13 +174,13 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
         Y3 = fma(cs[m], ys[m], Y3);
     }
     const double gain_c = (a.csf && Y3 > 0) ? Y3 * Y3 / A33 : 0.0;
-    double *cp = a.colp + (v * 2 + k) * (int64_t)FT_NPAR * a.Npad;
+    double *cp = a.colp + (v * a.nblk + k) * (int64_t)FT_NPAR * a.Npad;
     double gbest = 0.0;
     for (int i = threadIdx.x; i < a.Npad; i += blockDim.x) {
         double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0};
         if (i < Nk) {
             double sq = 0.0, dy = 0.0, d3 = 0.0;
-            const double *Ac = a.src ? Ar + (k ? a.start2 : a.start1) + i : nullptr;
+            const double *Ac = a.src ? Ar + a.startb[k] + i : nullptr;
             for (int m = 0; m < M; m++) {
                 double d = a.src ? Ac[(size_t)m * a.lda]
                                  : fma(wh[m], p.table[(size_t)rh[m] * p.N + i], wl[m] * p.table[(size_t)rl[m] * p.N + i]);
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     gbest = block_max(gbest, red);
     if (threadIdx.x == 0) {
         double *vp = a.voxp + v * 8;
-        vp[5 + k] = fmax(gbest, gain_c);
+        vp[5 + k] = fmax(gbest, gain_c);   // slots 5, 6, 7: blocks 0, 1, 2
         if (k == 0) {
             vp[0] = y_sq; vp[1] = A33; vp[2] = Y3; vp[3] = gain_c;
             vp[4] = 4.0 * (M + 8) * 2.2204e-16 * y_sq;   // c0: screening error scale
@@ -693,10 +706,10 @@ __global__ void __launch_bounds__(256) k_normalize(FastArgs a)
     const int k = blockIdx.y;
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     const double *Ar = a.A + (a.a_by_local ? v : row) * a.strideA;
-    const int Nk = k ? a.N2 : a.N1;
-    const int Nkpad = k ? a.ldn - a.N1pad : a.N1pad;
-    const int coff = k ? a.N1pad : 0, start = k ? a.start2 : a.start1;
-    const double *cp = a.colp + (v * 2 + k) * (int64_t)FT_NPAR * a.Npad;
+    const int Nk = a.Nb[k];
+    const int coff = a.dnoff[k], start = a.startb[k];
+    const int Nkpad = (k + 1 < a.nblk ? a.dnoff[k + 1] : a.ldn) - coff;
+    const double *cp = a.colp + (v * a.nblk + k) * (int64_t)FT_NPAR * a.Npad;
     double *dst = a.Dn + v * a.dn_stride + coff;
     const int M = a.p.M;
     const int m0 = blockIdx.z * GP_NROWCHUNK, m1 = min(a.Mp2, m0 + GP_NROWCHUNK);
@@ -731,7 +744,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  ::"r"(d), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(b) : "memory");
 }
 
-template <int CSF>
+// STORE: also write the normalised correlation tile to R[job] (the triple scan reads it).
+template <int CSF, int STORE>
 __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -743,17 +757,23 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     __shared__ double s_tolG;
     __shared__ int s_flag;
 
-    const int N1 = a.N1, N2 = a.N2;
+    const int job = blockIdx.z;
+    const int rb = a.job_rb[job], cb = a.job_cb[job];
+    const int N1 = a.Nb[rb], N2 = a.Nb[cb];
     const int64_t v = blockIdx.y;
     const int tI = blockIdx.x;
     const int i0 = tI * GP_TI;
+    if (i0 >= N1) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *vp = a.voxp + v * 8;
     const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
-    const double gpre = fmax(vp[5], vp[6]);
-    const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
-    const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
-    const int ntJ = (N2 + GP_TJ - 1) / GP_TJ;
+    const double gpre = fmax(vp[5 + rb], vp[5 + cb]);
+    const double *cp1 = a.colp + (v * a.nblk + rb) * (int64_t)FT_NPAR * a.Npad;
+    const double *cp2 = a.colp + (v * a.nblk + cb) * (int64_t)FT_NPAR * a.Npad;
+    const int doff1 = a.dnoff[rb] + i0, doff2 = a.dnoff[cb];
+    // STORE covers the whole zero-padded column block so that R has no unwritten entries
+    const int ntJ = STORE ? ((cb + 1 < a.nblk ? a.dnoff[cb + 1] : a.ldn) - a.dnoff[cb]) / GP_TJ
+                          : (N2 + GP_TJ - 1) / GP_TJ;
     const int nch = a.Mp2 / GP_KC;
     const int total = ntJ * nch;
     const double *Dv = a.Dn + v * a.dn_stride;
@@ -776,8 +796,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
             if (lane == 0) mbar_expect_tx(&s_full[st], GP_KC * (GP_TI + GP_TJ) * (unsigned)sizeof(double));
             __syncwarp();
             const double *src = Dv + (size_t)(ch * GP_KC + lane) * a.ldn;
-            bulk_g2s(d1 + (size_t)lane * GP_S1, src + i0, GP_TI * sizeof(double), &s_full[st]);
-            bulk_g2s(d2 + (size_t)lane * GP_S2, src + a.N1pad + jt * GP_TJ, GP_TJ * sizeof(double), &s_full[st]);
+            bulk_g2s(d1 + (size_t)lane * GP_S1, src + doff1, GP_TI * sizeof(double), &s_full[st]);
+            bulk_g2s(d2 + (size_t)lane * GP_S2, src + doff2 + jt * GP_TJ, GP_TJ * sizeof(double), &s_full[st]);
         }
         return;
     }
@@ -859,6 +879,15 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
             if (lane == 0) mbar_arrive(&s_empty[st]);
         }
 
+        if (STORE) {
+            double *Rv = a.R[job] + v * a.r_stride[job] + (size_t)(i0 + wrow + g) * a.ldr[job] + jt * GP_TJ + 2 * t4;
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++)
+                    *reinterpret_cast<double2 *>(Rv + (size_t)(8 * mt) * a.ldr[job] + 8 * nt) =
+                        make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        }
         // ---- closed-form screening of the thread's 32 pairs (see k_fast_pairs) ----
         __syncwarp();
         thr = fmax(thr, __longlong_as_double((long long)s_thr));
@@ -997,12 +1026,337 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     }
     consumer_sync();
     if (tid == 0) {
-        const int64_t o = v * a.ntI + tI;
+        const int64_t o = (v * a.njobs + job) * a.ntI + tI;
         a.cta_gain[o] = G;
         a.cta_tol[o] = tolG;
         a.cta_idx[o] = I == INT_MAX ? -1 : I;
         a.cta_flag[o] = s_flag;
         a.cta_ill[o] = Gill;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Triple scan: three searched blocks [N1, N2, N3] (three fascicles, or two fascicles + an
+// E-column compartment; reference `_3`, mf_utils.py:470-607).  The three normalised
+// correlation matrices of a voxel come from k_gemm_pairs<0, 1> (DMMA, stored to R; its
+// screening pass also yields the best 2-column solutions, i.e. every branch of `_3` that
+// does not depend on the third index).  k_triples then enumerates all N1*N2*N3 tuples on the
+// FP64 pipe: a CTA owns a (T1 x T2) tile of (i1, i2) pairs, every thread keeps 2 x 4 pairs in
+// registers (r12, 1 - r12^2 and the 2-column Cramer numerators U1, U2) and streams over i3
+// through a cp.async double-buffered shared-memory ring of R13^T / R23^T rows.  Per tuple,
+// with q1 = r13 - r12 r23, q2 = r23 - r12 r13:
+//     S  = c33 - r13 q1 - r23 q2            (3x3 determinant of the correlation matrix)
+//     D3 = c33 z3 - r13 U1 - r23 U2         (Cramer numerator of w3)
+//     W1 = U1 S - q1 D3,  W2 = U2 S - q2 D3 (c33 x Cramer numerators of w1, w2)
+//     gain = (n2 S + D3^2) / (c33 S),  n2 = z1 U1 + z2 U2
+// 13 FP64 operations, no division; "all weights positive and gain + error bound >= thr" is
+// decided on the sign bits of four doubles with integer instructions.
+// ---------------------------------------------------------------------------------
+#define TR_KC 32
+#define TR_MAXTHREADS 384
+
+struct TripleGeom {
+    int txt, tyt, T1, T2, nt1, nt2, threads;
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int TXT = a.tr_txt, TYT = a.tr_tyt;
+    const int T1 = 2 * TXT, T2 = 4 * TYT, rowlen = T1 + T2;
+    const int N1 = a.Nb[0], N2 = a.Nb[1], N3 = a.Nb[2];
+    double *z3s = smem + (size_t)2 * TR_KC * rowlen;       // [N3]
+    double *red = z3s + ((N3 + 1) & ~1);                   // [64]
+    __shared__ unsigned long long s_thr;
+    __shared__ double s_tolG;
+    __shared__ int s_flag;
+
+    const int64_t v = blockIdx.y;
+    const int t1 = blockIdx.x % a.tr_nt1, t2 = blockIdx.x / a.tr_nt1;
+    const int i10 = t1 * T1, i20 = t2 * T2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const bool active = tid < TXT * TYT;
+    const int tx = active ? tid % TXT : 0, ty = active ? tid / TXT : 0;
+    const double *vp = a.voxp + v * 8;
+    const double c0 = vp[4];
+    const double *cpz1 = a.colp + ((v * 3 + 0) * (int64_t)FT_NPAR + 2) * a.Npad;
+    const double *cpz2 = a.colp + ((v * 3 + 1) * (int64_t)FT_NPAR + 2) * a.Npad;
+    const double *cpz3 = a.colp + ((v * 3 + 2) * (int64_t)FT_NPAR + 2) * a.Npad;
+    const double *R12 = a.R[0] + v * a.r_stride[0];
+    const double *R13T = a.R[1] + v * a.r_stride[1];
+    const double *R23T = a.R[2] + v * a.r_stride[2];
+    const int ld12 = a.ldr[0], ld13 = a.ldr[1], ld23 = a.ldr[2];
+    unsigned long long *vthr = a.vthr + v;
+
+    // ---- voxel-wide starting threshold: certified lower bounds of the 2-column solutions ----
+    if (tid == 0) {
+        double t0 = fmax(fmax(vp[5], vp[6]), vp[7]);
+        for (int j = 0; j < 3; j++) {
+            const int ntj = (a.Nb[a.job_rb[j]] + GP_TI - 1) / GP_TI;
+            for (int t = 0; t < ntj; t++) {
+                const int64_t o = (v * 3 + j) * a.ntI + t;
+                if (a.cta_idx[o] >= 0) t0 = fmax(t0, a.cta_gain[o] - a.cta_tol[o]);
+            }
+        }
+        t0 = fmax(t0 - c0, 0.0);
+        const unsigned long long old = atomicMax(vthr, (unsigned long long)__double_as_longlong(t0));
+        s_thr = old > (unsigned long long)__double_as_longlong(t0) ? old : (unsigned long long)__double_as_longlong(t0);
+        s_flag = 0;
+    }
+    for (int i = tid; i < N3; i += blockDim.x) z3s[i] = cpz3[i];
+
+    // ---- chunk loader: rows i3 of R13^T[:, i1 tile] | R23^T[:, i2 tile] ----
+    const int nchunks = (N3 + TR_KC - 1) / TR_KC;
+    auto load_chunk = [&](int c, double *dst) {
+        const int segs = rowlen >> 1;
+        const int rows = min(TR_KC, N3 - c * TR_KC);
+        for (int e = tid; e < rows * segs; e += blockDim.x) {
+            const int r = e / segs, sg = e - r * segs;
+            const int i3 = c * TR_KC + r;
+            double *d = dst + (size_t)r * rowlen + 2 * sg;
+            const double *src;
+            bool ok;
+            if (2 * sg < T1) { const int col = i10 + 2 * sg; ok = col + 1 < ld13; src = R13T + (size_t)i3 * ld13 + col; }
+            else { const int col = i20 + 2 * sg - T1; ok = col + 1 < ld23; src = R23T + (size_t)i3 * ld23 + col; }
+            if (ok) cp_async16(d, src);
+            else { d[0] = 0.0; d[1] = 0.0; }
+        }
+    };
+    load_chunk(0, smem);
+
+    // ---- the thread's 2 x 4 pairs ----
+    // z1 / z2 are only needed when the threshold moves or a tuple is competitive: they are
+    // re-read from colp (L1 / L2) there instead of being kept in registers
+    double r12[8], c33[8], U1[8], U2[8], Tp[8];
+    unsigned valid = 0;
+    auto zrow = [&](int p) { const int i = i10 + 2 * tx + p; return (active && i < N1) ? __ldg(cpz1 + i) : 0.0; };
+    auto zcol = [&](int q) { const int j = i20 + 4 * ty + q; return (active && j < N2) ? __ldg(cpz2 + j) : 0.0; };
+    auto retarget = [&](double th) {
+        double z1[2], z2[4];
+#pragma unroll
+        for (int p = 0; p < 2; p++) z1[p] = zrow(p);
+#pragma unroll
+        for (int q = 0; q < 4; q++) z2[q] = zcol(q);
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            Tp[e] = fma(th, c33[e], -fma(z1[e >> 2], U1[e], z2[e & 3] * U2[e]));
+    };
+    cp_async_wait_all();
+    __syncthreads();
+    double thr = __longlong_as_double((long long)s_thr);
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i10 + 2 * tx + p, j = i20 + 4 * ty + q, e = p * 4 + q;
+            const bool ok = active && i < N1 && j < N2;
+            if (ok) valid |= 1u << e;
+            const double zz1 = zrow(p), zz2 = zcol(q);
+            r12[e] = ok ? R12[(size_t)i * ld12 + j] : 0.0;
+            c33[e] = fma(-r12[e], r12[e], 1.0);
+            U1[e] = fma(-r12[e], zz2, zz1);
+            U2[e] = fma(-r12[e], zz1, zz2);
+            Tp[e] = fma(thr, c33[e], -fma(zz1, U1[e], zz2 * U2[e]));
+        }
+
+    double gb = -1.0, tb = 0.0, gill = -1.0;
+    long long bidx = -1;
+    int flag = 0;
+    // (numerically) identical atoms in blocks 1 and 2, e.g. two fascicles along the same
+    // peak: every tuple of the pair is singular -> the voxel goes to the exact tier
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+        if ((valid >> e & 1u) && c33[e] < 1e-10) gill = INFINITY;
+
+    for (int c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) load_chunk(c + 1, smem + (size_t)((c + 1) & 1) * TR_KC * rowlen);
+        const double *B = smem + (size_t)(c & 1) * TR_KC * rowlen;
+        const int rows = min(TR_KC, N3 - c * TR_KC);
+        {   // pick up the voxel-wide threshold raised by other CTAs / warps
+            double tn = fmax(__longlong_as_double((long long)s_thr),
+                             __longlong_as_double((long long)*(volatile unsigned long long *)vthr));
+            if (tn > thr) { thr = tn; retarget(thr); }
+        }
+        for (int r = 0; r < rows; r++) {
+            const double *rowp = B + (size_t)r * rowlen;
+            const double2 r13v = *reinterpret_cast<const double2 *>(rowp + 2 * tx);
+            const double2 r23a = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty);
+            const double2 r23b = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty + 2);
+            const double z3 = z3s[c * TR_KC + r];
+            const double r13[2] = {r13v.x, r13v.y};
+            const double r23[4] = {r23a.x, r23a.y, r23b.x, r23b.y};
+            unsigned hit = 0;
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int e = p * 4 + q;
+                    const double q1 = fma(-r12[e], r23[q], r13[p]);
+                    const double q2 = fma(-r12[e], r13[p], r23[q]);
+                    const double S = fma(-r23[q], q2, fma(-r13[p], q1, c33[e]));
+                    const double D3 = fma(-r23[q], U2[e], fma(-r13[p], U1[e], c33[e] * z3));
+                    const double W1 = fma(-q1, D3, U1[e] * S);
+                    const double W2 = fma(-q2, D3, U2[e] * S);
+                    const double t = fma(-Tp[e], S, fma(D3, D3, c0));
+                    // all four sign bits clear <=> weights positive and gain + bound >= thr
+                    const int sg = __double2hiint(W1) | __double2hiint(W2) | __double2hiint(D3) | __double2hiint(t);
+                    if (sg >= 0) hit |= 1u << e;
+                }
+            hit &= valid;
+            if (__any_sync(0xffffffffu, hit != 0)) {
+                if (hit) {
+                    const double y_sq = vp[0];
+                    const double c1 = y_sq > 0 ? c0 / y_sq : 0.0, ynorm = sqrt(y_sq);
+                    const double tmax = 16.0 * c0, wide = 4.0 * tmax;
+                    double pc[8][4];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { pc[e][0] = r12[e]; pc[e][1] = c33[e]; pc[e][2] = U1[e]; pc[e][3] = U2[e]; }
+#pragma unroll 1
+                    for (int e = 0; e < 8; e++) {
+                        if (!(hit & (1u << e))) continue;
+                        const int p = e >> 2, q = e & 3;
+                        const double a12 = pc[e][0], k33 = pc[e][1], u1 = pc[e][2], u2 = pc[e][3];
+                        const double a13 = p ? r13v.y : r13v.x;
+                        const double a23 = q == 0 ? r23a.x : (q == 1 ? r23a.y : (q == 2 ? r23b.x : r23b.y));
+                        const double zz1 = zrow(p), zz2 = zcol(q);
+                        const double q1 = fma(-a12, a23, a13), q2 = fma(-a12, a13, a23);
+                        const double S = fma(-a23, q2, fma(-a13, q1, k33));
+                        const double D3 = fma(-a23, u2, fma(-a13, u1, k33 * z3));
+                        const double W1 = fma(-q1, D3, u1 * S), W2 = fma(-q2, D3, u2 * S);
+                        if (!(W1 > 0.0 && W2 > 0.0 && D3 > 0.0)) continue;
+                        const double dd = k33 * S;
+                        if (!(dd > 1e-13 && S > 0.0)) { gill = INFINITY; continue; }   // numerically singular
+                        // Cramer-form gain and its (pessimistic) evaluation error bound
+                        const double n2 = fma(zz1, u1, zz2 * u2);
+                        double gq = fma(n2, S, D3 * D3) / dd, tq = c0 / dd;
+                        // refined: weights from Cramer, gain from the stationary form 2 w.z - w'Gw,
+                        // whose error is second order in the weight error
+                        const double w1 = W1 / dd, w2 = W2 / dd, w3 = D3 / S;
+                        const double quad = fma(w1, w1, fma(w2, w2, w3 * w3)) +
+                                            2.0 * fma(w1 * w2, a12, fma(w1 * w3, a13, w2 * w3 * a23));
+                        const double gr = 2.0 * fma(w1, zz1, fma(w2, zz2, w3 * z3)) - quad;
+                        const double sw = w1 + w2 + w3, rel = c1 / dd;
+                        const double tr = c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq;
+                        if (tr < tq) { gq = gr; tq = tr; }
+                        if (tq > tmax) gill = fmax(gill, gq + tq);
+                        if (gq > gb) {
+                            flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
+                            gb = gq; tb = tq;
+                            bidx = ((long long)(c * TR_KC + r) * N1 + (i10 + 2 * tx + p)) * N2 + (i20 + 4 * ty + q);
+                        } else if (!(gb > gq + wide)) {
+                            flag = 1;
+                        }
+                    }
+                }
+                double lb = bidx >= 0 ? gb - tb : 0.0;               // certified lower bound
+                for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+                if (lb > thr) {
+                    if (lane == 0) {
+                        atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
+                        atomicMax(vthr, (unsigned long long)__double_as_longlong(lb));
+                    }
+                }
+                const double tn = fmax(lb, __longlong_as_double((long long)*(volatile unsigned long long *)&s_thr));
+                if (tn > thr) { thr = tn; retarget(thr); }
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+    }
+
+    // ---- reduction over the CTA: best gain, tie -> lower loop index ----
+    const double gt = bidx >= 0 ? gb : -1.0;
+    const double tolt = bidx >= 0 ? tb : 0.0;
+    double gm = gt;
+    long long im = bidx >= 0 ? bidx : LLONG_MAX;
+    for (int o = 16; o > 0; o >>= 1) {
+        double og = __shfl_xor_sync(0xffffffffu, gm, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, im, o);
+        if (og > gm || (og == gm && oi < im)) { gm = og; im = oi; }
+    }
+    for (int o = 16; o > 0; o >>= 1) gill = fmax(gill, __shfl_xor_sync(0xffffffffu, gill, o));
+    double *redg = red, *redl = red + 16;
+    long long *redi = (long long *)(red + 32);
+    if (lane == 0) { redg[warp] = gm; redi[warp] = im; redl[warp] = gill; }
+    __syncthreads();
+    double G = redg[0], Gill = redl[0];
+    long long I = redi[0];
+    for (int w = 1; w < nwarps; w++) {
+        if (redg[w] > G || (redg[w] == G && redi[w] < I)) { G = redg[w]; I = redi[w]; }
+        Gill = fmax(Gill, redl[w]);
+    }
+    if (bidx >= 0 && bidx == I) s_tolG = tolt;
+    __syncthreads();
+    const double tolG = I != LLONG_MAX ? s_tolG : 0.0;
+    if (bidx >= 0) {
+        const bool winner = bidx == I;
+        const bool close = gt + tolt >= G - tolG;
+        if ((winner && flag) || (!winner && close)) atomicOr(&s_flag, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int64_t o = v * a.tr_ntiles + blockIdx.x;
+        a.t_gain[o] = G;
+        a.t_tol[o] = tolG;
+        a.t_idx[o] = I == LLONG_MAX ? -1 : I;
+        a.t_flag[o] = s_flag;
+        a.t_ill[o] = Gill;
+    }
+}
+
+// select for the triple scan: one thread per voxel
+__global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const double *vp = a.voxp + v * 8;
+    const double c0 = vp[4];
+    // optimistic gain of every solution with at most two active columns
+    double g2 = fmax(fmax(vp[5], vp[6]), vp[7]);
+    for (int j = 0; j < 3; j++) {
+        const int ntj = (a.Nb[a.job_rb[j]] + GP_TI - 1) / GP_TI;
+        for (int t = 0; t < ntj; t++) {
+            const int64_t o = (v * 3 + j) * a.ntI + t;
+            if (a.cta_idx[o] >= 0) g2 = fmax(g2, a.cta_gain[o] + a.cta_tol[o]);
+            g2 = fmax(g2, a.cta_ill[o]);
+        }
+    }
+    double G = -1.0, tolG = 0.0;
+    long long I = -1;
+    int best_t = -1;
+    for (int t = 0; t < a.tr_ntiles; t++) {
+        const int64_t o = v * a.tr_ntiles + t;
+        if (a.t_idx[o] >= 0 && (a.t_gain[o] > G || (a.t_gain[o] == G && a.t_idx[o] < I))) {
+            G = a.t_gain[o]; tolG = a.t_tol[o]; I = a.t_idx[o]; best_t = t;
+        }
+    }
+    bool certain = I >= 0;
+    int reason = certain ? -1 : 0;
+    for (int t = 0; t < a.tr_ntiles && certain; t++) {
+        const int64_t o = v * a.tr_ntiles + t;
+        if (a.t_ill[o] >= G - tolG) { certain = false; reason = 1; }
+        if (t == best_t) { if (a.t_flag[o]) { certain = false; reason = 2; } continue; }
+        if (a.t_idx[o] >= 0 && a.t_gain[o] + a.t_tol[o] >= G - tolG) { certain = false; reason = 2; }
+    }
+    if (certain && !(G - tolG > g2 + 16.0 * c0)) { certain = false; reason = 3; }
+    if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
+    const int64_t row = a.vox_list ? a.vox_list[v] : v;
+    if (certain) {
+        a.tuple[row] = I;
+    } else {
+        int pos = atomicAdd(a.redo_count, 1);
+        a.redo_list[pos] = (int32_t)row;
+        if (a.redo_local) a.redo_local[pos] = (int32_t)v;
     }
 }
 
@@ -1128,6 +1482,9 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     a.a_by_local = fp.a_by_local; a.redo_local = fp.redo_local;
     a.Mp = g.Mp; a.Npad = g.Npad; a.ntI = g.ntI;
     a.Mp2 = g.Mp2; a.N1pad = g.N1pad; a.ldn = g.ldn;
+    a.nblk = 2; a.njobs = 1; a.job_rb[0] = 0; a.job_cb[0] = 1;
+    a.Nb[0] = fp.N1; a.Nb[1] = fp.N2; a.startb[0] = fp.start1; a.startb[1] = fp.start2;
+    a.dnoff[0] = 0; a.dnoff[1] = g.N1pad;
     const bool shared_dict = fp.src && fp.strideA == 0;
     a.dn_stride = shared_dict ? 0 : (int64_t)g.Mp2 * g.ldn;
     {
@@ -1175,7 +1532,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     };
     if (g.gemm) {
         const size_t smem = sizeof(double) * ((size_t)GP_NS * GP_STAGE + 8 * 5 * GP_TJ + 64);
-        void (*kern)(FastArgs) = fp.csf ? k_gemm_pairs<1> : k_gemm_pairs<0>;
+        void (*kern)(FastArgs) = fp.csf ? k_gemm_pairs<1, 0> : k_gemm_pairs<0, 0>;
         MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned zc = (unsigned)((g.Mp2 + GP_NROWCHUNK - 1) / GP_NROWCHUNK);
         if (shared_dict) {
@@ -1211,6 +1568,150 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     }
     MFB_LAUNCH(k_fast_select, (unsigned)((V + 127) / 128), 128, 0, st, a, V);
+    return MFB_OK;
+}
+
+
+// ------------------------------ triple scan, host side ------------------------------
+bool fast3_supported_explicit(int M, const BlockSpec &bs)
+{
+    if (bs.nb != 3 || M > 16384) return false;
+    for (int b = 0; b < 3; b++)
+        if (bs.size[b] < 2 || bs.size[b] > 4096) return false;
+    return true;
+}
+
+// thread layout (txt x tyt threads, 2 x 4 pairs each) wasting the fewest lanes and tile slots
+static TripleGeom triple_geom(int N1, int N2)
+{
+    TripleGeom best;
+    memset(&best, 0, sizeof(best));
+    double best_cost = 1e300;
+    for (int txt = 4; txt <= 64; txt++)
+        for (int tyt = 2; tyt <= 48; tyt++) {
+            const int nthr = txt * tyt;
+            if (nthr < 192 || nthr > TR_MAXTHREADS) continue;
+            const int T1 = 2 * txt, T2 = 4 * tyt;
+            const int nt1 = (N1 + T1 - 1) / T1, nt2 = (N2 + T2 - 1) / T2;
+            const int threads = (nthr + 31) / 32 * 32;
+            // lanes x tile slots spent per useful pair; mild preference for full CTAs
+            const double cost = (double)nt1 * T1 * nt2 * T2 * threads / nthr * (1.0 + 0.02 * (TR_MAXTHREADS - threads) / 32);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best.txt = txt; best.tyt = tyt; best.T1 = T1; best.T2 = T2; best.nt1 = nt1; best.nt2 = nt2;
+                best.threads = threads;
+            }
+        }
+    return best;
+}
+
+struct Fast3Layout {
+    int Mp2, Npad, Np[3], ldn, ntI;
+    TripleGeom tg;
+    size_t off_colp, off_voxp, off_gain, off_tol, off_ill, off_idx, off_flag, off_dn, off_r[3];
+    size_t off_tgain, off_ttol, off_till, off_tidx, off_tflag, off_vthr, total;
+    size_t r_elems[3];
+};
+
+static Fast3Layout fast3_layout(int M, const BlockSpec &bs, int64_t V, int shared_dict)
+{
+    Fast3Layout L;
+    L.Mp2 = (M + GP_KC - 1) / GP_KC * GP_KC;
+    int nmax = 0;
+    for (int b = 0; b < 3; b++) { L.Np[b] = (bs.size[b] + GP_TI - 1) / GP_TI * GP_TI; nmax = nmax > L.Np[b] ? nmax : L.Np[b]; }
+    L.Npad = nmax;
+    L.ldn = L.Np[0] + L.Np[1] + L.Np[2];
+    L.ntI = nmax / GP_TI;
+    L.tg = triple_geom(bs.size[0], bs.size[1]);
+    const int64_t Vd = shared_dict ? 1 : V;
+    const size_t ntile = (size_t)L.tg.nt1 * L.tg.nt2;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+    L.off_colp = take(sizeof(double) * V * 3 * FT_NPAR * L.Npad);
+    L.off_voxp = take(sizeof(double) * V * 8);
+    L.off_gain = take(sizeof(double) * V * 3 * L.ntI);
+    L.off_tol = take(sizeof(double) * V * 3 * L.ntI);
+    L.off_ill = take(sizeof(double) * V * 3 * L.ntI);
+    L.off_idx = take(sizeof(int) * V * 3 * L.ntI);
+    L.off_flag = take(sizeof(int) * V * 3 * L.ntI);
+    L.off_dn = take(sizeof(double) * Vd * (size_t)L.Mp2 * L.ldn);
+    L.r_elems[0] = (size_t)L.Np[0] * L.Np[1];   // R12   [N1p][N2p]
+    L.r_elems[1] = (size_t)L.Np[2] * L.Np[0];   // R13^T [N3p][N1p]
+    L.r_elems[2] = (size_t)L.Np[2] * L.Np[1];   // R23^T [N3p][N2p]
+    for (int j = 0; j < 3; j++) L.off_r[j] = take(sizeof(double) * Vd * L.r_elems[j]);
+    L.off_tgain = take(sizeof(double) * V * ntile);
+    L.off_ttol = take(sizeof(double) * V * ntile);
+    L.off_till = take(sizeof(double) * V * ntile);
+    L.off_tidx = take(sizeof(long long) * V * ntile);
+    L.off_tflag = take(sizeof(int) * V * ntile);
+    L.off_vthr = take(sizeof(unsigned long long) * V);
+    L.total = o;
+    return L;
+}
+
+size_t fast3_scratch_bytes(int M, const BlockSpec &bs, int64_t V, int shared_dict)
+{
+    return fast3_layout(M, bs, V, shared_dict).total;
+}
+
+int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda, int64_t strideA,
+                        int64_t V, const double *y, void *scratch, long long *tuple,
+                        int32_t *redo_list, int32_t *redo_count, int32_t *reasons, cudaStream_t st,
+                        cudaEvent_t *ev)
+{
+    if (V == 0) return MFB_OK;
+    if (V > 65535) { set_error("triple scan: at most 65535 voxels per launch"); return MFB_EINVAL; }
+    const int shared_dict = strideA == 0;
+    const Fast3Layout L = fast3_layout(M, bs, V, shared_dict);
+    FastArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p.M = M; a.src = 1; a.csf = 0;
+    a.A = A; a.lda = lda; a.strideA = strideA;
+    a.nblk = 3; a.njobs = 3;
+    int off = 0;
+    for (int b = 0; b < 3; b++) { a.Nb[b] = bs.size[b]; a.startb[b] = bs.start[b]; a.dnoff[b] = off; off += L.Np[b]; }
+    a.N1 = bs.size[0]; a.N2 = bs.size[1];
+    a.start1 = bs.start[0]; a.start2 = bs.start[1];
+    a.Mp = (M + 3) & ~3; a.Mp2 = L.Mp2; a.Npad = L.Npad; a.ntI = L.ntI; a.ldn = L.ldn; a.N1pad = L.Np[0];
+    a.dn_stride = shared_dict ? 0 : (int64_t)L.Mp2 * L.ldn;
+    a.job_rb[0] = 0; a.job_cb[0] = 1; a.ldr[0] = L.Np[1];
+    a.job_rb[1] = 2; a.job_cb[1] = 0; a.ldr[1] = L.Np[0];
+    a.job_rb[2] = 2; a.job_cb[2] = 1; a.ldr[2] = L.Np[1];
+    char *q = (char *)scratch;
+    a.colp = (double *)(q + L.off_colp); a.voxp = (double *)(q + L.off_voxp);
+    a.cta_gain = (double *)(q + L.off_gain); a.cta_tol = (double *)(q + L.off_tol);
+    a.cta_ill = (double *)(q + L.off_ill); a.cta_idx = (int *)(q + L.off_idx); a.cta_flag = (int *)(q + L.off_flag);
+    a.Dn = (double *)(q + L.off_dn);
+    for (int j = 0; j < 3; j++) { a.R[j] = (double *)(q + L.off_r[j]); a.r_stride[j] = shared_dict ? 0 : (int64_t)L.r_elems[j]; }
+    a.t_gain = (double *)(q + L.off_tgain); a.t_tol = (double *)(q + L.off_ttol); a.t_ill = (double *)(q + L.off_till);
+    a.t_idx = (long long *)(q + L.off_tidx); a.t_flag = (int *)(q + L.off_tflag);
+    a.vthr = (unsigned long long *)(q + L.off_vthr);
+    a.tr_txt = L.tg.txt; a.tr_tyt = L.tg.tyt; a.tr_nt1 = L.tg.nt1; a.tr_ntiles = L.tg.nt1 * L.tg.nt2;
+    a.y = y; a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count; a.reasons = reasons;
+
+    MFB_CUDA_TRY(cudaMemsetAsync(a.vthr, 0, sizeof(unsigned long long) * V, st));
+    const size_t smem_prep = sizeof(double) * (4 * M + 32) + sizeof(int) * 2 * M;
+    if (smem_prep > 200 * 1024) { set_error("triple scan: too many measurements"); return MFB_EUNSUPPORTED; }
+    if (smem_prep > 48 * 1024)
+        MFB_CUDA_TRY(cudaFuncSetAttribute(k_fast_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+    MFB_LAUNCH(k_fast_prep, dim3((unsigned)V, 3), 256, smem_prep, st, a);
+    const unsigned zc = (unsigned)((L.Mp2 + GP_NROWCHUNK - 1) / GP_NROWCHUNK);
+    MFB_LAUNCH(k_normalize, dim3((unsigned)(shared_dict ? 1 : V), 3, zc), 256, 0, st, a);
+    if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
+    {
+        const size_t smem = sizeof(double) * ((size_t)GP_NS * GP_STAGE + 8 * 5 * GP_TJ + 64);
+        void (*kern)(FastArgs) = k_gemm_pairs<0, 1>;
+        MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MFB_LAUNCH(kern, dim3(a.ntI, (unsigned)V, 3), GP_THREADS, smem, st, a);
+    }
+    {
+        const int rowlen = L.tg.T1 + L.tg.T2;
+        const size_t smem = sizeof(double) * ((size_t)2 * TR_KC * rowlen + ((bs.size[2] + 1) & ~1) + 64);
+        MFB_CUDA_TRY(cudaFuncSetAttribute(k_triples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MFB_LAUNCH(k_triples, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
+    }
+    if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
+    MFB_LAUNCH(k_select3, (unsigned)((V + 127) / 128), 128, 0, st, a, V);
     return MFB_OK;
 }
 

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mfb_version() == 1
+    assert lib.mfb_version() == 2
     assert lib.mfb_launch_count() >= 0
 
 

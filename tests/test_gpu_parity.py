@@ -479,3 +479,51 @@ def test_fit_materialised_fast_tier_equals_exact_tier(scheme, n_atoms, n_vox):
     assert st[0] > 0.9 * n2, st          # the screening tier decided almost every 2-fascicle voxel
     sub = np.arange(0, 16)
     compare_rows(fast[sub], oracle_rows(ph, sub), ph, idx=sub, exact_bits=True)
+
+
+def _triple_problem(sizes, M, V, seed, planted=3, signed=False):
+    rng = np.random.default_rng(seed)
+    nt = int(np.sum(sizes))
+    base = rng.random((M, nt)) * np.exp(-3.0 * rng.random((1, nt)) * np.linspace(0, 1, M)[:, None])
+    if signed:
+        base = base * rng.choice([-1.0, 1.0], size=(M, nt))
+    A = base[None] * (1.0 + 0.05 * rng.standard_normal((V, M, nt)))
+    st = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    wts = rng.uniform(0.2, 1.0, (V, 3))
+    wts[:, planted:] = 0.0
+    Y = np.stack([A[v][:, st + np.array([rng.integers(0, n) for n in sizes])] @ wts[v] for v in range(V)])
+    Y += 0.02 * rng.standard_normal(Y.shape)
+    return A, Y
+
+
+@pytest.mark.parametrize("sizes,M,planted,signed", [([60, 70, 50], 100, 3, False), ([300, 300, 300], 100, 3, False),
+                                                    ([90, 90, 6], 105, 3, False), ([33, 47, 129], 150, 3, False),
+                                                    ([64, 64, 64], 60, 2, False), ([50, 40, 30], 80, 3, True)])
+def test_solve_batch_triple_scan_equals_exact(sizes, M, planted, signed, monkeypatch):
+    """Three searched blocks (reference `_3`, mf_utils.py:470-607; BASELINE config 4 shape
+    [300, 300, 300]): the DMMA + FP64 triple scan must return exactly what the
+    reference-order search returns, and decide most 3-compartment voxels itself."""
+    V = 12 if sizes[0] >= 300 else 40
+    A, Y = _triple_problem(sizes, M, V, sum(sizes) + M, planted, signed)
+    _lib.solve_stats(reset=True)
+    fast = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+    stats = _lib.solve_stats(reset=True)
+    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
+    exact = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+    for f, e in zip(fast, exact):
+        assert np.array_equal(f, e)
+    assert stats[0] + stats[1] == V
+    if planted == 3 and not signed:
+        assert stats[0] >= 0.8 * V, stats
+    monkeypatch.delenv("MFB_SOLVE_EXACT")
+    fast = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))     # shared dictionary
+    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
+    exact = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))
+    for f, e in zip(fast, exact):
+        assert np.array_equal(f, e)
+    monkeypatch.delenv("MFB_SOLVE_EXACT")
+    if sizes[0] < 100:
+        for v in range(3):
+            w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(A[v], Y[v].copy(), np.asarray(sizes))
+            wo, subo, toto, objo, _ = orc.solve(A[v], Y[v], sizes)
+            assert np.array_equal(sub, subo) and np.array_equal(w, wo) and obj == objo
