@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
     const int T1 = 2 * TXT, T2 = 4 * TYT, rowlen = T1 + T2;
     const int N1 = a.Nb[0], N2 = a.Nb[1], N3 = a.Nb[2];
     double *z3s = smem + (size_t)2 * TR_KC * rowlen;       // [N3]
-    double *red = z3s + ((N3 + 1) & ~1);                   // [64]
+    double *red = z3s + ((N3 + 3) & ~3);                   // [64]
     __shared__ unsigned long long s_thr;
     __shared__ double s_tolG;
     __shared__ int s_flag;
@@ -1113,19 +1113,21 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
         s_thr = old > (unsigned long long)__double_as_longlong(t0) ? old : (unsigned long long)__double_as_longlong(t0);
         s_flag = 0;
     }
-    for (int i = tid; i < N3; i += blockDim.x) z3s[i] = cpz3[i];
+    // padding steps (i3 >= N3): zero correlations and z3 = -1 give D3 < 0, never a candidate
+    for (int i = tid; i < ((N3 + 3) & ~3); i += blockDim.x) z3s[i] = i < N3 ? cpz3[i] : -1.0;
 
     // ---- chunk loader: rows i3 of R13^T[:, i1 tile] | R23^T[:, i2 tile] ----
     const int nchunks = (N3 + TR_KC - 1) / TR_KC;
     auto load_chunk = [&](int c, double *dst) {
         const int segs = rowlen >> 1;
-        const int rows = min(TR_KC, N3 - c * TR_KC);
+        const int rows = min(TR_KC, ((N3 + 3) & ~3) - c * TR_KC);
         for (int e = tid; e < rows * segs; e += blockDim.x) {
             const int r = e / segs, sg = e - r * segs;
-            const int i3 = c * TR_KC + r;
+            const int i3 = min(c * TR_KC + r, N3 - 1);
             double *d = dst + (size_t)r * rowlen + 2 * sg;
             const double *src;
-            bool ok;
+            bool ok = c * TR_KC + r < N3;
+            if (!ok) { d[0] = 0.0; d[1] = 0.0; continue; }
             if (2 * sg < T1) { const int col = i10 + 2 * sg; ok = col + 1 < ld13; src = R13T + (size_t)i3 * ld13 + col; }
             else { const int col = i20 + 2 * sg - T1; ok = col + 1 < ld23; src = R23T + (size_t)i3 * ld23 + col; }
             if (ok) cp_async16(d, src);
@@ -1187,74 +1189,89 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                              __longlong_as_double((long long)*(volatile unsigned long long *)vthr));
             if (tn > thr) { thr = tn; retarget(thr); }
         }
-        for (int r = 0; r < rows; r++) {
-            const double *rowp = B + (size_t)r * rowlen;
-            const double2 r13v = *reinterpret_cast<const double2 *>(rowp + 2 * tx);
-            const double2 r23a = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty);
-            const double2 r23b = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty + 2);
-            const double z3 = z3s[c * TR_KC + r];
-            const double r13[2] = {r13v.x, r13v.y};
-            const double r23[4] = {r23a.x, r23a.y, r23b.x, r23b.y};
-            unsigned hit = 0;
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows; r0 += 4) {
+            // four i3 steps per vote: one basic block of 32 independent tuples for the scheduler.
+            // sgn[s] keeps the AND of the tuples' sign words of step s: bit 31 clear <=> some
+            // tuple of that step has positive weights and gain + bound >= thr
+            int sgn[4];
 #pragma unroll
-            for (int p = 0; p < 2; p++)
+            for (int s4 = 0; s4 < 4; s4++) {
+                const double *rowp = B + (size_t)(r0 + s4) * rowlen;
+                const double2 r13v = *reinterpret_cast<const double2 *>(rowp + 2 * tx);
+                const double2 r23a = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty);
+                const double2 r23b = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty + 2);
+                const double z3 = z3s[c * TR_KC + r0 + s4];
+                const double r13[2] = {r13v.x, r13v.y};
+                const double r23[4] = {r23a.x, r23a.y, r23b.x, r23b.y};
+                int sall = -1;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int e = p * 4 + q;
-                    const double q1 = fma(-r12[e], r23[q], r13[p]);
-                    const double q2 = fma(-r12[e], r13[p], r23[q]);
-                    const double S = fma(-r23[q], q2, fma(-r13[p], q1, c33[e]));
-                    const double D3 = fma(-r23[q], U2[e], fma(-r13[p], U1[e], c33[e] * z3));
-                    const double W1 = fma(-q1, D3, U1[e] * S);
-                    const double W2 = fma(-q2, D3, U2[e] * S);
-                    const double t = fma(-Tp[e], S, fma(D3, D3, c0));
-                    // all four sign bits clear <=> weights positive and gain + bound >= thr
-                    const int sg = __double2hiint(W1) | __double2hiint(W2) | __double2hiint(D3) | __double2hiint(t);
-                    if (sg >= 0) hit |= 1u << e;
-                }
-            hit &= valid;
-            if (__any_sync(0xffffffffu, hit != 0)) {
-                if (hit) {
+                for (int p = 0; p < 2; p++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int e = p * 4 + q;
+                        const double q1 = fma(-r12[e], r23[q], r13[p]);
+                        const double q2 = fma(-r12[e], r13[p], r23[q]);
+                        const double S = fma(-r23[q], q2, fma(-r13[p], q1, c33[e]));
+                        const double D3 = fma(-r23[q], U2[e], fma(-r13[p], U1[e], c33[e] * z3));
+                        const double W1 = fma(-q1, D3, U1[e] * S);
+                        const double W2 = fma(-q2, D3, U2[e] * S);
+                        const double t = fma(-Tp[e], S, fma(D3, D3, c0));
+                        sall &= (__double2hiint(W1) | __double2hiint(W2) | __double2hiint(D3)) | __double2hiint(t);
+                    }
+                sgn[s4] = sall;
+            }
+            const int sany = (sgn[0] & sgn[1]) & (sgn[2] & sgn[3]);
+            if (__any_sync(0xffffffffu, sany >= 0)) {
+                if (sany >= 0) {
                     const double y_sq = vp[0];
                     const double c1 = y_sq > 0 ? c0 / y_sq : 0.0, ynorm = sqrt(y_sq);
                     const double tmax = 16.0 * c0, wide = 4.0 * tmax;
                     double pc[8][4];
 #pragma unroll
                     for (int e = 0; e < 8; e++) { pc[e][0] = r12[e]; pc[e][1] = c33[e]; pc[e][2] = U1[e]; pc[e][3] = U2[e]; }
+                    const int smask = (sgn[0] >= 0 ? 1 : 0) | (sgn[1] >= 0 ? 2 : 0) | (sgn[2] >= 0 ? 4 : 0) | (sgn[3] >= 0 ? 8 : 0);
 #pragma unroll 1
-                    for (int e = 0; e < 8; e++) {
-                        if (!(hit & (1u << e))) continue;
-                        const int p = e >> 2, q = e & 3;
-                        const double a12 = pc[e][0], k33 = pc[e][1], u1 = pc[e][2], u2 = pc[e][3];
-                        const double a13 = p ? r13v.y : r13v.x;
-                        const double a23 = q == 0 ? r23a.x : (q == 1 ? r23a.y : (q == 2 ? r23b.x : r23b.y));
-                        const double zz1 = zrow(p), zz2 = zcol(q);
-                        const double q1 = fma(-a12, a23, a13), q2 = fma(-a12, a13, a23);
-                        const double S = fma(-a23, q2, fma(-a13, q1, k33));
-                        const double D3 = fma(-a23, u2, fma(-a13, u1, k33 * z3));
-                        const double W1 = fma(-q1, D3, u1 * S), W2 = fma(-q2, D3, u2 * S);
-                        if (!(W1 > 0.0 && W2 > 0.0 && D3 > 0.0)) continue;
-                        const double dd = k33 * S;
-                        if (!(dd > 1e-13 && S > 0.0)) { gill = INFINITY; continue; }   // numerically singular
-                        // Cramer-form gain and its (pessimistic) evaluation error bound
-                        const double n2 = fma(zz1, u1, zz2 * u2);
-                        double gq = fma(n2, S, D3 * D3) / dd, tq = c0 / dd;
-                        // refined: weights from Cramer, gain from the stationary form 2 w.z - w'Gw,
-                        // whose error is second order in the weight error
-                        const double w1 = W1 / dd, w2 = W2 / dd, w3 = D3 / S;
-                        const double quad = fma(w1, w1, fma(w2, w2, w3 * w3)) +
-                                            2.0 * fma(w1 * w2, a12, fma(w1 * w3, a13, w2 * w3 * a23));
-                        const double gr = 2.0 * fma(w1, zz1, fma(w2, zz2, w3 * z3)) - quad;
-                        const double sw = w1 + w2 + w3, rel = c1 / dd;
-                        const double tr = c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq;
-                        if (tr < tq) { gq = gr; tq = tr; }
-                        if (tq > tmax) gill = fmax(gill, gq + tq);
-                        if (gq > gb) {
-                            flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
-                            gb = gq; tb = tq;
-                            bidx = ((long long)(c * TR_KC + r) * N1 + (i10 + 2 * tx + p)) * N2 + (i20 + 4 * ty + q);
-                        } else if (!(gb > gq + wide)) {
-                            flag = 1;
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        if (!(smask >> s4 & 1)) continue;
+                        const int r = r0 + s4;
+                        const double *rowp = B + (size_t)r * rowlen;
+                        const double z3 = z3s[c * TR_KC + r];
+#pragma unroll 1
+                        for (int e = 0; e < 8; e++) {
+                            if (!(valid >> e & 1u)) continue;
+                            const int p = e >> 2, q = e & 3;
+                            const double a12 = pc[e][0], k33 = pc[e][1], u1 = pc[e][2], u2 = pc[e][3];
+                            const double a13 = rowp[2 * tx + p], a23 = rowp[T1 + 4 * ty + q];
+                            const double q1 = fma(-a12, a23, a13), q2 = fma(-a12, a13, a23);
+                            const double S = fma(-a23, q2, fma(-a13, q1, k33));
+                            const double D3 = fma(-a23, u2, fma(-a13, u1, k33 * z3));
+                            const double W1 = fma(-q1, D3, u1 * S), W2 = fma(-q2, D3, u2 * S);
+                            if (!(W1 > 0.0 && W2 > 0.0 && D3 > 0.0)) continue;
+                            const double dd = k33 * S;
+                            if (!(dd > 1e-13 && S > 0.0)) { gill = INFINITY; continue; }   // numerically singular
+                            // Cramer-form gain and its (pessimistic) evaluation error bound
+                            const double zz1 = zrow(p), zz2 = zcol(q);
+                            const double n2 = fma(zz1, u1, zz2 * u2);
+                            double gq = fma(n2, S, D3 * D3) / dd, tq = c0 / dd;
+                            if (!(gq + tq >= thr)) continue;
+                            // refined: weights from Cramer, gain from the stationary form 2 w.z - w'Gw,
+                            // whose error is second order in the weight error
+                            const double w1 = W1 / dd, w2 = W2 / dd, w3 = D3 / S;
+                            const double quad = fma(w1, w1, fma(w2, w2, w3 * w3)) +
+                                                2.0 * fma(w1 * w2, a12, fma(w1 * w3, a13, w2 * w3 * a23));
+                            const double gr = 2.0 * fma(w1, zz1, fma(w2, zz2, w3 * z3)) - quad;
+                            const double sw = w1 + w2 + w3, rel = c1 / dd;
+                            const double tr = c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq;
+                            if (tr < tq) { gq = gr; tq = tr; }
+                            if (tq > tmax) gill = fmax(gill, gq + tq);
+                            if (gq > gb) {
+                                flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
+                                gb = gq; tb = tq;
+                                bidx = ((long long)(c * TR_KC + r) * N1 + (i10 + 2 * tx + p)) * N2 + (i20 + 4 * ty + q);
+                            } else if (!(gb > gq + wide)) {
+                                flag = 1;
+                            }
                         }
                     }
                 }
@@ -1706,7 +1723,7 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     }
     {
         const int rowlen = L.tg.T1 + L.tg.T2;
-        const size_t smem = sizeof(double) * ((size_t)2 * TR_KC * rowlen + ((bs.size[2] + 1) & ~1) + 64);
+        const size_t smem = sizeof(double) * ((size_t)2 * TR_KC * rowlen + ((bs.size[2] + 3) & ~3) + 64);
         MFB_CUDA_TRY(cudaFuncSetAttribute(k_triples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(k_triples, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
     }
