@@ -423,17 +423,23 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             pl->stats[6] += head[2];          // ill-conditioned competitor
             pl->stats[7] += head[3] + 1e-6 * head[4] ;  // near ties (+ 1e-6 * pair-independent branch)
             if (n_redo > 0) MFB_TRY(run_exact(redo_list, n_redo, false));
-        } else if (!(flags & 1) && fast_supported_materialised(dp, Kt, ct, et)) {
-            // between-shell protocols and M > 112: materialise the rotated dictionaries of a
-            // sub-chunk (k_rotate_assemble), screen them with the explicit-source fast tier,
-            // redo the uncertain voxels on the same dictionaries in reference order
+        } else if (!(flags & 1) && (fast_supported_materialised(dp, Kt, ct, et) || fast3_supported_materialised(dp, Kt, ct, et))) {
+            // between-shell protocols, M > 112 and [N, N, E] voxels: materialise the rotated
+            // dictionaries of a sub-chunk (k_rotate_assemble), screen them with the
+            // explicit-source fast tier (pair scan, or triple scan when the EAR block is the
+            // third searched block), redo the uncertain voxels on the same dictionaries in
+            // reference order
+            const bool triple = et != 0;
             const int64_t lda = (bs.ntot + 1) & ~(int64_t)1;
             const int64_t strideA = (int64_t)M * lda;
-            const size_t per_vox = (size_t)strideA * sizeof(double) + fast_scratch_bytes(M, dp.N, dp.N, 1, 1, 0);
+            auto fbytes = [&](int64_t n) {
+                return triple ? fast3_scratch_bytes(M, bs, n, 0) : fast_scratch_bytes(M, dp.N, dp.N, n, 1, 0);
+            };
+            const size_t per_vox = (size_t)strideA * sizeof(double) + fbytes(1);
             int64_t sub = std::max<int64_t>(1, std::min<int64_t>(8192, 2 * pl->exact_budget / per_vox));
             sub = std::min(sub, cnt);
             MFB_TRY(pl->abuf.ensure((size_t)strideA * sizeof(double) * sub));
-            MFB_TRY(pl->fscratch.ensure(fast_scratch_bytes(M, dp.N, dp.N, sub, 1, 0)));
+            MFB_TRY(pl->fscratch.ensure(fbytes(sub)));
             MFB_TRY(pl->redo.ensure(sizeof(int32_t) * (2 * sub + 8)));
             int32_t *redo_count = pl->redo.as<int32_t>(), *reasons = redo_count + 1;
             int32_t *redo_list = redo_count + 8, *redo_local = redo_list + sub;
@@ -449,8 +455,13 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
                 MFB_TRY(launch_rotate_assemble(dp, ns, list + s0, peaks, pld, Kt, ct, et,
                                                pl->abuf.as<double>(), lda, strideA, st));
                 cudaEvent_t *ev = timed ? next_events() : nullptr;
-                MFB_TRY(launch_fast_search(dp, fp, ns, list + s0, peaks, pld, y, pl->fscratch.p,
-                                           pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev));
+                if (triple)
+                    MFB_TRY(launch_fast_search3(M, bs, pl->abuf.as<double>(), lda, strideA, ns, y, pl->fscratch.p,
+                                                pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev,
+                                                list + s0, 1, redo_local));
+                else
+                    MFB_TRY(launch_fast_search(dp, fp, ns, list + s0, peaks, pld, y, pl->fscratch.p,
+                                               pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev));
                 if (ev) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
                 int32_t head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 MFB_CUDA_TRY(cudaMemcpyAsync(head, redo_count, sizeof(head), cudaMemcpyDeviceToHost, st));

@@ -158,7 +158,9 @@ size_t fast3_scratch_bytes(int M, const BlockSpec &bs, int64_t V, int shared_dic
 int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda, int64_t strideA,
                         int64_t V, const double *y, void *scratch, long long *tuple,
                         int32_t *redo_list, int32_t *redo_count, int32_t *reasons, cudaStream_t st,
-                        cudaEvent_t *ev);
+                        cudaEvent_t *ev, const int32_t *vox_list = nullptr, int a_by_local = 0,
+                        int32_t *redo_local = nullptr);
+bool fast3_supported_materialised(const DevPlan &p, int K, int csf, int ear);
 
 // solve_batch helpers
 int launch_unpack_solution(int64_t V, int nb, const double *w5, const int32_t *idx5,

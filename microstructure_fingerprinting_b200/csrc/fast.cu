@@ -1433,6 +1433,12 @@ bool fast_supported_materialised(const DevPlan &p, int K, int csf, int ear)
     return K == 2 && !ear && p.N >= 8 && p.N <= 46000 && p.M <= 16384 && (csf == 0 || p.sig_csf);
 }
 
+// two fascicles + the EAR block ([N, N, E]): triple scan on materialised dictionaries
+bool fast3_supported_materialised(const DevPlan &p, int K, int csf, int ear)
+{
+    return K == 2 && ear && !csf && p.sig_ear && p.E >= 2 && p.N >= 2 && p.N <= 4096 && p.M <= 16384;
+}
+
 // Explicit dictionaries (mfb_solve_batch): two searched blocks, optionally a third block of
 // exactly one column (the CSF-like compartment).
 bool fast_supported_explicit(int M, const BlockSpec &bs)
@@ -1674,7 +1680,7 @@ size_t fast3_scratch_bytes(int M, const BlockSpec &bs, int64_t V, int shared_dic
 int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda, int64_t strideA,
                         int64_t V, const double *y, void *scratch, long long *tuple,
                         int32_t *redo_list, int32_t *redo_count, int32_t *reasons, cudaStream_t st,
-                        cudaEvent_t *ev)
+                        cudaEvent_t *ev, const int32_t *vox_list, int a_by_local, int32_t *redo_local)
 {
     if (V == 0) return MFB_OK;
     if (V > 65535) { set_error("triple scan: at most 65535 voxels per launch"); return MFB_EINVAL; }
@@ -1705,6 +1711,7 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     a.vthr = (unsigned long long *)(q + L.off_vthr);
     a.tr_txt = L.tg.txt; a.tr_tyt = L.tg.tyt; a.tr_nt1 = L.tg.nt1; a.tr_ntiles = L.tg.nt1 * L.tg.nt2;
     a.y = y; a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count; a.reasons = reasons;
+    a.vox_list = vox_list; a.a_by_local = a_by_local; a.redo_local = redo_local;
 
     MFB_CUDA_TRY(cudaMemsetAsync(a.vthr, 0, sizeof(unsigned long long) * V, st));
     const size_t smem_prep = sizeof(double) * (4 * M + 32) + sizeof(int) * 2 * M;

@@ -105,7 +105,7 @@ class Phantom(object):
 
 
 def make_phantom(n_atoms=96, n_vox=64, seed=0, frac_k=(0.1, 0.4, 0.5), csf_frac=0.3, ear=False,
-                 snr=30.0, n_ear=4, dic=None, scheme="exact"):
+                 snr=30.0, n_ear=4, dic=None, scheme="exact", ear_frac=0.1, ear_max_k=1):
     """Seeded phantom: numfasc in {0,1,2} with probabilities frac_k, CSF on csf_frac of the
     voxels, optional EAR on ~10%, crossing angle U(15,90) deg, M0 = 800, Gaussian noise."""
     rng = np.random.default_rng(seed)
@@ -119,7 +119,7 @@ def make_phantom(n_atoms=96, n_vox=64, seed=0, frac_k=(0.1, 0.4, 0.5), csf_frac=
     V = n_vox
     ph.K = rng.choice(3, size=V, p=np.asarray(frac_k) / np.sum(frac_k)).astype(np.int32)
     ph.csf = (rng.random(V) < csf_frac).astype(np.uint8)
-    ph.ear = ((rng.random(V) < 0.1) & (ph.K < 2)).astype(np.uint8) if ear else np.zeros(V, np.uint8)
+    ph.ear = ((rng.random(V) < ear_frac) & (ph.K <= ear_max_k)).astype(np.uint8) if ear else np.zeros(V, np.uint8)
     u1 = rng.standard_normal((V, 3))
     u1 /= np.linalg.norm(u1, axis=1, keepdims=True)
     t = rng.standard_normal((V, 3))

@@ -527,3 +527,22 @@ def test_solve_batch_triple_scan_equals_exact(sizes, M, planted, signed, monkeyp
             w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(A[v], Y[v].copy(), np.asarray(sizes))
             wo, subo, toto, objo, _ = orc.solve(A[v], Y[v], sizes)
             assert np.array_equal(sub, subo) and np.array_equal(w, wo) and obj == objo
+
+
+def test_fit_two_fascicles_plus_ear_triple_scan():
+    """[N, N, E] voxels (two fascicles + the extra-axonal restricted block, mf.py:398-408)
+    run the triple scan on materialised dictionaries; [N, N, 1, E] voxels stay on the
+    support-enumeration search.  Rows must equal the reference-order tier's and the oracle's."""
+    ph = make_phantom(n_atoms=90, n_vox=400, seed=31, frac_k=(0.05, 0.15, 0.8), csf_frac=0.25,
+                      ear=True, n_ear=6, ear_frac=0.6, ear_max_k=2)
+    msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, ph.sig_ear)
+    fast = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, ph.ear, 2, True, True, flags=0)
+    st = plan.stats()
+    exact = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, ph.ear, 2, True, True, flags=1)
+    plan.close()
+    assert np.array_equal(fast, exact)
+    n_nne = int(np.sum((ph.K == 2) & (ph.ear == 1) & (ph.csf == 0)))
+    assert n_nne > 50 and st[0] > 0, (n_nne, st)
+    sel = np.where((ph.K == 2) & (ph.ear == 1) & (ph.csf == 0))[0][:12]
+    compare_rows(fast[sel], oracle_rows(ph, sel), ph, idx=sel, exact_bits=True)
