@@ -17,6 +17,9 @@
  *       mfu.solve_exhaustive_posweights(A, y, dicsizes) (mfu:115-214) and the
  *       Numba kernels behind it (_1 mfu:225, _2 mfu:288, _3 mfu:470, _4up
  *       mfu:612), batched over voxels.
+ *   mfb_mc_average
+ *       mfu.monte_carlo_average (mfu:2758-2812), the spin average behind
+ *       mfu.get_PGSE_from_phases (mfu:2815-3015): dictionary generation.
  *   mfb_fit
  *       the voxel loop of MFModel.fit (mf:978-1028) over mf._fit_voxel
  *       (mf:340-461): rotate, assemble, solve, M0/nu/MSE/R2, pack params row.
@@ -120,6 +123,18 @@ int mfb_solve_batch(int device, int64_t V, int M, int nblocks,
                     int64_t strideA, const double *y, double *w,
                     int32_t *idx_sub, double *min_obj, double *y_rec,
                     void *stream);
+
+/*
+ * Monte-Carlo signal synthesis, mfu.monte_carlo_average (mf_utils.py:2758-2812):
+ *   signal[i] = (1/num_spins) * sum_l cos(Dscaling * sum_d gscaling[i,d] *
+ *               sim_phases[(delta_mapping[i]*num_spins + l)*dim + d])
+ * Device pointers: sim_phases n_entries*dim (row-major), delta_mapping n_seq (int64),
+ * gscaling n_seq*dim, signal n_seq (output).  dim in [1,8].  A delta_mapping entry that
+ * points outside sim_phases yields NaN for that sequence.
+ */
+int mfb_mc_average(int device, int64_t n_entries, int dim, const double *sim_phases,
+                   int64_t n_seq, const int64_t *delta_mapping, const double *gscaling,
+                   double Dscaling, int64_t num_spins, double *signal, void *stream);
 
 /* Process-wide counters of mfb_solve_batch, out[6]: voxels decided by the screening tier,
  * voxels redone by the reference-order tier, and why they were handed over ([2] no

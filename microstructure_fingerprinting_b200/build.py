@@ -10,7 +10,7 @@ LIB = os.path.join(HERE, "libmfb200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
 # exact.cu reproduces the reference's separately-rounded arithmetic: no FMA contraction.
-UNITS = [("exact.cu", ["-fmad=false"]), ("fast.cu", []), ("api.cu", [])]
+UNITS = [("exact.cu", ["-fmad=false"]), ("fast.cu", []), ("mc.cu", []), ("api.cu", [])]
 
 
 def _nvcc():

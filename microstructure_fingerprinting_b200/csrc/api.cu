@@ -210,6 +210,27 @@ extern "C" int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *
     return launch_lerp_rows(V, M, N, table, row_lo, row_hi, w_lo, w_hi, scale, out, ldd, (cudaStream_t)stream);
 }
 
+extern "C" int mfb_mc_average(int device, int64_t n_entries, int dim, const double *sim_phases,
+                              int64_t n_seq, const int64_t *delta_mapping, const double *gscaling,
+                              double Dscaling, int64_t num_spins, double *signal, void *stream)
+{
+    if (n_entries < 0 || dim < 1 || dim > 8 || n_seq < 0 || num_spins <= 0 ||
+        (n_seq > 0 && (!sim_phases || !delta_mapping || !gscaling || !signal))) {
+        set_error("mfb_mc_average: invalid argument");
+        return MFB_EINVAL;
+    }
+    if (n_seq == 0) return MFB_OK;
+    MFB_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nsplit = mc_nsplit(n_seq, num_spins);
+    double *partial = nullptr;
+    MFB_CUDA_TRY(cudaMallocAsync((void **)&partial, sizeof(double) * n_seq * nsplit, st));
+    int rc = launch_mc_average(n_entries, dim, sim_phases, n_seq, (const long long *)delta_mapping, gscaling,
+                               Dscaling, num_spins, nsplit, partial, signal, st);
+    cudaFreeAsync(partial, st);
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------
 // batched solve on explicit dictionaries
 // ---------------------------------------------------------------------------------

@@ -162,6 +162,12 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
                         int32_t *redo_local = nullptr);
 bool fast3_supported_materialised(const DevPlan &p, int K, int csf, int ear);
 
+// ------------------------- Monte-Carlo average (mc.cu) ------------------------------
+int mc_nsplit(int64_t n_seq, int64_t num_spins);
+int launch_mc_average(int64_t n_entries, int dim, const double *phases, int64_t n_seq,
+                      const long long *delta_mapping, const double *gscaling, double Dscaling,
+                      int64_t num_spins, int nsplit, double *partial, double *signal, cudaStream_t st);
+
 // solve_batch helpers
 int launch_unpack_solution(int64_t V, int nb, const double *w5, const int32_t *idx5,
                            double *w, int32_t *idx, cudaStream_t st);

@@ -12,6 +12,8 @@ Mirrors (same names, argument meaning, return types and error behaviour):
   rotate_atom                       reference mf_utils.py:1205-1437
   rotate_atom_2Dprotocol            reference mf_utils.py:1440-1690
   rotate_scheme_mat, vrrotvec2mat   reference mf_utils.py:1153-1202, 842-858
+  monte_carlo_average               reference mf_utils.py:2758-2812
+  get_PGSE_from_phases              reference mf_utils.py:2815-3015
 The numerical work (rotation, exhaustive search) runs in libmfb200.so on the GPU; this
 module only validates, marshals and keeps the small per-study tables on the host.
 There is no CPU fallback.
@@ -27,6 +29,7 @@ __all__ = ["solve_exhaustive_posweights", "solve_exhaustive_posweights_batch",
            "import_PGSE_scheme", "get_PGSE_scheme_from_bval_bvec_dense",
            "get_gyromagnetic_ratio", "DT_vec_to_2Darray", "loadmat", "from_ipython",
            "rotate_atom", "rotate_atom_2Dprotocol", "rotate_scheme_mat", "vrrotvec2mat",
+           "monte_carlo_average", "get_PGSE_from_phases",
            "MultiShellTable", "SchemePlan", "GpuPlan"]
 
 
@@ -831,3 +834,132 @@ def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF):
     out = _lerp_rows(table, row_lo[None, :], row_hi[None, :], w_lo[None, :], w_hi[None, :],
                      scale[None, :])[0]
     return np.reshape(out, sig_shape)
+
+
+# ----------------------------------------------------------------------------------
+# Monte-Carlo dictionary generation
+# ----------------------------------------------------------------------------------
+
+def monte_carlo_average(sim_phases, delta_mapping, gscaling, Dscaling, num_spins, device=0):
+    """Monte-Carlo DW-MRI signal as the spin average of the dephasing
+    (reference mf_utils.py:2758-2812):
+
+        S_i = (1/n_spin) sum_l cos(Dscaling * sum_d gscaling[i, d] * sim_phases[map(i)*n_spin + l, d])
+
+    sim_phases (n_ref*n_spin, n_dim) float64, delta_mapping (n_seq,) int64, gscaling
+    (n_seq, n_dim) float64.  Returns the (n_seq,) float64 signal.  Runs on the GPU
+    (mfb_mc_average); NumPy arrays or CUDA tensors are accepted."""
+    torch = _lib.require_cuda()
+    dev = torch.device('cuda', device)
+
+    def up(x, dt_np, dt_t):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=dev, dtype=dt_t).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=dt_np)).to(dev)
+    d_ph = up(sim_phases, np.float64, torch.float64)
+    d_map = up(delta_mapping, np.int64, torch.int64)
+    d_gs = up(gscaling, np.float64, torch.float64)
+    if d_ph.dim() != 2 or d_gs.dim() != 2 or d_map.dim() != 1:
+        raise ValueError("sim_phases and gscaling should be 2D arrays, delta_mapping a 1D array")
+    n_entries, dim = int(d_ph.shape[0]), int(d_ph.shape[1])
+    n_seq = int(d_map.shape[0])
+    if tuple(d_gs.shape) != (n_seq, dim):
+        raise ValueError("gscaling should have shape (%d, %d), detected %s"
+                         % (n_seq, dim, tuple(d_gs.shape)))
+    num_spins = int(num_spins)
+    if n_seq > 0:
+        lo, hi = int(d_map.min()), int(d_map.max())
+        if lo < 0 or (hi + 1) * num_spins > n_entries:
+            raise IndexError("delta_mapping refers to reference sequences outside sim_phases "
+                             "(%d entries, %d spins per sequence)" % (n_entries, num_spins))
+    out = torch.zeros((n_seq,), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = _lib.load().mfb_mc_average(device, n_entries, dim, d_ph.data_ptr(), n_seq, d_map.data_ptr(),
+                                        d_gs.data_ptr(), float(Dscaling), num_spins, out.data_ptr(), st)
+    _lib.check(rc, "mfb_mc_average")
+    return out.cpu().numpy()
+
+
+def _phase_file_encoding(ext):
+    """(byte order, dtype code, bytes per item) from a phase-file extension such as
+    '.bdouble' or '.lfloat' (reference mf_utils.py:2905-2930)."""
+    if not ext:
+        raise ValueError("Phase file extension not found.\nAborting as there is no way to tell "
+                         "which level of precision was used to store the phase values (e.g., "
+                         "float, double, ...).")
+    order = {'b': '>', 'l': '<'}.get(ext[1].lower())
+    if order is None:
+        raise ValueError("Phase file extension (after the dot) should start with a b for big "
+                         "endian or with a l for little endian. Detected: \"%s\"." % ext[1])
+    kind = ext[2:]
+    if kind in ('single', 'float'):
+        return order, 'f4', 4
+    if kind == 'double':
+        return order, 'f8', 8
+    raise ValueError("Data type of phase file specified in file extension (\"%s\") not supported."
+                     % kind)
+
+
+def get_PGSE_from_phases(phasefile, sch_mat_sim, sch_mat, dim=None, D_sim=None, D=None):
+    """PGSE signal of the protocol `sch_mat` from the spins' phases accumulated in a
+    Monte-Carlo simulation run with protocol `sch_mat_sim` (reference
+    mf_utils.py:2815-3015).  `phasefile` is 'path/to/base_phase_x.bdouble'; its siblings
+    '_phase_y', '_phase_z' are read for dim > 1.  The extension gives byte order (b/l) and
+    precision (double / single / float).  Every sequence of `sch_mat` must use a
+    (Delta, delta) pair present in `sch_mat_sim`; gradients are rescaled component-wise.
+    The spin average runs on the GPU (monte_carlo_average)."""
+    import os
+    names, maxdim = ['x', 'y', 'z'], 3
+    d_ratio_sqrt = 1.0
+    if D is not None:
+        if D_sim is None:
+            raise NameError("Simulation diffusivity should be specified if new signal "
+                            "diffusivity is set.")
+        d_ratio_sqrt = float(np.sqrt(D / D_sim))
+    if dim is None:
+        dim = maxdim
+    elif dim > maxdim:
+        raise ValueError("dim should be less than or equal to %d." % maxdim)
+    sim = import_PGSE_scheme(sch_mat_sim)
+    new = import_PGSE_scheme(sch_mat)
+    if np.any(new[:, dim:maxdim] != 0):
+        print("WARNING get_PGSE_from_phases: detected non-zero entries in gradient components "
+              "after dimension %d.\nThose components will be ignored but make sure the right "
+              "acquisition protocol was provided.\nIt is common for such protocols to contain "
+              "zeros in those gradient components, for instance after projection into the "
+              "xy-plane of a 3D protocol.\n" % dim)
+    n_seq, n_ref = new.shape[0], sim.shape[0]
+    g_sim = sim[:, :3] * sim[:, 3][:, np.newaxis]
+    g_new = new[:, :3] * new[:, 3][:, np.newaxis]
+    # reference sequence of each new sequence: LAST simulated row with the same (Delta, delta)
+    same = np.all(new[:, np.newaxis, 4:6] == sim[np.newaxis, :, 4:6], axis=2)      # (n_seq, n_ref)
+    mapping = np.where(same.any(axis=1), n_ref - 1 - np.argmax(same[:, ::-1], axis=1), -1).astype(np.int64)
+    bad = np.where(mapping < 0)[0]
+    if bad.size:
+        listing = '\n'.join('\t%4d -- %5g -- %5g' % (b, new[b, 4] * 1e3, new[b, 5] * 1e3) for b in bad)
+        raise ValueError('Acquisition protocol contains %d (Delta,delta) pair(s) (out of %d) not used '
+                         'to simulate the directional phases in the Monte Carlo simulation. List of '
+                         'unmatched sequences:\nSequ. no. -- Delta [ms] -- delta [ms]\n%s'
+                         % (bad.size, n_seq, listing))
+    gscaling = g_new[:, :dim] / g_sim[mapping, :dim]
+    if not os.path.isfile(phasefile):
+        raise RuntimeError("File %s does not exist." % phasefile)
+    nbytes = os.path.getsize(phasefile)
+    folder, tail = os.path.split(phasefile)
+    base, ext = os.path.splitext(tail)
+    order, code, width = _phase_file_encoding(ext)
+    if nbytes % (n_ref * width) != 0:
+        raise RuntimeError("Phase file %s is either corrupted or inconsistently named. Storage "
+                           "precision of items (%d bytes) times number of reference simulation "
+                           "sequences (%d) does not divide total size (%d bytes)."
+                           % (phasefile, width, n_ref, nbytes))
+    n_entries = nbytes // width
+    n_spins = n_entries // n_ref
+    phases = np.zeros((n_entries, dim))
+    for i in range(dim):
+        path_i = os.path.join(folder, base[:-len(names[i])] + names[i] + ext)
+        if not os.path.isfile(path_i):
+            raise RuntimeError("Phase file %s not found." % path_i)
+        phases[:, i] = np.fromfile(path_i, dtype=order + code, count=n_entries, sep="")
+    return monte_carlo_average(phases, mapping, gscaling, d_ratio_sqrt, n_spins)

@@ -311,7 +311,59 @@ def cleanup_cases():
     print("cleanup_cases written", np.unique(out["peaks_nf"], return_counts=True))
 
 
+def mc_cases():
+    """monte_carlo_average / get_PGSE_from_phases (mfu:2758-3015) on synthetic spin phases:
+    3 reference (Delta, delta) pairs, 6000 spins, phases ~ N(0, 1.5) per component, stored
+    as big-endian double and little-endian single phase files like the simulator writes."""
+    import tempfile
+    rng = np.random.default_rng(424242)
+    n_ref, n_spin = 3, 6000
+    sim = np.zeros((n_ref, 7))
+    sim[:, 0] = 1.0 / np.sqrt(3); sim[:, 1] = 1.0 / np.sqrt(3); sim[:, 2] = 1.0 / np.sqrt(3)
+    sim[:, 3] = [0.04, 0.05, 0.06]
+    sim[:, 4] = [0.020, 0.035, 0.050]
+    sim[:, 5] = [0.008, 0.010, 0.012]
+    sim[:, 6] = 0.08
+    phases = 1.5 * rng.standard_normal((n_ref * n_spin, 3))
+    n_seq = 40
+    pick = rng.integers(0, n_ref, n_seq)
+    new = np.zeros((n_seq, 7))
+    g = rng.standard_normal((n_seq, 3)); g /= np.linalg.norm(g, axis=1, keepdims=True)
+    new[:, :3] = g
+    new[:, 3] = rng.uniform(0.0, 0.08, n_seq)
+    new[:5, 3] = 0.0
+    new[:, 4:6] = sim[pick, 4:6]
+    new[:, 6] = 0.08
+    out = {"sim": sim, "new": new, "phases": phases, "n_spin": n_spin}
+    # direct calls of the Numba kernel
+    gsc = (new[:, :3] * new[:, 3:4]) / (sim[pick, :3] * sim[pick, 3:4])
+    for dim in (2, 3):
+        for ds in (1.0, 0.73):
+            out["avg_d%d_s%g" % (dim, ds)] = mfu.monte_carlo_average(
+                np.ascontiguousarray(phases[:, :dim]), pick.astype(np.int64),
+                np.ascontiguousarray(gsc[:, :dim]), float(ds), n_spin)
+    out["pick"], out["gsc"] = pick, gsc
+    # through the file interface
+    with tempfile.TemporaryDirectory() as tmp:
+        for i, nm in enumerate("xyz"):
+            phases[:, i].astype(">f8").tofile(os.path.join(tmp, "sub_phase_%s.bdouble" % nm))
+            phases[:, i].astype("<f4").tofile(os.path.join(tmp, "sub_phase_%s.lfloat" % nm))
+        out["file_bdouble_d3"] = mfu.get_PGSE_from_phases(os.path.join(tmp, "sub_phase_x.bdouble"), sim, new)
+        out["file_bdouble_d3_D"] = mfu.get_PGSE_from_phases(os.path.join(tmp, "sub_phase_x.bdouble"), sim, new,
+                                                              dim=3, D_sim=2.0e-9, D=1.1e-9)
+        new2 = new.copy()
+        ang = rng.uniform(0, 2 * np.pi, n_seq)
+        new2[:, 0], new2[:, 1], new2[:, 2] = np.cos(ang), np.sin(ang), 0.0
+        out["new2"] = new2
+        out["file_lfloat_d2"] = mfu.get_PGSE_from_phases(os.path.join(tmp, "sub_phase_x.lfloat"), sim, new2, dim=2)
+    np.savez_compressed(os.path.join(OUT, "mc_cases.npz"), **out)
+    print("mc_cases written", out["file_bdouble_d3"][:4])
+
+
 if __name__ == "__main__":
+    mc_cases()
+    if "--only-mc" in sys.argv:
+        sys.exit(0)
     cleanup_cases()
     lowlevel_rotation_cases()
     solver_cases()

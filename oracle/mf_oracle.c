@@ -290,3 +290,23 @@ void orc_reconstruct(int M, int nb, const double *A, int lda, const int32_t *tot
         y_rec[k] = s;
     }
 }
+
+/* monte_carlo_average (mfu:2758-2812): per sequence, the spins of its reference
+ * sequence are visited in order; the phase is the left-to-right sum over the
+ * gradient components of separately rounded products; the signal is the running
+ * sum of cos(Dscaling * phase) divided by the number of spins. */
+#include <math.h>
+void orc_mc_average(long long n_seq, int dim, const double *sim_phases, const long long *delta_mapping,
+                    const double *gscaling, double Dscaling, long long num_spins, double *signal)
+{
+    for (long long iseq = 0; iseq < n_seq; iseq++) {
+        const long long start = delta_mapping[iseq] * num_spins;
+        double s = 0.0;
+        for (long long l = 0; l < num_spins; l++) {
+            double ph = 0.0;
+            for (int d = 0; d < dim; d++) ph += gscaling[iseq * dim + d] * sim_phases[(start + l) * dim + d];
+            s += cos(Dscaling * ph);
+        }
+        signal[iseq] = s / (double)num_spins;
+    }
+}

@@ -287,3 +287,18 @@ def lerp_rows(table, row_lo, row_hi, w_lo, w_hi, scale=None):
     if scale is not None:
         out = scale[..., None] * out
     return out
+
+
+def mc_average(sim_phases, delta_mapping, gscaling, Dscaling, num_spins):
+    """monte_carlo_average (mfu:2758-2812), sequential C restatement."""
+    ph = np.ascontiguousarray(sim_phases, dtype=np.float64)
+    dm = np.ascontiguousarray(delta_mapping, dtype=np.int64)
+    gs = np.ascontiguousarray(gscaling, dtype=np.float64)
+    out = np.zeros(dm.size)
+    L = _lib()
+    L.orc_mc_average.argtypes = [ctypes.c_longlong, ctypes.c_int, _dp, ctypes.POINTER(ctypes.c_longlong), _dp,
+                                 ctypes.c_double, ctypes.c_longlong, _dp]
+    L.orc_mc_average.restype = None
+    L.orc_mc_average(dm.size, ph.shape[1], _d(ph), dm.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                     _d(gs), float(Dscaling), int(num_spins), _d(out))
+    return out

@@ -546,3 +546,60 @@ def test_fit_two_fascicles_plus_ear_triple_scan():
     assert n_nne > 50 and st[0] > 0, (n_nne, st)
     sel = np.where((ph.K == 2) & (ph.ear == 1) & (ph.csf == 0))[0][:12]
     compare_rows(fast[sel], oracle_rows(ph, sel), ph, idx=sel, exact_bits=True)
+
+
+@pytest.fixture(scope="module")
+def mc_cases():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mc_cases.npz"))
+
+
+def test_monte_carlo_average_matches_reference(mc_cases):
+    """mfb_mc_average against the unmodified Numba kernel (mf_utils.py:2758-2812) and the
+    CPU oracle.  Tolerance 1e-12 absolute on signals in [-1, 1]: the GPU sums the spins in
+    a tree and its cos() differs from libm's in the last ulp."""
+    g = mc_cases
+    n_spin = int(g["n_spin"])
+    for dim in (2, 3):
+        for ds in (1.0, 0.73):
+            got = mfu.monte_carlo_average(np.ascontiguousarray(g["phases"][:, :dim]), g["pick"].astype(np.int64),
+                                          np.ascontiguousarray(g["gsc"][:, :dim]), ds, n_spin)
+            assert got.shape == (g["pick"].size,) and got.dtype == np.float64
+            assert np.allclose(got, g["avg_d%d_s%g" % (dim, ds)], rtol=0, atol=1e-12)
+            assert np.allclose(got, orc.mc_average(g["phases"][:, :dim], g["pick"], g["gsc"][:, :dim], ds, n_spin),
+                               rtol=0, atol=1e-12)
+    # larger problem, single component: exact value for a constant phase, average of cos
+    ph = np.full((3 * 50000, 1), 0.5)
+    got = mfu.monte_carlo_average(ph, np.array([0, 2, 1], dtype=np.int64), np.array([[0.0], [1.0], [2.0]]), 1.0, 50000)
+    assert np.allclose(got, np.cos([0.0, 0.5, 1.0]), rtol=0, atol=1e-13)
+    with pytest.raises(IndexError):
+        mfu.monte_carlo_average(ph, np.array([3], dtype=np.int64), np.array([[1.0]]), 1.0, 50000)
+
+
+def test_get_PGSE_from_phases_matches_reference(mc_cases, tmp_path):
+    """File interface (mf_utils.py:2815-3015): phase files written like the simulator does
+    (big-endian double, little-endian single), (Delta, delta) mapping, gradient scaling,
+    diffusivity rescaling; error behaviour of the reference."""
+    g = mc_cases
+    for i, nm in enumerate("xyz"):
+        g["phases"][:, i].astype(">f8").tofile(str(tmp_path / ("sub_phase_%s.bdouble" % nm)))
+        g["phases"][:, i].astype("<f4").tofile(str(tmp_path / ("sub_phase_%s.lfloat" % nm)))
+    fx = str(tmp_path / "sub_phase_x.bdouble")
+    assert np.allclose(mfu.get_PGSE_from_phases(fx, g["sim"], g["new"]), g["file_bdouble_d3"], rtol=0, atol=1e-12)
+    assert np.allclose(mfu.get_PGSE_from_phases(fx, g["sim"], g["new"], dim=3, D_sim=2.0e-9, D=1.1e-9),
+                       g["file_bdouble_d3_D"], rtol=0, atol=1e-12)
+    assert np.allclose(mfu.get_PGSE_from_phases(str(tmp_path / "sub_phase_x.lfloat"), g["sim"], g["new2"], dim=2),
+                       g["file_lfloat_d2"], rtol=0, atol=1e-12)
+    with pytest.raises(NameError):
+        mfu.get_PGSE_from_phases(fx, g["sim"], g["new"], D=1e-9)
+    with pytest.raises(ValueError, match="dim should be"):
+        mfu.get_PGSE_from_phases(fx, g["sim"], g["new"], dim=4)
+    bad = g["new"].copy()
+    bad[3, 4] = 0.0333          # a Delta no simulated sequence used (TE stays >= Delta + delta)
+    with pytest.raises(ValueError, match="not used to simulate"):
+        mfu.get_PGSE_from_phases(fx, g["sim"], bad)
+    with pytest.raises(RuntimeError, match="does not exist"):
+        mfu.get_PGSE_from_phases(str(tmp_path / "nope_phase_x.bdouble"), g["sim"], g["new"])
+    with pytest.raises(ValueError, match="not supported"):
+        (tmp_path / "sub_phase_x.bint").write_bytes(b"0" * 24)
+        mfu.get_PGSE_from_phases(str(tmp_path / "sub_phase_x.bint"), g["sim"], g["new"])

@@ -132,3 +132,15 @@ def test_fit_rows_match_reference(ukbb, tag):
     ysq = np.sum(ukbb["data"][mask] ** 2, axis=1) / ukbb["data"].shape[-1]
     assert np.all(np.abs(rows[:, -2] - ref("MSE")) <= 1e-12 * ysq + 1e-9 * ref("MSE"))
     assert np.allclose(rows[:, -1], ref("R2"), rtol=1e-9, atol=1e-12)
+
+
+def test_mc_average_oracle_matches_reference():
+    """monte_carlo_average (mfu:2758-2812): the sequential C restatement against the
+    unmodified Numba kernel (tests/golden/mc_cases.npz, oracle/make_golden.py mc_cases)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mc_cases.npz"))
+    for dim in (2, 3):
+        for ds in (1.0, 0.73):
+            got = orc.mc_average(g["phases"][:, :dim], g["pick"], g["gsc"][:, :dim], ds, int(g["n_spin"]))
+            # same summation order; libm vs Numba's cos may differ in the last ulp per term
+            assert np.allclose(got, g["avg_d%d_s%g" % (dim, ds)], rtol=0, atol=1e-14)
