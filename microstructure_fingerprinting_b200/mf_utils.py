@@ -29,7 +29,7 @@ __all__ = ["solve_exhaustive_posweights", "solve_exhaustive_posweights_batch",
            "import_PGSE_scheme", "get_PGSE_scheme_from_bval_bvec_dense",
            "get_gyromagnetic_ratio", "DT_vec_to_2Darray", "loadmat", "from_ipython",
            "rotate_atom", "rotate_atom_2Dprotocol", "rotate_scheme_mat", "vrrotvec2mat",
-           "monte_carlo_average", "get_PGSE_from_phases",
+           "monte_carlo_average", "get_PGSE_from_phases", "solve_rotated_2Dprotocol_batch",
            "MultiShellTable", "SchemePlan", "GpuPlan"]
 
 
@@ -541,7 +541,7 @@ def solve_exhaustive_posweights(A, y, dicsizes, printmsg=None):
 # HARDI / AxCaliber rotations of an M-row dictionary (low-level API)
 # ----------------------------------------------------------------------------------
 
-def _lerp_rows(table, row_lo, row_hi, w_lo, w_hi, scale=None, device=0):
+def _lerp_rows(table, row_lo, row_hi, w_lo, w_hi, scale=None, device=0, return_device=False):
     """out[v, m, :] = scale * (w_hi * table[row_hi] + w_lo * table[row_lo]) on the GPU
     (mfb_lerp_rows).  Plan arrays are (V, M); returns a NumPy array (V, M, N)."""
     torch = _lib.require_cuda()
@@ -563,7 +563,7 @@ def _lerp_rows(table, row_lo, row_hi, w_lo, w_hi, scale=None, device=0):
                                        d_wl.data_ptr(), d_wh.data_ptr(),
                                        None if d_sc is None else d_sc.data_ptr(), out.data_ptr(), N, st)
     _lib.check(rc, "mfb_lerp_rows")
-    return out.cpu().numpy()
+    return out if return_device else out.cpu().numpy()
 
 
 def _lerp_plan(xs, x_new):
@@ -723,13 +723,225 @@ def _opposite_pairs(dirs_un):
     return np.where(np.isclose(dirs_un @ dirs_un.T, -1))
 
 
-def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF):
+class _Protocol2D(object):
+    """Direction-independent part of rotate_atom_2Dprotocol (reference
+    mf_utils.py:1440-1690): reference frame, lookup table of perpendicular signals, and per
+    (Delta, delta) pair the sorted signed-G nodes of every reference line."""
+
+    def __init__(self, sch_mat, refdir, DIFF):
+        if np.any(sch_mat[:, 2] != 0):
+            raise ValueError("Use the original schemefile with zeros for gz.\n"
+                             "Specify the reference and new orientations separately.")
+        sch = np.array(sch_mat, dtype=np.float64, copy=True)      # private: never touch the caller's
+        self.gam = get_gyromagnetic_ratio('H')
+        self.G, self.Delta, self.delta = sch[:, 3].copy(), sch[:, 4].copy(), sch[:, 5].copy()
+        self.is_b0, self.is_b = (self.G == 0), (self.G != 0)
+        self.M = M = sch.shape[0]
+        self.DIFF = DIFF
+        g_ref, nz_ref, Gperp_ref, Gpar_ref = _perp_frame(sch, refdir)
+        # NB: when refdir is the z axis _perp_frame normalised the in-plane directions of `sch`
+        # in place (like the reference); every new frame is computed from that state
+        assert np.all(np.isclose(self.G ** 2, Gperp_ref ** 2 + Gpar_ref ** 2)), \
+            "Inconsistency in parallel and perpendicular gradient components for reference fasicle."
+        self.S_par_ref = np.exp(-(self.gam * self.delta * Gpar_ref) ** 2 * (self.Delta - self.delta / 3) * DIFF)
+        assert np.all(np.isclose(self.S_par_ref[self.is_b0], 1)), \
+            "Reference fascicle: parallel signal should  be one in b0 sequences."
+        self.sch = sch
+        # unique laboratory gradient directions: sequences sharing one behave identically
+        self.lab_un, self.lab_id = np.unique(sch[:, 0:3], return_inverse=True, axis=0)
+        self.lab_id = np.ravel(self.lab_id)
+        pairs, pair_of = np.unique(sch[:, 4:6], return_inverse=True, axis=0)
+        self.pair_of = np.ravel(pair_of)
+        self.n_pairs = pairs.shape[0]
+        self.pairs = []
+        self.b0_row = np.full(self.n_pairs, -1, dtype=np.int64)    # table row of the shell's b0 signal
+        self.extra = []                                            # (pair, rows to average)
+        for ip in range(self.n_pairs):
+            ind = np.where(self.pair_of == ip)[0]
+            ref_un, ref_id = np.unique(g_ref[ind, :], return_inverse=True, axis=0)
+            ref_id = np.ravel(ref_id)
+            assert ref_un.shape[0] in (3, 5), (
+                "Problem at delta pair %d/%d: found %d unique gradient directions in plane perpendicular"
+                " to reference fascicle (including b0 zero dirs)." % (ip + 1, self.n_pairs, ref_un.shape[0]))
+            ig, ig_op = _opposite_pairs(ref_un)
+            assert ig.size in (2, 4), (
+                "Problem at delta pair %d/%d: found %d instead of 4 (2x2, redundant) pairs of opposite "
+                "directions in plane perpendicular to reference fascicle." % (ip + 1, self.n_pairs, ig.size))
+            lines = {}
+            for k in range(ig.size):          # nodes of the line through ref_un[ig[k]], signed along it
+                sel_ref = ind[(ref_id == ig[k]) | (ref_id == ig_op[k])]
+                Gs_ref = Gperp_ref[sel_ref] * np.sign(g_ref[sel_ref, :] @ ref_un[ig[k], :])
+                order = np.argsort(Gs_ref, kind="mergesort")        # interp1d(assume_sorted=False)
+                lines[int(ig[k])] = (Gs_ref[order], sel_ref[order])
+            b0s = np.where(self.is_b0 & (self.pair_of == ip))[0]
+            if b0s.size == 1:
+                self.b0_row[ip] = b0s[0]
+            elif b0s.size > 1:
+                self.b0_row[ip] = M + len(self.extra)
+                self.extra.append(b0s)
+            self.pairs.append({"ind": ind, "ref_un": ref_un, "lines": lines,
+                               "lab": np.unique(self.lab_id[ind])})
+
+    def table(self, sig):
+        """Lookup-table rows: perpendicular reference signals, then the mean b0 signal of the
+        (Delta, delta) pairs with several b0 sequences."""
+        S_perp_ref = sig / self.S_par_ref[:, np.newaxis]
+        if not self.extra:
+            return S_perp_ref
+        return np.vstack([S_perp_ref] + [np.mean(sig[rows, :], axis=0) for rows in self.extra])
+
+    def frames(self, newdirs):
+        """In-plane unit directions gp (V, U, 2), in-plane norms nrm (V, U) and |g_z| (V, U) of
+        the U unique laboratory directions seen from fascicles along newdirs (V, 3)
+        (rotate_scheme_mat + the in-plane normalisation of the reference, mfu:1153-1202,
+        1530-1535)."""
+        d = np.asarray(newdirs, dtype=np.float64)
+        V = d.shape[0]
+        if np.any(~np.isclose(np.sum(d ** 2, axis=1), 1)):
+            raise ValueError("cyldir1 and cyldir2 should have unit norm.")
+        U = self.lab_un.shape[0]
+        ax = np.stack([-d[:, 1], d[:, 0], np.zeros(V)], axis=1)          # cross(z, newdir)
+        n2 = np.sum(ax ** 2, axis=1)
+        rot = n2 > 0
+        g = np.broadcast_to(self.lab_un[np.newaxis], (V, U, 3)).copy()
+        if np.any(rot):
+            a = ax[rot] / np.sqrt(n2[rot])[:, np.newaxis]
+            ang = -np.arccos(d[rot, 2])
+            s_, c_ = np.sin(ang), np.cos(ang)
+            t_ = 1 - c_
+            x, y, z = a[:, 0], a[:, 1], a[:, 2]
+            R = np.empty((a.shape[0], 3, 3))
+            R[:, 0, 0], R[:, 0, 1], R[:, 0, 2] = t_ * x * x + c_, t_ * x * y - s_ * z, t_ * x * z + s_ * y
+            R[:, 1, 0], R[:, 1, 1], R[:, 1, 2] = t_ * x * y + s_ * z, t_ * y * y + c_, t_ * y * z - s_ * x
+            R[:, 2, 0], R[:, 2, 1], R[:, 2, 2] = t_ * x * z - s_ * y, t_ * y * z + s_ * x, t_ * z * z + c_
+            gr = np.matmul(self.lab_un[np.newaxis], np.transpose(R, (0, 2, 1)))   # (Vr, U, 3)
+            gr[np.abs(gr) <= np.finfo(float).eps] = 0
+            gn = np.sqrt(np.sum(gr ** 2, axis=2, keepdims=True))
+            np.divide(gr, gn, out=gr, where=gn > 0)
+            g[rot] = gr
+        gp = g[:, :, 0:2].copy()
+        nrm = np.sqrt(np.sum(gp ** 2, axis=2))
+        np.divide(gp, nrm[:, :, np.newaxis], out=gp, where=(nrm > 0)[:, :, np.newaxis])
+        return gp, nrm, np.abs(g[:, :, 2])
+
+    def plan(self, newdirs, strict=True):
+        """Interpolation plan of every sequence for every direction: (row_lo, row_hi, w_lo,
+        w_hi, scale), each (V, M).  strict=True raises the reference's AssertionError when a
+        direction breaks the protocol's assumptions (e.g. a fascicle in the gradient plane,
+        which projects both gradient lines onto one); strict=False returns a sixth array
+        ok (V,) instead and gives those directions an all-zero plan."""
+        gp, nrm, gz = self.frames(newdirs)
+        bad = np.zeros(gp.shape[0], dtype=bool)
+        V, M = gp.shape[0], self.M
+        G = self.G
+        Gperp = G[np.newaxis, :] * nrm[:, self.lab_id]
+        Gpar = gz[:, self.lab_id] * G[np.newaxis, :]
+        assert np.all(np.isclose(G[np.newaxis, :] ** 2, Gperp ** 2 + Gpar ** 2)), \
+            "Inconsistency in parallel and perpendicular gradient components for new fascicle."
+        S_par = np.exp(-(self.gam * self.delta[np.newaxis, :] * Gpar) ** 2 *
+                       (self.Delta - self.delta / 3)[np.newaxis, :] * self.DIFF)
+        assert np.all(np.isclose(S_par[:, self.is_b0], 1)), \
+            "New fascicle: parallel signal should  be equal to 1 in b0 sequences."
+        row_lo = np.broadcast_to(np.arange(M, dtype=np.int32), (V, M)).copy()   # b0: own row
+        row_hi = row_lo.copy()
+        w_lo, w_hi = np.ones((V, M)), np.zeros((V, M))
+        covered = np.broadcast_to(self.is_b0, (V, M)).copy()
+        for ip, pr in enumerate(self.pairs):
+            ind, lab, ref_un = pr["ind"], pr["lab"], pr["ref_un"]
+            P = lab.size
+            rows = gp[:, lab, :]                                         # (V, P, 2)
+            # np.unique(axis=0) of each voxel's rows: lexicographic sort + exact duplicates
+            order = np.lexsort((rows[:, :, 1], rows[:, :, 0]), axis=-1)   # (V, P)
+            srt = np.take_along_axis(rows, order[:, :, np.newaxis], axis=1)
+            first = np.ones((V, P), dtype=bool)
+            first[:, 1:] = np.any(srt[:, 1:, :] != srt[:, :-1, :], axis=2)
+            uid_sorted = np.cumsum(first, axis=1) - 1                    # unique index of sorted row
+            n_un = uid_sorted[:, -1] + 1
+            bad_here = (n_un != 3) & (n_un != 5)
+            bad |= bad_here
+            if strict and np.any(bad_here):
+                v = int(np.where(bad_here)[0][0])
+                raise AssertionError(
+                    "Problem at delta pair %d/%d: found %d unique gradient directions in plane perpendicular to "
+                    "new fascicle (including b0 zero dirs)." % (ip + 1, self.n_pairs, n_un[v]))
+            new_id = np.empty((V, P), dtype=np.int64)                    # unique index of lab dir lab[j]
+            np.put_along_axis(new_id, order, uid_sorted, axis=1)
+            # opposite pairs among the unique rows; a line is named by its lower unique index
+            dots = np.einsum('vik,vjk->vij', srt, srt)
+            opp = np.isclose(dots, -1) & first[:, :, np.newaxis] & first[:, np.newaxis, :]
+            opp &= np.triu(np.ones((P, P), dtype=bool), 1)[np.newaxis]
+            n_lines = opp.sum(axis=(1, 2))
+            bad_here = (n_lines != 1) & (n_lines != 2)
+            bad |= bad_here
+            if strict and np.any(bad_here):
+                v = int(np.where(bad_here)[0][0])
+                raise AssertionError(
+                    "Problem at delta pair %d/%d: found %d instead of 2 pairs of opposite directions, in plane "
+                    " perpendicular to new fascicle." % (ip + 1, self.n_pairs, n_lines[v]))
+            # per sorted row: is it the lower / upper member of a line?
+            lower = opp.any(axis=2)                                      # (V, P) sorted position i of (i, j)
+            upper = opp.any(axis=1)
+            partner_of_upper = np.argmax(opp, axis=1)                    # for sorted j: its i
+            # gradients that became parallel to the new fascicle: mean b0 signal of the shell
+            for j in range(P):
+                m_rows = ind[self.lab_id[ind] == lab[j]]
+                if not np.any(self.is_b[m_rows]):
+                    continue                                             # the b0 "direction"
+                mb = m_rows[self.is_b[m_rows]]
+                van = ~(nrm[:, lab[j]] > 0)                              # (V,)
+                if np.any(van):
+                    assert self.b0_row[ip] >= 0, (
+                        "Shell %d/%d: some new line directions are completely parallel to new fascicle, "
+                        "implying free diffusion. However, no b0 measurements in the reference signal are "
+                        "available for this shell. We therefore can't properly scale the new signal."
+                        % (ip + 1, self.n_pairs))
+                    vv = np.where(van)[0][:, np.newaxis]
+                    row_lo[vv, mb[np.newaxis, :]] = row_hi[vv, mb[np.newaxis, :]] = self.b0_row[ip]
+                    w_lo[vv, mb[np.newaxis, :]], w_hi[vv, mb[np.newaxis, :]] = 1.0, 0.0
+                    covered[vv, mb[np.newaxis, :]] = True
+                # the first sorted row of this direction's unique class carries the line flags
+                ar = np.arange(V)
+                rep = np.argmax(uid_sorted == new_id[:, j][:, np.newaxis], axis=1)
+                is_lo, is_up = lower[ar, rep], upper[ar, rep]
+                on_line = (is_lo | is_up) & ~van & ~bad
+                if not np.any(on_line):
+                    continue
+                assert np.all(self.is_b[mb]), (
+                    "Problem at delta pair %d/%d: trying to interpolate b0 sequences." % (ip + 1, self.n_pairs))
+                line_pos = np.where(is_lo, rep, partner_of_upper[ar, rep])   # sorted position of line_new
+                line_new = srt[ar, line_pos, :]                          # (V, 2)
+                sgn = np.sign(np.sum(rows[:, j, :] * line_new, axis=1))  # (V,)
+                i_max = np.argmax(line_new @ ref_un.T, axis=1)           # closest reference line
+                for im in np.unique(i_max[on_line]):
+                    vs = np.where(on_line & (i_max == im))[0]
+                    if int(im) not in pr["lines"]:
+                        raise ValueError("rotate_atom_2Dprotocol: no reference line matches a new line "
+                                         "direction at delta pair %d/%d" % (ip + 1, self.n_pairs))
+                    nodes, node_rows = pr["lines"][int(im)]
+                    x = Gperp[vs[:, np.newaxis], mb[np.newaxis, :]] * sgn[vs][:, np.newaxis]
+                    lo, hi, wl, wh = _lerp_plan(nodes, x)
+                    vv = vs[:, np.newaxis]
+                    row_lo[vv, mb[np.newaxis, :]], row_hi[vv, mb[np.newaxis, :]] = node_rows[lo], node_rows[hi]
+                    w_lo[vv, mb[np.newaxis, :]], w_hi[vv, mb[np.newaxis, :]] = wl, wh
+                    covered[vv, mb[np.newaxis, :]] = True
+        # sequences no rule reached keep a zero perpendicular signal, like the reference
+        scale = np.where(covered, S_par, 0.0)
+        if strict:
+            return row_lo, row_hi, w_lo, w_hi, scale
+        scale[bad, :] = 0.0
+        return row_lo, row_hi, w_lo, w_hi, scale, ~bad
+
+
+def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF, return_device=False):
     """Rotate signals of a 2D AxCaliber-like protocol (gradients in the xy plane, pairs of
     opposite polarities along one or two lines) from a fascicle along `refdir` to `newdir`
     (reference mf_utils.py:1440-1690): signal = parallel free-diffusion factor times the
     perpendicular signal, the latter interpolated linearly in the signed perpendicular
     gradient intensity along the closest reference line, per (Delta, delta) pair.
-    """
+
+    Extension: `newdir` of shape (V, 3) rotates to V directions at once (one vectorised host
+    plan, one GPU launch) and returns (V,) + sig.shape; with return_device=True the result
+    stays on the GPU as a torch tensor (V, M, N)."""
     sig_shape = sig.shape
     if sig.ndim == 1:
         sig = sig[:, np.newaxis]
@@ -740,100 +952,108 @@ def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF):
         raise ValueError("Signal and scheme matrix must have the same "
                          "number of elements (sequences) along their first"
                          " dimension. Detected %d and %d." % (sig_shape[0], sch_mat.shape[0]))
-    sch_mat = np.array(sch_mat, dtype=np.float64, copy=True)   # private: never touch the caller's
-    gam = get_gyromagnetic_ratio('H')
-    G, Delta, delta = sch_mat[:, 3], sch_mat[:, 4], sch_mat[:, 5]
-    is_b0, is_b = (G == 0), (G != 0)
-    M = sch_mat.shape[0]
+    newdir = np.asarray(newdir, dtype=np.float64)
+    batched = newdir.ndim == 2
+    proto = _Protocol2D(sch_mat, refdir, DIFF)
+    row_lo, row_hi, w_lo, w_hi, scale = proto.plan(newdir.reshape(-1, 3))
+    out = _lerp_rows(proto.table(sig), row_lo, row_hi, w_lo, w_hi, scale, return_device=return_device)
+    if return_device:
+        return out
+    if batched:
+        return out.reshape((newdir.shape[0],) + sig_shape)
+    return np.reshape(out[0], sig_shape)
 
-    g_ref, nz_ref, Gperp_ref, Gpar_ref = _perp_frame(sch_mat, refdir)
-    assert np.all(np.isclose(G ** 2, Gperp_ref ** 2 + Gpar_ref ** 2)), \
-        "Inconsistency in parallel and perpendicular gradient components for reference fasicle."
-    S_par_ref = np.exp(-(gam * delta * Gpar_ref) ** 2 * (Delta - delta / 3) * DIFF)
-    assert np.all(np.isclose(S_par_ref[is_b0], 1)), \
-        "Reference fascicle: parallel signal should  be one in b0 sequences."
-    S_perp_ref = sig / S_par_ref[:, np.newaxis]          # lookup-table rows 0..M-1
 
-    g_new, nz_new, Gperp_new, Gpar_new = _perp_frame(sch_mat, newdir)
-    assert np.all(np.isclose(G ** 2, Gperp_new ** 2 + Gpar_new ** 2)), \
-        "Inconsistency in parallel and perpendicular gradient components for new fascicle."
-    S_par_new = np.exp(-(gam * delta * Gpar_new) ** 2 * (Delta - delta / 3) * DIFF)
-    assert np.all(np.isclose(S_par_new[is_b0], 1)), \
-        "New fascicle: parallel signal should  be equal to 1 in b0 sequences."
+def solve_rotated_2Dprotocol_batch(sig, sch_mat, refdir, peaks, Y, DIFF, sig_iso=None, chunk=48, device=0):
+    """Low-level AxCaliber-like pipeline for many voxels (extension; per voxel it is what the
+    reference's users write by hand, cf. tests/integration/test_exhaustive_fingerprinting.py:163-249):
 
-    # interpolation plan: b0 sequences copy their own row
-    row_lo = np.arange(M, dtype=np.int32)
-    row_hi = np.arange(M, dtype=np.int32)
-    w_lo, w_hi = np.ones(M), np.zeros(M)
-    extra_rows = []
-    covered = is_b0.copy()
+        D_k = rotate_atom_2Dprotocol(sig, sch_mat, refdir, peaks[v, k], DIFF)      k = 0 .. K-1
+        solve_exhaustive_posweights([D_0 .. D_{K-1} (, sig_iso)], Y[v], [N] * K (+ [1]))
 
-    pairs, pair_of = np.unique(sch_mat[:, 4:6], return_inverse=True, axis=0)
-    pair_of = np.ravel(pair_of)
-    for ip in range(pairs.shape[0]):
-        in_pair = pair_of == ip
-        ind = np.where(in_pair)[0]
-        ref_un, ref_id = np.unique(g_ref[ind, :], return_inverse=True, axis=0)
-        ref_id = np.ravel(ref_id)
-        assert ref_un.shape[0] in (3, 5), (
-            "Problem at delta pair %d/%d: found %d unique gradient directions in plane perpendicular"
-            " to reference fascicle (including b0 zero dirs)." % (ip + 1, pairs.shape[0], ref_un.shape[0]))
-        ig, ig_op = _opposite_pairs(ref_un)
-        assert ig.size in (2, 4), (
-            "Problem at delta pair %d/%d: found %d instead of 4 (2x2, redundant) pairs of opposite "
-            "directions in plane perpendicular to reference fascicle." % (ip + 1, pairs.shape[0], ig.size))
-        new_un, new_id = np.unique(g_new[ind, :], return_inverse=True, axis=0)
-        new_id = np.ravel(new_id)
-        assert new_un.shape[0] in (3, 5), (
-            "Problem at delta pair %d/%d: found %d unique gradient directions in plane perpendicular to "
-            "new fascicle (including b0 zero dirs)." % (ip + 1, pairs.shape[0], new_un.shape[0]))
-        pn, pn_op = _opposite_pairs(new_un)
-        upper = pn < pn_op
-        pn, pn_op = pn[upper], pn_op[upper]
-        assert pn.size in (1, 2), (
-            "Problem at delta pair %d/%d: found %d instead of 2 pairs of opposite directions, in plane "
-            " perpendicular to new fascicle." % (ip + 1, pairs.shape[0], pn.size))
+    sig (M, N) single-fascicle dictionary along refdir, peaks (V, K, 3) unit vectors with
+    K = 2, Y (V, M), optional isotropic column sig_iso (M,).  The interpolation plans of a
+    chunk of voxels are built on the host (vectorised, in a worker thread, while the GPU
+    searches the previous chunk), the rotated dictionaries are assembled on the GPU
+    (mfb_lerp_rows) and never leave it, the search is mfb_solve_batch.
 
-        # gradients that became parallel to the new fascicle: mean b0 signal of the shell
-        vanished = ~nz_new & is_b & in_pair
-        shell_b0 = is_b0 & in_pair
-        if np.sum(vanished) > 0:
-            assert np.sum(shell_b0) > 0, (
-                "Shell %d/%d: some new line directions are completely parallel to new fascicle, "
-                "implying free diffusion. However, no b0 measurements in the reference signal are "
-                "available for this shell. We therefore can't properly scale the new signal."
-                % (ip + 1, pairs.shape[0]))
-            if np.sum(shell_b0) == 1:
-                row_lo[vanished] = row_hi[vanished] = np.where(shell_b0)[0][0]
-            else:
-                extra_rows.append(np.mean(sig[shell_b0, :], axis=0))
-                row_lo[vanished] = row_hi[vanished] = M + len(extra_rows) - 1
-            w_lo[vanished], w_hi[vanished] = 1.0, 0.0
-            covered |= vanished
+    Returns (w (V, nb), ind_subdic (V, nb) int32, min_obj (V,), ok (V,) bool); voxels whose
+    peak breaks the protocol's assumptions (reference AssertionError, e.g. a fascicle lying
+    in the gradient plane) have ok = False and zero outputs."""
+    import threading
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device('cuda', device)
+    sig = np.ascontiguousarray(sig, dtype=np.float64)
+    peaks = np.ascontiguousarray(peaks, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    V, K = peaks.shape[0], peaks.shape[1]
+    M, N = sig.shape
+    if K != 2 or peaks.shape[2] != 3:
+        raise ValueError("peaks should have shape (V, 2, 3)")
+    if Y.shape != (V, M):
+        raise ValueError("Y should have shape (%d, %d)" % (V, M))
+    iso = 0 if sig_iso is None else 1
+    ntot = K * N + iso
+    sizes = np.ascontiguousarray(np.array([N] * K + [1] * iso, dtype=np.int64))
+    nb = sizes.size
+    proto = _Protocol2D(sch_mat, refdir, DIFF)
+    d_table = torch.from_numpy(np.ascontiguousarray(proto.table(sig))).to(dev)
+    d_iso = None if sig_iso is None else torch.from_numpy(np.ascontiguousarray(sig_iso, dtype=np.float64)).to(dev)
+    w_out = np.zeros((V, nb))
+    sub_out = np.zeros((V, nb), dtype=np.int32)
+    obj_out = np.zeros(V)
+    ok_out = np.zeros(V, dtype=bool)
+    chunks = [(s0, min(V, s0 + chunk)) for s0 in range(0, V, chunk)]
 
-        for il in range(pn.size):
-            line_new = new_un[pn[il], :]
-            sel_new = ind[(new_id == pn[il]) | (new_id == pn_op[il])]
-            assert np.all(is_b[sel_new]), (
-                "Problem at delta pair %d/%d, new line direction %d/%d: trying to interpolate b0 "
-                "sequences." % (ip + 1, pairs.shape[0], il, pn.size))
-            Gs_new = Gperp_new[sel_new] * np.sign(g_new[sel_new, :] @ line_new)
-            i_max = np.argmax(ref_un @ line_new)     # closest reference line
-            line_ref = ref_un[i_max, :]
-            k = np.where(i_max == ig)[0]
-            sel_ref = ind[(ref_id == ig[k]) | (ref_id == ig_op[k])]
-            Gs_ref = Gperp_ref[sel_ref] * np.sign(g_ref[sel_ref, :] @ line_ref)
-            order = np.argsort(Gs_ref, kind="mergesort")   # interp1d(assume_sorted=False)
-            lo, hi, wl, wh = _lerp_plan(Gs_ref[order], Gs_new)
-            row_lo[sel_new], row_hi[sel_new] = sel_ref[order][lo], sel_ref[order][hi]
-            w_lo[sel_new], w_hi[sel_new] = wl, wh
-            covered[sel_new] = True
-    table = S_perp_ref if not extra_rows else np.vstack([S_perp_ref] + extra_rows)
-    # sequences no rule reached keep a zero perpendicular signal, like the reference
-    scale = np.where(covered, S_par_new, 0.0)
-    out = _lerp_rows(table, row_lo[None, :], row_hi[None, :], w_lo[None, :], w_hi[None, :],
-                     scale[None, :])[0]
-    return np.reshape(out, sig_shape)
+    def make_plan(c):
+        s0, s1 = chunks[c]
+        return proto.plan(peaks[s0:s1].reshape(-1, 3), strict=False)
+
+    nxt = {}
+
+    def worker(c):
+        try:
+            nxt[c] = make_plan(c)
+        except Exception as exc:       # re-raised in the main thread
+            nxt[c] = exc
+    if chunks:
+        worker(0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    for c, (s0, s1) in enumerate(chunks):
+        plan = nxt.pop(c)
+        if isinstance(plan, Exception):
+            raise plan
+        th = None
+        if c + 1 < len(chunks):
+            th = threading.Thread(target=worker, args=(c + 1,))
+            th.start()
+        nv = s1 - s0
+        rl, rh, wl, wh, sc, ok = plan
+        okv = ok.reshape(nv, K).all(axis=1)
+        d_pl = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (rl, rh, wl, wh, sc)]
+        A = torch.empty((nv, M, ntot), dtype=torch.float64, device=dev)
+        if iso:
+            A[:, :, K * N] = d_iso[None, :]
+        with torch.cuda.device(dev):
+            for k in range(K):
+                # directions are ordered (voxel, fascicle): fascicle k of every voxel is a strided view
+                pk = [x.view(nv, K, M)[:, k, :].contiguous() for x in d_pl]
+                rc = lib.mfb_lerp_rows(device, nv, M, N, d_table.data_ptr(), pk[0].data_ptr(), pk[1].data_ptr(),
+                                       pk[2].data_ptr(), pk[3].data_ptr(), pk[4].data_ptr(),
+                                       A.data_ptr() + 8 * k * N, ntot, st)
+                _lib.check(rc, "mfb_lerp_rows")
+        good = np.where(okv)[0]
+        if good.size:
+            gi = torch.from_numpy(good).to(dev)
+            Ag = A if good.size == nv else A.index_select(0, gi).contiguous()
+            Yg = torch.from_numpy(Y[s0:s1][good]).to(dev)
+            w, sub, tot, obj, _ = solve_exhaustive_posweights_batch(Ag, Yg, sizes, device=device, return_device=True)
+            w_out[s0 + good], sub_out[s0 + good], obj_out[s0 + good] = w.cpu().numpy(), sub.cpu().numpy(), obj.cpu().numpy()
+            ok_out[s0 + good] = True
+        if th is not None:
+            th.join()
+    return w_out, sub_out, obj_out, ok_out
 
 
 # ----------------------------------------------------------------------------------

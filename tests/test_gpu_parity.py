@@ -603,3 +603,46 @@ def test_get_PGSE_from_phases_matches_reference(mc_cases, tmp_path):
     with pytest.raises(ValueError, match="not supported"):
         (tmp_path / "sub_phase_x.bint").write_bytes(b"0" * 24)
         mfu.get_PGSE_from_phases(str(tmp_path / "sub_phase_x.bint"), g["sim"], g["new"])
+
+
+def test_rotate_atom_2d_batched_and_pipeline(lowlevel):
+    """Batched rotate_atom_2Dprotocol (one vectorised host plan, one launch) equals the
+    per-direction calls, and the chunked AxCaliber pipeline (plans on the host in a worker
+    thread, dictionaries assembled and searched on the GPU) equals the hand-written
+    per-voxel sequence rotate_atom_2Dprotocol x 2 + solve_exhaustive_posweights."""
+    g = lowlevel
+    ref = np.array([0.0, 0.0, 1.0])
+    sig, sch, DIFF = g["ax_sig"], g["ax_sch"], float(g["ax_DIFF"])
+    batch = mfu.rotate_atom_2Dprotocol(sig, sch, ref, g["ax_dirs"], DIFF)
+    assert batch.shape == (g["ax_dirs"].shape[0],) + sig.shape
+    for v, want in enumerate(g["ax_rot"]):
+        assert np.allclose(batch[v], want, rtol=1e-12, atol=1e-300)
+        assert np.array_equal(batch[v], mfu.rotate_atom_2Dprotocol(sig, sch, ref, g["ax_dirs"][v], DIFF))
+    # a fascicle in the gradient plane projects both gradient lines onto one: reference AssertionError
+    with pytest.raises(AssertionError, match="pairs of opposite directions"):
+        mfu.rotate_atom_2Dprotocol(sig, sch, ref, np.array([np.sqrt(0.5), np.sqrt(0.5), 0.0]), DIFF)
+
+    # pipeline on a richer dictionary: scaled / mixed copies of the fixture atoms
+    rng = np.random.default_rng(12)
+    N = 24
+    mix = rng.random((sig.shape[1], N)) + 0.05
+    dic = sig @ (mix / mix.sum(axis=0, keepdims=True))
+    V = 20
+    peaks = rng.standard_normal((V, 2, 3))
+    peaks[:, :, 2] += np.sign(peaks[:, :, 2]) * 1.0            # away from the gradient plane
+    peaks /= np.linalg.norm(peaks, axis=2, keepdims=True)
+    peaks[3, 1] = [np.sqrt(0.5), np.sqrt(0.5), 0.0]            # breaks the protocol's assumptions
+    Y = np.zeros((V, sig.shape[0]))
+    truth = rng.integers(0, N, (V, 2))
+    for v in range(V):
+        if v == 3:
+            continue
+        D = [mfu.rotate_atom_2Dprotocol(dic, sch, ref, peaks[v, k], DIFF) for k in range(2)]
+        Y[v] = 0.6 * D[0][:, truth[v, 0]] + 0.4 * D[1][:, truth[v, 1]] + 1e-3 * rng.standard_normal(sig.shape[0])
+    w, sub, obj, ok = mfu.solve_rotated_2Dprotocol_batch(dic, sch, ref, peaks, Y, DIFF, chunk=7)
+    assert not ok[3] and ok.sum() == V - 1
+    for v in (0, 1, 5, 19):
+        D = np.hstack([mfu.rotate_atom_2Dprotocol(dic, sch, ref, peaks[v, k], DIFF) for k in range(2)])
+        w1, sub1, tot1, obj1, _ = mfu.solve_exhaustive_posweights(D, Y[v].copy(), np.array([N, N]))
+        assert np.array_equal(sub[v], sub1) and np.array_equal(w[v], w1) and obj[v] == obj1
+        assert np.array_equal(sub[v], truth[v])
