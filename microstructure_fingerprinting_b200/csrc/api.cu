@@ -440,6 +440,9 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             MFB_CUDA_TRY(cudaMemcpyAsync(head, redo_count, sizeof(head), cudaMemcpyDeviceToHost, st));
             MFB_CUDA_TRY(cudaStreamSynchronize(st));
             const int32_t n_redo = head[0];
+            if (getenv("MFB_FAST_DEBUG") && (atoi(getenv("MFB_FAST_DEBUG")) & 8))
+                fprintf(stderr, "[mfb] %lld voxels: %d rare-path warp entries, %d competitive pairs\n",
+                        (long long)cnt, head[5], head[6]);
             pl->stats[0] += (double)(cnt - n_redo);
             pl->stats[6] += head[2];          // ill-conditioned competitor
             pl->stats[7] += head[3] + 1e-6 * head[4] ;  // near ties (+ 1e-6 * pair-independent branch)

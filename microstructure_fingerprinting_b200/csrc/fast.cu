@@ -37,10 +37,14 @@ namespace mfb {
 #define FT_S1 (FT_TI + 4)  // row strides: == 4 mod 16 doubles -> conflict-free fragment loads
 #define FT_S2 (FT_TJ + 4)
 #define FT_NPAR 7          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu
+#define FT_VP 12           // per-voxel scalars (voxp): see FastArgs
 
 // 1 - rho^2 below which a pair is tracked as ill-conditioned (its screening error bound
 // c0 / det is no longer small against typical gaps between competing pairs)
 static constexpr double kIllDet = 1e-4;
+// A competitive pair / tuple whose (refined) error bound exceeds kIllTol * c0 is tracked as
+// ill-conditioned: it can win only through the exact tier.
+static constexpr double kIllTol = 64.0;
 
 struct FastArgs {
     DevPlan p;         // table source: rotation plan; explicit source: only p.M is used
@@ -72,7 +76,8 @@ struct FastArgs {
     int Mp;            // M padded to a multiple of 4
     int Npad;          // max(N1, N2) padded to a multiple of FT_TJ
     int ntI;           // i1 tiles per voxel
-    int debug;            // timing experiments only (MFB_FAST_DEBUG): 1 skip epilogue, 2 skip gathers
+    int debug;            // experiments only (MFB_FAST_DEBUG): 1 skip epilogue, 2 skip gathers (timing, results
+                          // invalid); 4 keep the Cramer-form error bound (no refinement)
     const int32_t *vox_list;
     const double *peaks;
     int peaks_ld;
@@ -80,7 +85,7 @@ struct FastArgs {
     int *ip_rows;      // [v][2][M][2]  rl, rh
     double *ip_w;      // [v][2][M][2]  wl, wh
     double *colp;      // [v][2][FT_NPAR][Npad]
-    double *voxp;      // [v][8]  y_sq, A33, Y3, gain_c, c0, Gpre(fasc 0), Gpre(fasc 1), -
+    double *voxp;      // [v][FT_VP]  y_sq, A33, Y3, gain_c, c0, Gpre(block 0..2), best single atom of block 0..2, -
     double *cta_gain;  // [v][ntI]
     double *cta_tol;   // [v][ntI]
     int *cta_idx;      // [v][ntI]
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     const double gain_c = (a.csf && Y3 > 0) ? Y3 * Y3 / A33 : 0.0;
     double *cp = a.colp + (v * a.nblk + k) * (int64_t)FT_NPAR * a.Npad;
     double gbest = 0.0;
+    int ibest = 0;
     for (int i = threadIdx.x; i < a.Npad; i += blockDim.x) {
         double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0};
         if (i < Nk) {
@@ -192,7 +198,8 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
             if (!a.csf) {
                 par[0] = r;            // scale
                 par[2] = dy * r;       // z
-                gbest = fmax(gbest, dy > 0 ? dy * dy / sq : 0.0);
+                const double gi = dy > 0 ? dy * dy / sq : 0.0;
+                if (gi > gbest) { gbest = gi; ibest = i; }
             } else {
                 const double gam = d3 * r * rsqrt(A33);      // corr(atom, csf)
                 const double kap2 = fmax(1.0 - gam * gam, 1e-300);
@@ -206,15 +213,24 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
                 par[4] = kap;
                 par[5] = gam;
                 par[6] = dy * r;                             // zu
-                gbest = fmax(gbest, nnls2_gain(sq, d3, A33, dy, Y3));
+                const double gi = nnls2_gain(sq, d3, A33, dy, Y3);
+                if (gi > gbest) { gbest = gi; ibest = i; }
             }
         }
         for (int q = 0; q < FT_NPAR; q++) cp[(size_t)q * a.Npad + i] = par[q];
     }
+    const double gmine = gbest;
     gbest = block_max(gbest, red);
+    // atom holding the best single-column gain (lowest index on ties): the pair scan starts there
+    __shared__ int s_ibest;
+    if (threadIdx.x == 0) s_ibest = INT_MAX;
+    __syncthreads();
+    if (gmine == gbest) atomicMin(&s_ibest, ibest);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        double *vp = a.voxp + v * 8;
+        double *vp = a.voxp + v * FT_VP;
         vp[5 + k] = fmax(gbest, gain_c);   // slots 5, 6, 7: blocks 0, 1, 2
+        vp[8 + k] = (double)s_ibest;
         if (k == 0) {
             vp[0] = y_sq; vp[1] = A33; vp[2] = Y3; vp[3] = gain_c;
             vp[4] = 4.0 * (M + 8) * 2.2204e-16 * y_sq;   // c0: screening error scale
@@ -231,17 +247,19 @@ template <int CSF>
 __device__ __forceinline__ bool pair_gain(double rho, double z1, double z2, double b1, double b2,
                                           double k1, double k2, double g1, double g2, double zu1,
                                           double zu2, double Y3, double gain_c, double &num,
-                                          double &det)
+                                          double &det, double &re, double &za, double &zb, double &gadd)
 {
     const double w1 = fma(-rho, z2, z1);
     const double w2 = fma(-rho, z1, z2);
     det = fma(-rho, rho, 1.0);
     num = fma(z1, w1, z2 * w2);
+    re = rho; za = z1; zb = z2; gadd = 0.0;     // the 2 x 2 system the gain belongs to
     bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
     if (CSF) {
         const double w3 = fma(-b2, w2, fma(-b1, w1, Y3 * det));
         pos = pos && (__double2hiint(w3) > 0);
         num = fma(gain_c, det, num);
+        gadd = gain_c;
         if (!pos) {
             // best of the 2-column sub-problems: only the fascicle pair depends on (i1, i2);
             // the atom + CSF ones are pair-independent and live in gpre
@@ -251,9 +269,25 @@ __device__ __forceinline__ bool pair_gain(double rho, double z1, double z2, doub
             pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
             det = fma(-r, r, 1.0);
             num = fma(zu1, v1, zu2 * v2);
+            re = r; za = zu1; zb = zu2; gadd = 0.0;
         }
     }
     return pos;
+}
+
+// Rare path: sharpen (gain, error bound) of a competitive pair.  The Cramer form num / det
+// loses c0 / det to cancellation; the stationary form 2 w.z - w'Gw evaluated at the Cramer
+// weights is second order in their error, so its bound only carries the input errors of the
+// correlations and projections (relative c1 = c0 / |y|^2) times (|w|_1^2 + |w|_1 |y|).
+__device__ __forceinline__ void refine_pair(double re, double za, double zb, double gadd, double rdet,
+                                            double c0, double c1, double y_sq, double &gq, double &tq)
+{
+    const double w1 = fma(-re, zb, za) * rdet, w2 = fma(-re, za, zb) * rdet;
+    const double gr = 2.0 * fma(w1, za, w2 * zb) - fma(w1, w1, fma(w2, w2, 2.0 * re * w1 * w2)) + gadd;
+    const double sw = fabs(w1) + fabs(w2), rel = c1 * rdet;
+    // |w|_1 |y| <= (|w|_1^2 + |y|^2) / 2
+    const double tr = fma(1.5 * c1, sw * sw, fma(4.0 * rel * rel, y_sq, (gadd != 0.0 ? 1.5 : 0.5) * c0));
+    if (tr < tq) { gq = gr; tq = tr; }
 }
 
 // ---- mbarrier helpers (producer / consumer ring) ----
@@ -280,6 +314,64 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 __device__ __forceinline__ void consumer_sync()
 {
     asm volatile("bar.sync 1, %0;" ::"n"(FT_CONS) : "memory");
+}
+
+// Seed of the voxel-wide screening threshold: the certified lower bound of the gain of ONE
+// real pair, (best single atom of block 1, best single atom of block 2).  Without it every
+// warp's first tile floods the competitive-pair path (any pair beats the single-atom bound).
+// grid V, one warp.
+__global__ void __launch_bounds__(32) k_fast_seed(FastArgs a)
+{
+    const DevPlan &p = a.p;
+    const int M = p.M, lane = threadIdx.x;
+    const int64_t v = blockIdx.x;
+    const double *vp = a.voxp + v * FT_VP;
+    const int i1 = max(0, min(a.N1 - 1, (int)vp[8])), i2 = max(0, min(a.N2 - 1, (int)vp[9]));
+    const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
+    const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
+    const int64_t row = a.vox_list ? a.vox_list[v] : v;
+    const double *Ar = a.src ? a.A + (a.a_by_local ? v : row) * a.strideA : nullptr;
+    const double sc1 = cp1[i1], sc2 = cp2[i2];
+    const double al1 = a.csf ? cp1[(size_t)a.Npad + i1] : 0.0, al2 = a.csf ? cp2[(size_t)a.Npad + i2] : 0.0;
+    double acc = 0.0;
+    for (int m = lane; m < M; m += 32) {
+        double d1, d2;
+        if (a.src) {
+            d1 = Ar[(size_t)m * a.lda + a.start1 + i1];
+            d2 = Ar[(size_t)m * a.lda + a.start2 + i2];
+        } else {
+            const int64_t o1 = ((v * 2 + 0) * M + m) * 2, o2 = ((v * 2 + 1) * M + m) * 2;
+            d1 = fma(a.ip_w[o1 + 1], p.table[(size_t)a.ip_rows[o1 + 1] * p.N + i1],
+                     a.ip_w[o1] * p.table[(size_t)a.ip_rows[o1] * p.N + i1]);
+            d2 = fma(a.ip_w[o2 + 1], p.table[(size_t)a.ip_rows[o2 + 1] * p.N + i2],
+                     a.ip_w[o2] * p.table[(size_t)a.ip_rows[o2] * p.N + i2]);
+        }
+        if (a.csf) {
+            const double c = a.src ? Ar[(size_t)m * a.lda + a.start3] : p.sig_csf[m];
+            d1 = fma(-al1, c, d1);
+            d2 = fma(-al2, c, d2);
+        }
+        acc = fma(d1 * sc1, d2 * sc2, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const double c0 = vp[4];
+        double num, det, re, za, zb, gadd;
+        bool pos;
+        if (a.csf)
+            pos = pair_gain<1>(acc, cp1[(size_t)2 * a.Npad + i1], cp2[(size_t)2 * a.Npad + i2],
+                               cp1[(size_t)3 * a.Npad + i1], cp2[(size_t)3 * a.Npad + i2],
+                               cp1[(size_t)4 * a.Npad + i1], cp2[(size_t)4 * a.Npad + i2],
+                               cp1[(size_t)5 * a.Npad + i1], cp2[(size_t)5 * a.Npad + i2],
+                               cp1[(size_t)6 * a.Npad + i1], cp2[(size_t)6 * a.Npad + i2], vp[2], vp[3],
+                               num, det, re, za, zb, gadd);
+        else
+            pos = pair_gain<0>(acc, cp1[(size_t)2 * a.Npad + i1], cp2[(size_t)2 * a.Npad + i2], 0, 0, 0, 0, 0, 0,
+                               0, 0, 0, 0, num, det, re, za, zb, gadd);
+        double lb = 0.0;
+        if (pos && det > 1e-6) lb = fmax((num - c0) / det - 2.0 * c0, 0.0);
+        a.vthr[v] = (unsigned long long)__double_as_longlong(lb);
+    }
 }
 
 // Warp-specialised pair scan.  Warps 0..7 (consumers): DMMA correlation tile + closed-form
@@ -316,12 +408,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const int tI = blockIdx.x;
     const int i0 = tI * FT_TI;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double *vp = a.voxp + v * 8;
+    const double *vp = a.voxp + v * FT_VP;
     const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
     const double gpre = fmax(vp[5], vp[6]);
     const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
     const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
     const int ntJ = (N2 + FT_TJ - 1) / FT_TJ;
+    // the i2 scan starts at the tile of block 2's best single atom and wraps around: on smooth
+    // dictionaries strong pairs are met early, the screening threshold rises at once and the
+    // competitive-pair path stays rare
+    const int jt0 = min(ntJ - 1, max(0, (int)vp[9]) / FT_TJ);
+    unsigned long long *vthr = a.vthr + v;                // threshold shared by the voxel's CTAs
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     const double *Ar = SRC ? a.A + (a.a_by_local ? v : row) * a.strideA : nullptr;
 
@@ -344,7 +441,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         }
     }
     if (tid == 0) {
-        s_thr = (unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0));
+        s_thr = max((unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0)),
+                    *(volatile unsigned long long *)vthr);
         s_flag = 0;
         for (int st = 0; st < FT_NS; st++) { mbar_init(&s_full[st], FT_PROD); mbar_init(&s_empty[st], FT_CONS); }
     }
@@ -361,7 +459,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             const int st = jt % FT_NS;
             if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
             if ((a.debug & 2) && jt >= FT_NS) { mbar_arrive(&s_full[st]); continue; }
-            const int j = jt * FT_TJ + jj;
+            const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
+            if (pt == 0) atomicMax(&s_thr, *(volatile unsigned long long *)vthr);
+            const int j = jr * FT_TJ + jj;
             const bool ok = j < N2;
             const double csc = ok ? __ldg(cp2 + j) : 0.0;
             const double cal = (CSF && ok) ? __ldg(cp2 + (size_t)a.Npad + j) : 0.0;
@@ -404,7 +504,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             }
             for (int e = pt; e < 5 * FT_TJ; e += FT_PROD)
                 colq[(st * 5 + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
-                    __ldg(cp2 + (size_t)(e / FT_TJ + 2) * a.Npad + jt * FT_TJ + (e % FT_TJ));
+                    __ldg(cp2 + (size_t)(e / FT_TJ + 2) * a.Npad + jr * FT_TJ + (e % FT_TJ));
             mbar_arrive(&s_full[st]);
         }
         return;
@@ -412,7 +512,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 
     // =============================== consumers ===============================
     const int g = lane >> 2, t4 = lane & 3;
-    const double wide = 4.0 * c0 / kIllDet;
+    const double wide = 4.0 * kIllTol * c0;
+    const double c1 = 4.0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
     const double negc0 = -c0;
     // ---- resident i1 tile: rotate, project out the CSF column, normalise ----
     {
@@ -471,6 +572,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 
     for (int jt = 0; jt < ntJ; jt++) {
         const int st = jt % FT_NS;
+        const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
         mbar_wait(&s_full[st], (unsigned)(jt / FT_NS) & 1u);
         thr = fmax(thr, __longlong_as_double((long long)s_thr));
 
@@ -484,7 +586,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         const double *B_ = D2s + (size_t)st * Mp * FT_S2 + (size_t)t4 * FT_S2 + g;
         // 8-atom blocks of this tile that hold real atoms (warp-uniform): the last i1 / i2
         // tiles of a dictionary whose size is not a multiple of the tile are partly empty
-        const int ntv = min(4, (N2 - jt * FT_TJ + 7) >> 3);
+        const int ntv = min(4, (N2 - jr * FT_TJ + 7) >> 3);
         if (ntv == 4 && mtv == 2) {
 #pragma unroll 3
             for (int ks = 0; ks < Mp / 4; ks++) {
@@ -599,6 +701,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         }
         // ---- rare: some lane of the warp has a competitive pair ----
         if (__any_sync(0xffffffffu, hit != 0)) {
+            if (a.debug & 8) {   // experiment: count rare-path entries (warps) and competitive pairs
+                if (lane == 0) atomicAdd(&a.reasons[4], 1);
+                if (hit) atomicAdd(&a.reasons[5], __popc(hit));
+            }
             if (hit) {
                 // off the hot path: one instantiation of the closed form, accumulators read
                 // back through a (local-memory) copy indexed at run time
@@ -614,18 +720,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                     if (!(hit & (1u << q))) continue;
                     const int nt = q >> 2, e = (q >> 1) & 1, mt = q & 1;
                     const int c = 8 * nt + 2 * t4 + e;
-                    double num, det;
+                    double num, det, re, za, zb, gadd;
                     pair_gain<CSF>(rcopy[q], mt ? z1[1] : z1[0], cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
                                    mt ? k1[1] : k1[0], cq[2 * FT_TJ + c], mt ? g1[1] : g1[0],
                                    cq[3 * FT_TJ + c], mt ? zu1[1] : zu1[0], cq[4 * FT_TJ + c], Y3, gain_c,
-                                   num, det);
+                                   num, det, re, za, zb, gadd);
                     if (!(det > 1e-12)) { gill = INFINITY; continue; }   // numerically singular
-                    const double gq = num / det, tq = c0 / det;
-                    if (det < kIllDet) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
+                    const double rdet = 1.0 / det;
+                    double gq = num * rdet, tq = c0 * rdet;
+                    if (!(gq + tq >= thr)) continue;
+                    if (!(a.debug & 4)) refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
+                    if (tq > kIllTol * c0) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
                     if (gq > gb) {
                         flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
                         gb = gq; tb = tq;
-                        bidx = (i0 + wrow + 8 * mt + g) * N2 + jt * FT_TJ + c;
+                        bidx = (i0 + wrow + 8 * mt + g) * N2 + jr * FT_TJ + c;
                     } else if (!(gb > gq + wide)) {
                         flag = 1;
                     }
@@ -635,7 +744,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
             if (lb > thr) {
                 thr = lb;
-                if (lane == 0) atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
+                if (lane == 0) {
+                    atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
+                    atomicMax(vthr, (unsigned long long)__double_as_longlong(lb));
+                }
             }
         }
         mbar_arrive(&s_empty[st]);
@@ -765,7 +877,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     const int i0 = tI * GP_TI;
     if (i0 >= N1) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double *vp = a.voxp + v * 8;
+    const double *vp = a.voxp + v * FT_VP;
     const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
     const double gpre = fmax(vp[5 + rb], vp[5 + cb]);
     const double *cp1 = a.colp + (v * a.nblk + rb) * (int64_t)FT_NPAR * a.Npad;
@@ -804,7 +916,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 
     // ===================================== consumers =====================================
     const int g = lane >> 2, t4 = lane & 3;
-    const double wide = 4.0 * c0 / kIllDet;
+    const double wide = 4.0 * kIllTol * c0;
+    const double c1 = 4.0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
     const double negc0 = -c0;
     const int wrow = warp * 16;
     double *cq = colq + warp * 5 * GP_TJ;
@@ -969,14 +1082,17 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
                     if (!(hit & (1u << q))) continue;
                     const int nt = q >> 2, e = (q >> 1) & 1, mt = q & 1;
                     const int c = 8 * nt + 2 * t4 + e;
-                    double num, det;
+                    double num, det, re, za, zb, gadd;
                     pair_gain<CSF>(rcopy[q], mt ? z1[1] : z1[0], cq[c], mt ? b1[1] : b1[0],
                                    CSF ? cq[GP_TJ + c] : 0.0, mt ? k1[1] : k1[0], CSF ? cq[2 * GP_TJ + c] : 0.0,
                                    mt ? g1[1] : g1[0], CSF ? cq[3 * GP_TJ + c] : 0.0, mt ? zu1[1] : zu1[0],
-                                   CSF ? cq[4 * GP_TJ + c] : 0.0, Y3, gain_c, num, det);
+                                   CSF ? cq[4 * GP_TJ + c] : 0.0, Y3, gain_c, num, det, re, za, zb, gadd);
                     if (!(det > 1e-12)) { gill = INFINITY; continue; }
-                    const double gq = num / det, tq = c0 / det;
-                    if (det < kIllDet) gill = fmax(gill, gq + tq);
+                    const double rdet = 1.0 / det;
+                    double gq = num * rdet, tq = c0 * rdet;
+                    if (!(gq + tq >= thr)) continue;
+                    if (!(a.debug & 4)) refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
+                    if (tq > kIllTol * c0) gill = fmax(gill, gq + tq);
                     if (gq > gb) {
                         flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
                         gb = gq; tb = tq;
@@ -1087,7 +1203,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const bool active = tid < TXT * TYT;
     const int tx = active ? tid % TXT : 0, ty = active ? tid / TXT : 0;
-    const double *vp = a.voxp + v * 8;
+    const double *vp = a.voxp + v * FT_VP;
     const double c0 = vp[4];
     const double *cpz1 = a.colp + ((v * 3 + 0) * (int64_t)FT_NPAR + 2) * a.Npad;
     const double *cpz2 = a.colp + ((v * 3 + 1) * (int64_t)FT_NPAR + 2) * a.Npad;
@@ -1336,7 +1452,7 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
 {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
-    const double *vp = a.voxp + v * 8;
+    const double *vp = a.voxp + v * FT_VP;
     const double c0 = vp[4];
     // optimistic gain of every solution with at most two active columns
     double g2 = fmax(fmax(vp[5], vp[6]), vp[7]);
@@ -1384,7 +1500,7 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
 {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
-    const double *vp = a.voxp + v * 8;
+    const double *vp = a.voxp + v * FT_VP;
     const double c0 = vp[4];
     const double gpre = fmax(vp[5], vp[6]);
     double G = -1.0, tolG = 0.0;
@@ -1478,7 +1594,8 @@ size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V, int src, int shared_
         s += al256(sizeof(double) * V * 2 * M * 2);
     }
     s += al256(sizeof(double) * V * 2 * FT_NPAR * g.Npad);
-    s += al256(sizeof(double) * V * 8);
+    s += al256(sizeof(double) * V * FT_VP);
+    s += al256(sizeof(unsigned long long) * V);
     s += 3 * al256(sizeof(double) * V * g.ntI);
     s += 2 * al256(sizeof(int) * V * g.ntI);
     if (g.gemm) s += al256(sizeof(double) * (shared_dict ? 1 : V) * (size_t)g.Mp2 * g.ldn);
@@ -1521,7 +1638,8 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         a.ip_w = (double *)q; q += al256(sizeof(double) * V * 2 * p.M * 2);
     }
     a.colp = (double *)q; q += al256(sizeof(double) * V * 2 * FT_NPAR * a.Npad);
-    a.voxp = (double *)q; q += al256(sizeof(double) * V * 8);
+    a.voxp = (double *)q; q += al256(sizeof(double) * V * FT_VP);
+    a.vthr = (unsigned long long *)q; q += al256(sizeof(unsigned long long) * V);
     a.cta_gain = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_tol = (double *)q; q += al256(sizeof(double) * V * a.ntI);
     a.cta_ill = (double *)q; q += al256(sizeof(double) * V * a.ntI);
@@ -1544,7 +1662,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     auto shifted = [&](int64_t v0) {
         FastArgs b = a;
         if (!fp.src) { b.ip_rows += v0 * 2 * p.M * 2; b.ip_w += v0 * 2 * p.M * 2; }
-        b.colp += v0 * 2 * FT_NPAR * a.Npad; b.voxp += v0 * 8;
+        b.colp += v0 * 2 * FT_NPAR * a.Npad; b.voxp += v0 * FT_VP; b.vthr += v0;
         b.cta_gain += v0 * a.ntI; b.cta_tol += v0 * a.ntI; b.cta_ill += v0 * a.ntI;
         b.cta_idx += v0 * a.ntI; b.cta_flag += v0 * a.ntI;
         if (b.Dn) b.Dn += v0 * a.dn_stride;
@@ -1583,6 +1701,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         void (*kern)(FastArgs) = fp.csf ? (fp.src ? k_fast_pairs<1, 1> : k_fast_pairs<1, 0>)
                                         : (fp.src ? k_fast_pairs<0, 1> : k_fast_pairs<0, 0>);
         MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MFB_LAUNCH(k_fast_seed, (unsigned)V, 32, 0, st, a);
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
         for (int64_t v0 = 0; v0 < V; v0 += maxy) {
             const int64_t nv = V - v0 < maxy ? V - v0 : maxy;
@@ -1651,7 +1770,7 @@ static Fast3Layout fast3_layout(int M, const BlockSpec &bs, int64_t V, int share
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
     L.off_colp = take(sizeof(double) * V * 3 * FT_NPAR * L.Npad);
-    L.off_voxp = take(sizeof(double) * V * 8);
+    L.off_voxp = take(sizeof(double) * V * FT_VP);
     L.off_gain = take(sizeof(double) * V * 3 * L.ntI);
     L.off_tol = take(sizeof(double) * V * 3 * L.ntI);
     L.off_ill = take(sizeof(double) * V * 3 * L.ntI);
