@@ -136,6 +136,10 @@ int mfb_mc_average(int device, int64_t n_entries, int dim, const double *sim_pha
                    int64_t n_seq, const int64_t *delta_mapping, const double *gscaling,
                    double Dscaling, int64_t num_spins, double *signal, void *stream);
 
+/* mfb_solve_batch keeps its device workspace between calls; mfb_trim frees the workspace of
+ * `device` (a later call allocates it again). */
+int mfb_trim(int device);
+
 /* Process-wide counters of mfb_solve_batch, out[6]: voxels decided by the screening tier,
  * voxels redone by the reference-order tier, and why they were handed over ([2] no
  * candidate, [3] ill-conditioned competitor, [4] near tie, [5] a solution with fewer active

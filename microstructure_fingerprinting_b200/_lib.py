@@ -38,6 +38,7 @@ SYMBOLS = {
                                     ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int]),
     "mfb_fit_stats": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "mfb_solve_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
+    "mfb_trim": (ctypes.c_int, [ctypes.c_int]),
     "mfb_mc_average": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, c_vp, ctypes.c_int64, c_vp,
                                       c_vp, ctypes.c_double, ctypes.c_int64, c_vp, c_vp]),
 }

@@ -4,6 +4,7 @@
 // winning tuple in the reference's arithmetic, pack the params rows.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -79,6 +80,27 @@ struct mfb_plan {
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t exact_budget = (size_t)3 << 30;  // bytes of materialised dictionaries per sub-chunk
 };
+
+// per-device workspace of mfb_solve_batch
+static const int kMaxDevices = 64;
+struct SolveCache {
+    std::mutex mu;
+    Buf scratch, tuple, asmall, idx5, w5, redo;
+};
+static SolveCache g_solve_cache[kMaxDevices];
+
+extern "C" int mfb_trim(int device)
+{
+    if (device < 0 || device >= kMaxDevices) { set_error("mfb_trim: device index out of range"); return MFB_EINVAL; }
+    SolveCache &c = g_solve_cache[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.scratch.p || c.tuple.p) {
+        MFB_CUDA_TRY(cudaSetDevice(device));
+        Buf *bufs[] = {&c.scratch, &c.tuple, &c.asmall, &c.idx5, &c.w5, &c.redo};
+        for (Buf *b : bufs) b->release();
+    }
+    return MFB_OK;
+}
 
 // counters of the mfb_solve_batch calls of this process: voxels decided by the screening
 // tier, voxels redone in reference order, hand-over reasons (no candidate, ill-conditioned
@@ -268,9 +290,15 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     const size_t budget = per_vox > ((size_t)1 << 20) ? (size_t)6 << 30 : (size_t)1 << 30;
     int64_t sub = std::max<int64_t>(1, std::min<int64_t>((fast || fast3) ? 8192 : 65535, budget / per_vox));
     sub = std::min(sub, V);
-    Buf scratch, tuple, asmall, idx5, w5, redo;
+    // workspace of the device, kept between calls (mfb_trim releases it): allocating and
+    // freeing gigabytes per call costs milliseconds and synchronises the device
+    if (device < 0 || device >= kMaxDevices) { set_error("mfb_solve_batch: device index out of range"); return MFB_EINVAL; }
+    SolveCache &cache = g_solve_cache[device];
+    std::lock_guard<std::mutex> lock(cache.mu);
+    Buf &scratch = cache.scratch, &tuple = cache.tuple, &asmall = cache.asmall, &idx5 = cache.idx5, &w5 = cache.w5,
+        &redo = cache.redo;
     int rc = MFB_OK;
-    auto cleanup = [&]() { scratch.release(); tuple.release(); asmall.release(); idx5.release(); w5.release(); redo.release(); };
+    auto cleanup = [&]() {};
     size_t sbytes = exact_scratch_bytes(sub, bs);
     if (fast) sbytes = std::max(sbytes, fast_scratch_bytes(M, bs.size[0], bs.size[1], sub, 1, shared_dict));
     if (fast3) sbytes = std::max(sbytes, fast3_scratch_bytes(M, bs, sub, shared_dict));
