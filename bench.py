@@ -293,7 +293,7 @@ def main():
         # CPU baseline on a bounded sample (rank 0, N = 1 only)
         if world == 1:
             from oracle import oracle as orc
-            ns = int(args.cpu_voxels) if args.cpu_voxels else 24
+            ns = int(args.cpu_voxels) if args.cpu_voxels else 256      # ~18 s on one core
             tab = orc.init_table(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
             op = orc.plan_scheme(tab, ph.sch)
             t0 = time.perf_counter()

@@ -61,6 +61,7 @@ struct FastArgs {
     int32_t *redo_local;  // local indices of the voxels handed to the exact tier
     int nblk;          // searched blocks (2, or 3 for the triple scan)
     int Nb[3], startb[3], dnoff[3];   // atoms, first column in A, first column in Dn of each block
+    int nsplit;        // k_gemm_pairs: CTAs sharing one i1 tile, each scanning a slice of the i2 tiles
     int njobs;         // k_gemm_pairs jobs per voxel (1: the pair scan; 3: the correlation matrices of a triple scan)
     int job_rb[3], job_cb[3];         // row / column block of each job
     double *R[3];      // job outputs (STORE): [v][rows padded][ldr], normalised correlations
@@ -873,7 +874,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     const int rb = a.job_rb[job], cb = a.job_cb[job];
     const int N1 = a.Nb[rb], N2 = a.Nb[cb];
     const int64_t v = blockIdx.y;
-    const int tI = blockIdx.x;
+    // blockIdx.x = i1 tile + (tiles) * slice: the CTAs of a voxel are adjacent in launch order,
+    // so the voxels in flight (and their Dn copies) stay few enough for the L2
+    const int ntI1 = a.ntI / a.nsplit;
+    const int tI = blockIdx.x % ntI1, sp = blockIdx.x / ntI1;
     const int i0 = tI * GP_TI;
     if (i0 >= N1) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -887,7 +891,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     const int ntJ = STORE ? ((cb + 1 < a.nblk ? a.dnoff[cb + 1] : a.ldn) - a.dnoff[cb]) / GP_TJ
                           : (N2 + GP_TJ - 1) / GP_TJ;
     const int nch = a.Mp2 / GP_KC;
-    const int total = ntJ * nch;
+    const int jt_lo = (int)((long long)sp * ntJ / a.nsplit), jt_hi = (int)((long long)(sp + 1) * ntJ / a.nsplit);
+    const int total = (jt_hi - jt_lo) * nch;
     const double *Dv = a.Dn + v * a.dn_stride;
 
     if (tid == 0) {
@@ -901,7 +906,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     if (tid >= FT_CONS) {
         // ============ producer warp: one D1 row (1 KB) and one D2 row (512 B) per lane ============
         for (int s = 0; s < total; s++) {
-            const int st = s % GP_NS, jt = s / nch, ch = s - jt * nch;
+            const int st = s % GP_NS, jt = jt_lo + s / nch, ch = s % nch;
             if (s >= GP_NS) mbar_wait(&s_empty[st], (unsigned)((s / GP_NS) - 1) & 1u);
             double *d1 = stages + (size_t)st * GP_STAGE;
             double *d2 = d1 + GP_KC * GP_S1;
@@ -937,7 +942,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     int bidx = -1, flag = 0;
 
     int s = 0;
-    for (int jt = 0; jt < ntJ; jt++) {
+    for (int jt = jt_lo; jt < jt_hi; jt++) {
         // this warp's copy of the i2 tile's per-atom parameters (z, beta, kappa, gamma, zu);
         // Npad is a multiple of GP_TJ here, so the reads stay inside colp
         __syncwarp();
@@ -1142,7 +1147,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     }
     consumer_sync();
     if (tid == 0) {
-        const int64_t o = (v * a.njobs + job) * a.ntI + tI;
+        const int64_t o = (v * a.njobs + job) * a.ntI + blockIdx.x;
         a.cta_gain[o] = G;
         a.cta_tol[o] = tolG;
         a.cta_idx[o] = I == INT_MAX ? -1 : I;
@@ -1567,7 +1572,7 @@ bool fast_supported_explicit(int M, const BlockSpec &bs)
 
 // Geometry shared by fast_scratch_bytes and launch_fast_search.
 struct FastGeom {
-    int Mp, Mp2, Npad, ntI, N1pad, ldn;
+    int Mp, Mp2, Npad, ntI, N1pad, ldn, nsplit;
     bool gemm;      // general-M path (k_normalize + k_gemm_pairs)
 };
 static FastGeom fast_geom(int M, int N1, int N2)
@@ -1579,9 +1584,22 @@ static FastGeom fast_geom(int M, int N1, int N2)
     const int padto = g.gemm ? GP_TI : FT_TJ;
     g.Npad = (Nmax + padto - 1) / padto * padto;
     g.ntI = g.gemm ? (N1 + GP_TI - 1) / GP_TI : (N1 + FT_TI - 1) / FT_TI;
+    g.nsplit = 1;
     g.Mp2 = (M + GP_KC - 1) / GP_KC * GP_KC;
     g.N1pad = (N1 + GP_TI - 1) / GP_TI * GP_TI;
     g.ldn = g.N1pad + (N2 + GP_TJ - 1) / GP_TJ * GP_TJ;
+    if (g.gemm) {
+        // one voxel's normalised copy is Mp2 * ldn * 8 bytes; when a few of them exceed the L2
+        // (126 MB) the i1 tile, re-read once per i2 tile, would come from HBM every time: spread
+        // a voxel over ~128 CTAs (i1 tiles x i2 slices) so that ~1 voxel is in flight per wave
+        const double mb = (double)g.Mp2 * g.ldn * 8.0 / 1e6;
+        const int ntJ = (N2 + GP_TJ - 1) / GP_TJ;
+        if (mb * 148.0 / g.ntI > 100.0) {
+            int ns = (128 + g.ntI - 1) / g.ntI;
+            g.nsplit = ns < 1 ? 1 : (ns > ntJ ? ntJ : ns);
+            g.ntI *= g.nsplit;
+        }
+    }
     return g;
 }
 
@@ -1622,7 +1640,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     a.a_by_local = fp.a_by_local; a.redo_local = fp.redo_local;
     a.Mp = g.Mp; a.Npad = g.Npad; a.ntI = g.ntI;
     a.Mp2 = g.Mp2; a.N1pad = g.N1pad; a.ldn = g.ldn;
-    a.nblk = 2; a.njobs = 1; a.job_rb[0] = 0; a.job_cb[0] = 1;
+    a.nblk = 2; a.njobs = 1; a.job_rb[0] = 0; a.job_cb[0] = 1; a.nsplit = g.nsplit;
     a.Nb[0] = fp.N1; a.Nb[1] = fp.N2; a.startb[0] = fp.start1; a.startb[1] = fp.start2;
     a.dnoff[0] = 0; a.dnoff[1] = g.N1pad;
     const bool shared_dict = fp.src && fp.strideA == 0;
@@ -1809,7 +1827,7 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     memset(&a, 0, sizeof(a));
     a.p.M = M; a.src = 1; a.csf = 0;
     a.A = A; a.lda = lda; a.strideA = strideA;
-    a.nblk = 3; a.njobs = 3;
+    a.nblk = 3; a.njobs = 3; a.nsplit = 1;
     int off = 0;
     for (int b = 0; b < 3; b++) { a.Nb[b] = bs.size[b]; a.startb[b] = bs.start[b]; a.dnoff[b] = off; off += L.Np[b]; }
     a.N1 = bs.size[0]; a.N2 = bs.size[1];
