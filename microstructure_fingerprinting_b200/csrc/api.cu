@@ -71,7 +71,7 @@ struct mfb_plan {
     DevPlan dp;
     std::vector<void *> owned;
     // per-chunk workspace
-    Buf type, nbv, lists, counts, tuple, asmall, idx5, w5, obj, yrec, abuf, scratch, fscratch, redo;
+    Buf type, nbv, lists, counts, tuple, asmall, idx5, w5, obj, yrec, abuf, scratch, fscratch, redo, redomask;
     // host staging for mfb_fit_host
     Buf d_y, d_peaks, d_K, d_csf, d_ear, d_params;
     cudaStream_t stream = nullptr;
@@ -85,7 +85,7 @@ struct mfb_plan {
 static const int kMaxDevices = 64;
 struct SolveCache {
     std::mutex mu;
-    Buf scratch, tuple, asmall, idx5, w5, redo;
+    Buf scratch, tuple, asmall, idx5, w5, redo, redomask;
 };
 static SolveCache g_solve_cache[kMaxDevices];
 
@@ -96,7 +96,7 @@ extern "C" int mfb_trim(int device)
     std::lock_guard<std::mutex> lock(c.mu);
     if (c.scratch.p || c.tuple.p) {
         MFB_CUDA_TRY(cudaSetDevice(device));
-        Buf *bufs[] = {&c.scratch, &c.tuple, &c.asmall, &c.idx5, &c.w5, &c.redo};
+        Buf *bufs[] = {&c.scratch, &c.tuple, &c.asmall, &c.idx5, &c.w5, &c.redo, &c.redomask};
         for (Buf *b : bufs) b->release();
     }
     return MFB_OK;
@@ -199,7 +199,7 @@ extern "C" void mfb_plan_destroy(mfb_plan *pl)
     cudaSetDevice(pl->device);
     for (void *p : pl->owned) cudaFree(p);
     Buf *bufs[] = {&pl->type, &pl->nbv, &pl->lists, &pl->counts, &pl->tuple, &pl->asmall,
-                   &pl->idx5, &pl->w5, &pl->obj, &pl->yrec, &pl->abuf, &pl->scratch, &pl->fscratch, &pl->redo,
+                   &pl->idx5, &pl->w5, &pl->obj, &pl->yrec, &pl->abuf, &pl->scratch, &pl->fscratch, &pl->redo, &pl->redomask,
                    &pl->d_y, &pl->d_peaks, &pl->d_K, &pl->d_csf, &pl->d_ear, &pl->d_params};
     for (Buf *b : bufs) b->release();
     for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
@@ -296,7 +296,8 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     SolveCache &cache = g_solve_cache[device];
     std::lock_guard<std::mutex> lock(cache.mu);
     Buf &scratch = cache.scratch, &tuple = cache.tuple, &asmall = cache.asmall, &idx5 = cache.idx5, &w5 = cache.w5,
-        &redo = cache.redo;
+        &redo = cache.redo, &redomask = cache.redomask;
+    const int mask_ld = exact_mask_ld(bs);
     int rc = MFB_OK;
     auto cleanup = [&]() {};
     size_t sbytes = exact_scratch_bytes(sub, bs);
@@ -305,7 +306,7 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     if ((rc = scratch.ensure(sbytes)) || (rc = tuple.ensure(sizeof(long long) * sub)) ||
         (rc = asmall.ensure(sizeof(double) * sub * M * kMaxBlocks)) ||
         (rc = idx5.ensure(sizeof(int32_t) * sub * kMaxBlocks)) || (rc = w5.ensure(sizeof(double) * sub * kMaxBlocks)) ||
-        (rc = redo.ensure(sizeof(int32_t) * (sub + 8)))) {
+        (rc = redo.ensure(sizeof(int32_t) * (sub + 8))) || (fast && (rc = redomask.ensure((size_t)sub * 2 * mask_ld)))) {
         cleanup();
         return rc;
     }
@@ -328,6 +329,7 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
                 fp.src = 1; fp.N1 = bs.size[0]; fp.N2 = bs.size[1]; fp.A = Av; fp.lda = lda; fp.strideA = strideA;
                 fp.start1 = bs.start[0]; fp.start2 = bs.start[1]; fp.start3 = bs.nb == 3 ? bs.start[2] : 0;
                 fp.csf = bs.nb == 3;
+                fp.redo_mask = redomask.as<uint8_t>(); fp.mask_ld = mask_ld;
                 rc = launch_fast_search(dummy, fp, nv, nullptr, nullptr, 0, yv, scratch.p, tuple.as<long long>(),
                                         redo_list, redo_count, reasons, st, nullptr);
             } else {
@@ -343,7 +345,8 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
             for (int i = 0; i < 4; i++) g_solve_stats[2 + i] += head[1 + i];
             if (n_redo > 0)
                 rc = launch_exact_search(n_redo, M, bs, Av, lda, strideA, yv, M, redo_list, scratch.p,
-                                         tuple.as<long long>(), st, nullptr, redo_list);
+                                         tuple.as<long long>(), st, nullptr, redo_list,
+                                         fast ? redomask.as<uint8_t>() : nullptr, mask_ld);
         } else {
             rc = launch_exact_search(nv, M, bs, Av, lda, strideA, yv, M, nullptr, scratch.p,
                                      tuple.as<long long>(), st);
@@ -421,7 +424,8 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             return ev;
         };
         // exact tier: materialise the dictionaries of a sub-chunk, search in reference order
-        auto run_exact = [&](const int32_t *lst, int64_t n, bool time_it) -> int {
+        auto run_exact = [&](const int32_t *lst, int64_t n, bool time_it, const uint8_t *mask = nullptr,
+                             int mask_ld = 0) -> int {
             const int64_t lda = (bs.ntot + 1) & ~(int64_t)1;
             const size_t per_vox = (size_t)M * lda * sizeof(double);
             int64_t sub = std::max<int64_t>(1, std::min<int64_t>(65535, pl->exact_budget / per_vox));
@@ -434,7 +438,8 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
                                                pl->abuf.as<double>(), lda, (int64_t)M * lda, st));
                 cudaEvent_t *ev = time_it ? next_events() : nullptr;
                 MFB_TRY(launch_exact_search(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda, y, M,
-                                            lst + s0, pl->scratch.p, pl->tuple.as<long long>(), st, ev));
+                                            lst + s0, pl->scratch.p, pl->tuple.as<long long>(), st, ev, nullptr,
+                                            mask ? mask + (size_t)s0 * 2 * mask_ld : nullptr, mask_ld));
                 if (ev) { pl->stats[3] += 1; pl->stats[4] += (double)ns; }
                 MFB_TRY(launch_gather_from_A(ns, M, bs, pl->abuf.as<double>(), lda, (int64_t)M * lda,
                                              pl->tuple.as<long long>(), lst + s0, pl->asmall.as<double>(),
@@ -450,6 +455,9 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             FastProblem fp;
             memset(&fp, 0, sizeof(fp));
             fp.src = 0; fp.N1 = fp.N2 = dp.N; fp.csf = ct;
+            const int mask_ld = exact_mask_ld(bs);
+            MFB_TRY(pl->redomask.ensure((size_t)cnt * 2 * mask_ld));
+            fp.redo_mask = pl->redomask.as<uint8_t>(); fp.mask_ld = mask_ld;
             MFB_TRY(pl->redo.ensure(sizeof(int32_t) * (nv + 8)));
             int32_t *redo_count = pl->redo.as<int32_t>();   // [count, reasons[4], -, -, -, list...]
             int32_t *reasons = redo_count + 1;
@@ -474,7 +482,7 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             pl->stats[0] += (double)(cnt - n_redo);
             pl->stats[6] += head[2];          // ill-conditioned competitor
             pl->stats[7] += head[3] + 1e-6 * head[4] ;  // near ties (+ 1e-6 * pair-independent branch)
-            if (n_redo > 0) MFB_TRY(run_exact(redo_list, n_redo, false));
+            if (n_redo > 0) MFB_TRY(run_exact(redo_list, n_redo, false, pl->redomask.as<uint8_t>(), mask_ld));
         } else if (!(flags & 1) && (fast_supported_materialised(dp, Kt, ct, et) || fast3_supported_materialised(dp, Kt, ct, et))) {
             // between-shell protocols, M > 112 and [N, N, E] voxels: materialise the rotated
             // dictionaries of a sub-chunk (k_rotate_assemble), screen them with the
@@ -501,6 +509,11 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             fp.A = pl->abuf.as<double>(); fp.lda = lda; fp.strideA = strideA;
             fp.start1 = 0; fp.start2 = dp.N; fp.start3 = ct ? 2 * dp.N : 0;
             fp.a_by_local = 1; fp.redo_local = redo_local;
+            const int mask_ld = exact_mask_ld(bs);
+            if (!triple) {
+                MFB_TRY(pl->redomask.ensure((size_t)sub * 2 * mask_ld));
+                fp.redo_mask = pl->redomask.as<uint8_t>(); fp.mask_ld = mask_ld;
+            }
             for (int64_t s0 = 0; s0 < cnt; s0 += sub) {
                 const int64_t ns = std::min(sub, cnt - s0);
                 MFB_CUDA_TRY(cudaMemsetAsync(redo_count, 0, 8 * sizeof(int32_t), st));
@@ -527,7 +540,8 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
                     MFB_TRY(pl->scratch.ensure(exact_scratch_bytes(n_redo, bs)));
                     MFB_TRY(launch_exact_search(n_redo, M, bs, pl->abuf.as<double>(), lda, strideA, y, M,
                                                 redo_list, pl->scratch.p, pl->tuple.as<long long>(), st,
-                                                nullptr, redo_local));
+                                                nullptr, redo_local, triple ? nullptr : pl->redomask.as<uint8_t>(),
+                                                mask_ld));
                 }
                 MFB_TRY(launch_gather_from_A(ns, M, bs, pl->abuf.as<double>(), lda, strideA,
                                              pl->tuple.as<long long>(), list + s0, pl->asmall.as<double>(),

@@ -91,7 +91,13 @@ size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs);
 int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, int64_t lda,
                         int64_t strideA, const double *y, int64_t y_ld,
                         const int32_t *vox_list, void *scratch, long long *tuple_out,
-                        cudaStream_t st, cudaEvent_t *ev = nullptr, const int32_t *a_list = nullptr);
+                        cudaStream_t st, cudaEvent_t *ev = nullptr, const int32_t *a_list = nullptr,
+                        const uint8_t *tile_mask = nullptr, int mask_ld = 0);
+inline int exact_mask_ld(const BlockSpec &bs)
+{
+    const int n = bs.size[0] > bs.size[1] ? bs.size[0] : bs.size[1];
+    return (n + 63) / 64;
+}
 
 // Copy the winning tuple's columns into Asmall[row(v)] (M x kMaxBlocks, row-major) and
 // decode the per-block indices into idx_sub[row(v)*kMaxBlocks + b].
@@ -140,6 +146,8 @@ struct FastProblem {
     int csf;            // a third, single-column block is present
     int a_by_local;     // explicit + vox_list: local voxel v reads A + v*strideA (vox_list maps y / tuple rows only)
     int32_t *redo_local;  // optional: local indices of the voxels handed to the exact tier
+    uint8_t *redo_mask;   // optional: [redo position][2][mask_ld] row / column tiles (64 atoms) the exact
+    int mask_ld;          // tier must scan for that voxel (see k_fast_select)
 };
 bool fast_supported(const DevPlan &p, int K, int csf, int ear);
 bool fast_supported_explicit(int M, const BlockSpec &bs);

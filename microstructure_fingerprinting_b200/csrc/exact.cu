@@ -323,6 +323,8 @@ struct ExactArgs {
     long long *tile_idx;
     int ntiles;
     const int32_t *a_list;   // optional: dictionary index of voxel v (default: v itself)
+    const uint8_t *tile_mask;  // optional: [v][2][mask_ld] row / column tiles to scan (others are skipped)
+    int mask_ld;
 };
 
 __device__ __forceinline__ const double *ex_A(const ExactArgs &a, int64_t v)
@@ -420,6 +422,18 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
     __shared__ double sy[EX_KC];
     __shared__ Best red[32];
     const int64_t v = blockIdx.z;
+    if (a.tile_mask) {
+        // the screening tier certified that the minimum lies in the rows / columns of a few atoms
+        const uint8_t *mk = a.tile_mask + (size_t)v * 2 * a.mask_ld;
+        if (!mk[blockIdx.y] && !mk[a.mask_ld + blockIdx.x]) {
+            if (threadIdx.x == 0) {
+                const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+                a.tile_res[v * a.ntiles + tile] = INFINITY;
+                a.tile_idx[v * a.ntiles + tile] = LLONG_MAX;
+            }
+            return;
+        }
+    }
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     const int N1 = a.bs.size[0], N2 = a.bs.size[1];
     const int tI = blockIdx.y * EX_T, tJ = blockIdx.x * EX_T;
@@ -811,7 +825,7 @@ size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs)
 int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, int64_t lda,
                         int64_t strideA, const double *y, int64_t y_ld, const int32_t *vox_list,
                         void *scratch, long long *tuple_out, cudaStream_t st, cudaEvent_t *ev,
-                        const int32_t *a_list)
+                        const int32_t *a_list, const uint8_t *tile_mask, int mask_ld)
 {
     if (V == 0) return MFB_OK;
     if (bs.nb < 1 || bs.nb > kMaxBlocks) {
@@ -826,6 +840,8 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
     a.M = M; a.bs = bs; a.A = A; a.lda = lda; a.strideA = strideA; a.y = y; a.y_ld = y_ld;
     a.vox_list = vox_list;
     a.a_list = a_list;
+    a.tile_mask = (bs.nb == 2 || bs.nb == 3) ? tile_mask : nullptr;
+    a.mask_ld = mask_ld;
     a.ntiles = exact_ntiles(bs);
     char *p = (char *)scratch;
     a.colsq = (double *)p; p += align256(sizeof(double) * V * bs.ntot);

@@ -36,7 +36,7 @@ namespace mfb {
 #define FT_NS 3             // stages of the i2-tile ring
 #define FT_S1 (FT_TI + 4)  // row strides: == 4 mod 16 doubles -> conflict-free fragment loads
 #define FT_S2 (FT_TJ + 4)
-#define FT_NPAR 7          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu
+#define FT_NPAR 8          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu, single-solution gain
 #define FT_VP 12           // per-voxel scalars (voxp): see FastArgs
 
 // 1 - rho^2 below which a pair is tracked as ill-conditioned (its screening error bound
@@ -45,6 +45,11 @@ static constexpr double kIllDet = 1e-4;
 // A competitive pair / tuple whose (refined) error bound exceeds kIllTol * c0 is tracked as
 // ill-conditioned: it can win only through the exact tier.
 static constexpr double kIllTol = 64.0;
+// The screening threshold starts kPreMargin * c0 below the best solution with fewer active
+// columns (single atom, atom + CSF): a voxel without any competitive pair is then certified to
+// be won by such a solution with that margin, and its reference-order search can be
+// restricted to the rows / columns of the atoms that can hold it (k_fast_select).
+static constexpr double kPreMargin = 32.0;
 
 struct FastArgs {
     DevPlan p;         // table source: rotation plan; explicit source: only p.M is used
@@ -59,6 +64,8 @@ struct FastArgs {
     int64_t dn_stride;
     int ldn, N1pad, Mp2;
     int32_t *redo_local;  // local indices of the voxels handed to the exact tier
+    uint8_t *redo_mask;   // [redo position][2][mask_ld]: 64-atom row / column tiles the exact tier must scan
+    int mask_ld;
     int nblk;          // searched blocks (2, or 3 for the triple scan)
     int Nb[3], startb[3], dnoff[3];   // atoms, first column in A, first column in Dn of each block
     int nsplit;        // k_gemm_pairs: CTAs sharing one i1 tile, each scanning a slice of the i2 tiles
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     double gbest = 0.0;
     int ibest = 0;
     for (int i = threadIdx.x; i < a.Npad; i += blockDim.x) {
-        double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0};
+        double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (i < Nk) {
             double sq = 0.0, dy = 0.0, d3 = 0.0;
             const double *Ac = a.src ? Ar + a.startb[k] + i : nullptr;
@@ -200,6 +207,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
                 par[0] = r;            // scale
                 par[2] = dy * r;       // z
                 const double gi = dy > 0 ? dy * dy / sq : 0.0;
+                par[7] = gi;
                 if (gi > gbest) { gbest = gi; ibest = i; }
             } else {
                 const double gam = d3 * r * rsqrt(A33);      // corr(atom, csf)
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
                 par[5] = gam;
                 par[6] = dy * r;                             // zu
                 const double gi = nnls2_gain(sq, d3, A33, dy, Y3);
+                par[7] = gi;
                 if (gi > gbest) { gbest = gi; ibest = i; }
             }
         }
@@ -442,7 +451,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         }
     }
     if (tid == 0) {
-        s_thr = max((unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0)),
+        s_thr = max((unsigned long long)__double_as_longlong(fmax(gpre - kPreMargin * c0, 0.0)),
                     *(volatile unsigned long long *)vthr);
         s_flag = 0;
         for (int st = 0; st < FT_NS; st++) { mbar_init(&s_full[st], FT_PROD); mbar_init(&s_empty[st], FT_CONS); }
@@ -568,7 +577,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const int mtv = max(0, min(2, (N1 - (i0 + wrow) + 7) >> 3));   // valid 8-row blocks of this warp
 
     // thread-local best (central gain gb, tolerance tb) and the shared screening threshold
-    double gb = -1.0, tb = 0.0, thr = fmax(gpre - c0, 0.0), gill = -1.0;
+    double gb = -1.0, tb = 0.0, thr = fmax(gpre - kPreMargin * c0, 0.0), gill = -1.0;
     int bidx = -1, flag = 0;
 
     for (int jt = 0; jt < ntJ; jt++) {
@@ -896,7 +905,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     const double *Dv = a.Dn + v * a.dn_stride;
 
     if (tid == 0) {
-        s_thr = (unsigned long long)__double_as_longlong(fmax(gpre - c0, 0.0));
+        s_thr = (unsigned long long)__double_as_longlong(fmax(gpre - kPreMargin * c0, 0.0));
         s_flag = 0;
         for (int st = 0; st < GP_NS; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], FT_CONS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -938,7 +947,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
         zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
     }
     const int mtv = max(0, min(2, (N1 - (i0 + wrow) + 7) >> 3));
-    double gb = -1.0, tb = 0.0, thr = fmax(gpre - c0, 0.0), gill = -1.0;
+    double gb = -1.0, tb = 0.0, thr = fmax(gpre - kPreMargin * c0, 0.0), gill = -1.0;
     int bidx = -1, flag = 0;
 
     int s = 0;
@@ -1534,6 +1543,25 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
         int pos = atomicAdd(a.redo_count, 1);
         a.redo_list[pos] = (int32_t)row;
         if (a.redo_local) a.redo_local[pos] = (int32_t)v;
+        if (a.redo_mask) {
+            // No competitive pair at all: the winner is a solution with one fascicle atom
+            // (alone or with the CSF column).  Every tuple that can reach the minimum then lies
+            // in the row of an atom of block 1, or the column of an atom of block 2, whose
+            // single-solution gain is within the margin of the best: only those 64-atom tiles
+            // need the reference-order search.  Not applicable when the CSF-only or the
+            // all-zero solution could win (their first tuple in loop order can be anywhere).
+            uint8_t *mk = a.redo_mask + (size_t)pos * 2 * a.mask_ld;
+            const double gain_c = vp[3], margin = kPreMargin * c0;
+            const bool restricted = reason == 0 && gpre > margin && gain_c < gpre - margin;
+            for (int t = 0; t < 2 * a.mask_ld; t++) mk[t] = restricted ? 0 : 1;
+            if (restricted)
+                for (int k = 0; k < 2; k++) {
+                    const double *gs = a.colp + ((v * a.nblk + k) * (int64_t)FT_NPAR + 7) * a.Npad;
+                    const int Nk = a.Nb[k];
+                    for (int i = 0; i < Nk; i++)
+                        if (gs[i] >= gpre - margin) mk[k * a.mask_ld + (i >> 6)] = 1;
+                }
+        }
     }
 }
 
@@ -1638,6 +1666,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     a.A = fp.A; a.lda = fp.lda; a.strideA = fp.strideA;
     a.start1 = fp.start1; a.start2 = fp.start2; a.start3 = fp.start3;
     a.a_by_local = fp.a_by_local; a.redo_local = fp.redo_local;
+    a.redo_mask = fp.redo_mask; a.mask_ld = fp.mask_ld;
     a.Mp = g.Mp; a.Npad = g.Npad; a.ntI = g.ntI;
     a.Mp2 = g.Mp2; a.N1pad = g.N1pad; a.ldn = g.ldn;
     a.nblk = 2; a.njobs = 1; a.job_rb[0] = 0; a.job_cb[0] = 1; a.nsplit = g.nsplit;
