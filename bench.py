@@ -98,6 +98,28 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print on fd 1 (e.g. NCCL's version banner) goes to stderr; the one
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def make_workload(V, N, seed, csf_frac=0.3):
     from tests.phantom import make_phantom
     return make_phantom(n_atoms=N, n_vox=V, seed=seed, frac_k=(0.0, 0.0, 1.0), csf_frac=csf_frac,
@@ -141,7 +163,7 @@ def run_reference(args):
                                        "C oracle port of the reference's _fit_voxel, one thread "
                                        "per core" % sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, V):
@@ -164,6 +186,7 @@ def main():
     ap.add_argument("--cpu-voxels", type=int, default=0)
     ap.add_argument("--exact", action="store_true", help="force the exact tier (verification)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -306,7 +329,7 @@ def main():
                                     "sample": "first %d voxels of the same batch, C oracle port of "
                                               "_fit_voxel on one core" % ns,
                                     "indices_match_gpu": ok}
-        print(json.dumps(line))
+        emit(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()
