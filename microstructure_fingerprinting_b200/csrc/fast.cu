@@ -93,7 +93,8 @@ struct FastArgs {
     int *ip_rows;      // [v][2][M][2]  rl, rh
     double *ip_w;      // [v][2][M][2]  wl, wh
     double *colp;      // [v][2][FT_NPAR][Npad]
-    double *voxp;      // [v][FT_VP]  y_sq, A33, Y3, gain_c, c0, Gpre(block 0..2), best single atom of block 0..2, -
+    double *voxp;      // [v][FT_VP]  y_sq, A33, Y3, gain_c3 (CSF projection), c0, Gpre(block 0..2), best single atom
+                       //             of block 0..2, gain of the CSF-only solution
     double *cta_gain;  // [v][ntI]
     double *cta_tol;   // [v][ntI]
     int *cta_idx;      // [v][ntI]
@@ -186,7 +187,12 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
         A33 = fma(cs[m], cs[m], A33);
         Y3 = fma(cs[m], ys[m], Y3);
     }
-    const double gain_c = (a.csf && Y3 > 0) ? Y3 * Y3 / A33 : 0.0;
+    // gain_c3: projection of y on the CSF column, the CSF share of the gain of every solution
+    // that contains the column with its UNCONSTRAINED weight (valid whatever the sign of Y3: the
+    // three-compartment weight w3 can be positive although csf.y is not); gain_c: the CSF-only
+    // NNLS solution, which needs Y3 > 0
+    const double gain_c3 = a.csf ? Y3 * Y3 / A33 : 0.0;
+    const double gain_c = (a.csf && Y3 > 0) ? gain_c3 : 0.0;
     double *cp = a.colp + (v * a.nblk + k) * (int64_t)FT_NPAR * a.Npad;
     double gbest = 0.0;
     int ibest = 0;
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
         vp[5 + k] = fmax(gbest, gain_c);   // slots 5, 6, 7: blocks 0, 1, 2
         vp[8 + k] = (double)s_ibest;
         if (k == 0) {
-            vp[0] = y_sq; vp[1] = A33; vp[2] = Y3; vp[3] = gain_c;
+            vp[0] = y_sq; vp[1] = A33; vp[2] = Y3; vp[3] = gain_c3; vp[11] = gain_c;
             vp[4] = 4.0 * (M + 8) * 2.2204e-16 * y_sq;   // c0: screening error scale
         }
     }
@@ -1551,7 +1557,7 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
             // need the reference-order search.  Not applicable when the CSF-only or the
             // all-zero solution could win (their first tuple in loop order can be anywhere).
             uint8_t *mk = a.redo_mask + (size_t)pos * 2 * a.mask_ld;
-            const double gain_c = vp[3], margin = kPreMargin * c0;
+            const double gain_c = vp[11], margin = kPreMargin * c0;
             const bool restricted = reason == 0 && gpre > margin && gain_c < gpre - margin;
             for (int t = 0; t < 2 * a.mask_ld; t++) mk[t] = restricted ? 0 : 1;
             if (restricted)

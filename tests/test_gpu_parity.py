@@ -646,3 +646,15 @@ def test_rotate_atom_2d_batched_and_pipeline(lowlevel):
         w1, sub1, tot1, obj1, _ = mfu.solve_exhaustive_posweights(D, Y[v].copy(), np.array([N, N]))
         assert np.array_equal(sub[v], sub1) and np.array_equal(w[v], w1) and obj[v] == obj1
         assert np.array_equal(sub[v], truth[v])
+
+
+def test_solve_batch_fuzz_fast_equals_exact():
+    """Random shapes (pair scan M <= 112, general-M pair scan, triple scan; signed data, shared
+    dictionaries, zero signals, zero planted weights): screening tier == reference-order tier."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_solve_batch.py")
+    spec = importlib.util.spec_from_file_location("fuzz_solve_batch", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(ncases=40, seed=77, verbose=False) == 0
