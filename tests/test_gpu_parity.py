@@ -658,3 +658,16 @@ def test_solve_batch_fuzz_fast_equals_exact():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(ncases=40, seed=77, verbose=False) == 0
+
+
+def test_fit_fuzz_fast_equals_exact():
+    """Random MFModel.fit-path problems (dictionary size, exact-G / between-shell / M = 271
+    protocols, SNR, CSF / EAR, fascicle-count mix, planted degenerate voxels): rows of the
+    screening tiers == rows of the reference-order tier, bit for bit."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_fit.py")
+    spec = importlib.util.spec_from_file_location("fuzz_fit", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(ncases=20, seed=5, verbose=False) == 0
