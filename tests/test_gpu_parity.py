@@ -671,3 +671,29 @@ def test_fit_fuzz_fast_equals_exact():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(ncases=20, seed=5, verbose=False) == 0
+
+
+def test_solve_fuzz_vs_oracle():
+    """Random small shapes (1-3 blocks, signed and non-negative data): whatever tier decides,
+    weights, indices and objective are bit-identical to the CPU oracle (= the reference)."""
+    rng = np.random.default_rng(99)
+    for case in range(36):
+        nb = int(rng.integers(1, 4))
+        M = int(rng.choice([4, 9, 33, 100, 120]))
+        sizes = [int(rng.integers(1, 60)) for _ in range(nb)]
+        if nb >= 2 and rng.random() < 0.5:
+            sizes[0], sizes[1] = int(rng.integers(8, 150)), int(rng.integers(8, 150))
+        if nb == 3 and rng.random() < 0.4:
+            sizes[2] = 1
+        nt = int(np.sum(sizes))
+        A = rng.random((M, nt)) + 0.02
+        if rng.random() < 0.3:
+            A *= rng.choice([-1.0, 1.0], size=A.shape)
+        st = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+        V = 5
+        Y = np.stack([A[:, st + np.array([rng.integers(0, n) for n in sizes])] @ (rng.random(nb) * (rng.random(nb) < 0.8))
+                      for _ in range(V)]) + rng.choice([0.0, 0.03]) * rng.standard_normal((V, M))
+        w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+        for v in range(V):
+            wo, subo, toto, objo, _ = orc.solve(A, Y[v], sizes)
+            assert np.array_equal(sub[v], subo) and np.array_equal(w[v], wo) and obj[v] == objo, (case, sizes, M, v)
