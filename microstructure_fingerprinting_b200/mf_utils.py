@@ -30,6 +30,7 @@ __all__ = ["solve_exhaustive_posweights", "solve_exhaustive_posweights_batch",
            "get_gyromagnetic_ratio", "DT_vec_to_2Darray", "loadmat", "from_ipython",
            "rotate_atom", "rotate_atom_2Dprotocol", "rotate_scheme_mat", "vrrotvec2mat",
            "monte_carlo_average", "get_PGSE_from_phases", "solve_rotated_2Dprotocol_batch",
+           "solve_rotated_batch",
            "MultiShellTable", "SchemePlan", "GpuPlan"]
 
 
@@ -574,36 +575,11 @@ def _lerp_plan(xs, x_new):
     return j - 1, j, (x_hi - x_new) / (x_hi - x_lo), (x_new - x_lo) / (x_hi - x_lo)
 
 
-def rotate_atom(sig, sch_mat, ordir, newdir, DIFF, S0, warnings=True):
-    """Rotate HARDI signals of single fascicles from `ordir` to `newdir`
-    (reference mf_utils.py:1205-1437).
-
-    Per (G, Delta, delta) shell of `sch_mat`: nodes = sorted unique |g.ordir| (first
-    occurrences), the free-diffusion point (1, exp(-b*DIFF)*S0) appended unless a node
-    equals 1, the near-perpendicular cluster merged into its mean, linear interpolation /
-    extrapolation at |g.newdir|; b0 rows are copied.  Returns an array shaped like `sig`.
-    Extension: `newdir` of shape (V, 3) returns (V,) + sig.shape.
-    """
-    assert isinstance(sig, np.ndarray), "Input sig should be a NumPy ndarray"
-    assert isinstance(sch_mat, np.ndarray), "Input sch_mat should be a NumPy ndarray"
-    assert isinstance(ordir, np.ndarray), "Input ordir should be a NumPy ndarray"
-    assert isinstance(newdir, np.ndarray), "Input newdir should be a NumPy ndarray"
-    sig_shape = sig.shape
-    if sig.ndim == 1:
-        sig = sig.reshape((sig.size, 1))
-    if not isinstance(DIFF, np.ndarray):
-        DIFF = np.array([[DIFF]])
-    assert isinstance(S0, np.ndarray), "Input S0 should be a NumPy ndarray"
-    if S0.ndim == 1:
-        S0 = S0[:, np.newaxis]
-    if sch_mat.shape[1] < 6:
-        raise ValueError('sch_mat must be a N-by-6 or7 matrix')
-    if sch_mat.shape[0] != sig.shape[0]:
-        raise ValueError('sch_mat and sig must have the same number of rows')
-    assert sig.shape == S0.shape, "The S0 matrix should have the same size as the signal matrix"
-
-    batched = newdir.ndim == 2 and newdir.shape[1] == 3 and newdir.size > 3
-    dirs = newdir.reshape(-1, 3) if batched else newdir.reshape(1, 3)
+def _rotate_atom_plan(sig, sch_mat, ordir, dirs, DIFF, S0, warnings=True):
+    """Interpolation plan of rotate_atom (reference mf_utils.py:1205-1437) for a batch of
+    directions dirs (V, 3): lookup table (raw rows, then per shell the nodes' rows including
+    the free-diffusion anchor and the merged near-perpendicular cluster) and (row_lo, row_hi,
+    w_lo, w_hi), each (V, M)."""
     V, M = dirs.shape[0], sig.shape[0]
     gam = get_gyromagnetic_ratio('H')
     gnorm = np.sqrt((sch_mat[:, 0:3] ** 2).sum(axis=1, keepdims=True))
@@ -659,7 +635,42 @@ def rotate_atom(sig, sch_mat, ordir, newdir, DIFF, S0, warnings=True):
         w_lo[:, ind], w_hi[:, ind] = wl, wh
         rows.append(ys)
         n_rows += ys.shape[0]
-    out = _lerp_rows(np.vstack(rows), row_lo, row_hi, w_lo, w_hi)
+    return np.vstack(rows), row_lo, row_hi, w_lo, w_hi
+
+
+def rotate_atom(sig, sch_mat, ordir, newdir, DIFF, S0, warnings=True):
+    """Rotate HARDI signals of single fascicles from `ordir` to `newdir`
+    (reference mf_utils.py:1205-1437).
+
+    Per (G, Delta, delta) shell of `sch_mat`: nodes = sorted unique |g.ordir| (first
+    occurrences), the free-diffusion point (1, exp(-b*DIFF)*S0) appended unless a node
+    equals 1, the near-perpendicular cluster merged into its mean, linear interpolation /
+    extrapolation at |g.newdir|; b0 rows are copied.  Returns an array shaped like `sig`.
+    Extension: `newdir` of shape (V, 3) returns (V,) + sig.shape.
+    """
+    assert isinstance(sig, np.ndarray), "Input sig should be a NumPy ndarray"
+    assert isinstance(sch_mat, np.ndarray), "Input sch_mat should be a NumPy ndarray"
+    assert isinstance(ordir, np.ndarray), "Input ordir should be a NumPy ndarray"
+    assert isinstance(newdir, np.ndarray), "Input newdir should be a NumPy ndarray"
+    sig_shape = sig.shape
+    if sig.ndim == 1:
+        sig = sig.reshape((sig.size, 1))
+    if not isinstance(DIFF, np.ndarray):
+        DIFF = np.array([[DIFF]])
+    assert isinstance(S0, np.ndarray), "Input S0 should be a NumPy ndarray"
+    if S0.ndim == 1:
+        S0 = S0[:, np.newaxis]
+    if sch_mat.shape[1] < 6:
+        raise ValueError('sch_mat must be a N-by-6 or7 matrix')
+    if sch_mat.shape[0] != sig.shape[0]:
+        raise ValueError('sch_mat and sig must have the same number of rows')
+    assert sig.shape == S0.shape, "The S0 matrix should have the same size as the signal matrix"
+
+    batched = newdir.ndim == 2 and newdir.shape[1] == 3 and newdir.size > 3
+    dirs = newdir.reshape(-1, 3) if batched else newdir.reshape(1, 3)
+    V = dirs.shape[0]
+    table, row_lo, row_hi, w_lo, w_hi = _rotate_atom_plan(sig, sch_mat, ordir, dirs, DIFF, S0, warnings)
+    out = _lerp_rows(table, row_lo, row_hi, w_lo, w_hi)
     if np.any(np.isnan(out)):
         raise ValueError('Nan detected after rotation of substrate(s).')
     if batched:
@@ -964,57 +975,41 @@ def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF, return_device=Fal
     return np.reshape(out[0], sig_shape)
 
 
-def solve_rotated_2Dprotocol_batch(sig, sch_mat, refdir, peaks, Y, DIFF, sig_iso=None, chunk=48, device=0):
-    """Low-level AxCaliber-like pipeline for many voxels (extension; per voxel it is what the
-    reference's users write by hand, cf. tests/integration/test_exhaustive_fingerprinting.py:163-249):
-
-        D_k = rotate_atom_2Dprotocol(sig, sch_mat, refdir, peaks[v, k], DIFF)      k = 0 .. K-1
-        solve_exhaustive_posweights([D_0 .. D_{K-1} (, sig_iso)], Y[v], [N] * K (+ [1]))
-
-    sig (M, N) single-fascicle dictionary along refdir, peaks (V, K, 3) unit vectors with
-    K = 2, Y (V, M), optional isotropic column sig_iso (M,).  The interpolation plans of a
-    chunk of voxels are built on the host (vectorised, in a worker thread, while the GPU
-    searches the previous chunk), the rotated dictionaries are assembled on the GPU
-    (mfb_lerp_rows) and never leave it, the search is mfb_solve_batch.
-
-    Returns (w (V, nb), ind_subdic (V, nb) int32, min_obj (V,), ok (V,) bool); voxels whose
-    peak breaks the protocol's assumptions (reference AssertionError, e.g. a fascicle lying
-    in the gradient plane) have ok = False and zero outputs."""
+def _solve_rotated_batch(table, plan_fn, N, peaks, Y, sig_iso, chunk, device):
+    """Chunked rotate + search pipeline shared by solve_rotated_batch (HARDI, rotate_atom) and
+    solve_rotated_2Dprotocol_batch: plan_fn(dirs (D, 3)) -> (row_lo, row_hi, w_lo, w_hi, scale or
+    None, ok (D,)) is evaluated on the host in a worker thread for the next chunk while the GPU
+    assembles (mfb_lerp_rows) and searches (mfb_solve_batch) the current one; the rotated
+    dictionaries never leave the GPU."""
     import threading
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = torch.device('cuda', device)
-    sig = np.ascontiguousarray(sig, dtype=np.float64)
     peaks = np.ascontiguousarray(peaks, dtype=np.float64)
     Y = np.ascontiguousarray(Y, dtype=np.float64)
-    V, K = peaks.shape[0], peaks.shape[1]
-    M, N = sig.shape
-    if K != 2 or peaks.shape[2] != 3:
+    if peaks.ndim != 3 or peaks.shape[1] != 2 or peaks.shape[2] != 3:
         raise ValueError("peaks should have shape (V, 2, 3)")
-    if Y.shape != (V, M):
-        raise ValueError("Y should have shape (%d, %d)" % (V, M))
+    V, K = peaks.shape[0], peaks.shape[1]
+    M = Y.shape[1]
+    if Y.shape[0] != V:
+        raise ValueError("Y should have %d rows" % V)
     iso = 0 if sig_iso is None else 1
     ntot = K * N + iso
     sizes = np.ascontiguousarray(np.array([N] * K + [1] * iso, dtype=np.int64))
     nb = sizes.size
-    proto = _Protocol2D(sch_mat, refdir, DIFF)
-    d_table = torch.from_numpy(np.ascontiguousarray(proto.table(sig))).to(dev)
+    d_table = torch.from_numpy(np.ascontiguousarray(table, dtype=np.float64)).to(dev)
     d_iso = None if sig_iso is None else torch.from_numpy(np.ascontiguousarray(sig_iso, dtype=np.float64)).to(dev)
     w_out = np.zeros((V, nb))
     sub_out = np.zeros((V, nb), dtype=np.int32)
     obj_out = np.zeros(V)
     ok_out = np.zeros(V, dtype=bool)
     chunks = [(s0, min(V, s0 + chunk)) for s0 in range(0, V, chunk)]
-
-    def make_plan(c):
-        s0, s1 = chunks[c]
-        return proto.plan(peaks[s0:s1].reshape(-1, 3), strict=False)
-
     nxt = {}
 
     def worker(c):
         try:
-            nxt[c] = make_plan(c)
+            s0, s1 = chunks[c]
+            nxt[c] = plan_fn(peaks[s0:s1].reshape(-1, 3))
         except Exception as exc:       # re-raised in the main thread
             nxt[c] = exc
     if chunks:
@@ -1031,16 +1026,17 @@ def solve_rotated_2Dprotocol_batch(sig, sch_mat, refdir, peaks, Y, DIFF, sig_iso
         nv = s1 - s0
         rl, rh, wl, wh, sc, ok = plan
         okv = ok.reshape(nv, K).all(axis=1)
-        d_pl = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (rl, rh, wl, wh, sc)]
+        d_pl = [None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (rl, rh, wl, wh, sc)]
         A = torch.empty((nv, M, ntot), dtype=torch.float64, device=dev)
         if iso:
             A[:, :, K * N] = d_iso[None, :]
         with torch.cuda.device(dev):
             for k in range(K):
                 # directions are ordered (voxel, fascicle): fascicle k of every voxel is a strided view
-                pk = [x.view(nv, K, M)[:, k, :].contiguous() for x in d_pl]
+                pk = [None if x is None else x.view(nv, K, M)[:, k, :].contiguous() for x in d_pl]
                 rc = lib.mfb_lerp_rows(device, nv, M, N, d_table.data_ptr(), pk[0].data_ptr(), pk[1].data_ptr(),
-                                       pk[2].data_ptr(), pk[3].data_ptr(), pk[4].data_ptr(),
+                                       pk[2].data_ptr(), pk[3].data_ptr(),
+                                       None if pk[4] is None else pk[4].data_ptr(),
                                        A.data_ptr() + 8 * k * N, ntot, st)
                 _lib.check(rc, "mfb_lerp_rows")
         good = np.where(okv)[0]
@@ -1054,6 +1050,53 @@ def solve_rotated_2Dprotocol_batch(sig, sch_mat, refdir, peaks, Y, DIFF, sig_iso
         if th is not None:
             th.join()
     return w_out, sub_out, obj_out, ok_out
+
+
+def solve_rotated_2Dprotocol_batch(sig, sch_mat, refdir, peaks, Y, DIFF, sig_iso=None, chunk=48, device=0):
+    """Low-level AxCaliber-like pipeline for many voxels (extension; per voxel it is what the
+    reference's users write by hand, cf. tests/integration/test_exhaustive_fingerprinting.py:163-249):
+
+        D_k = rotate_atom_2Dprotocol(sig, sch_mat, refdir, peaks[v, k], DIFF)      k = 0, 1
+        solve_exhaustive_posweights([D_0, D_1 (, sig_iso)], Y[v], [N, N (, 1)])
+
+    sig (M, N) single-fascicle dictionary along refdir, peaks (V, 2, 3) unit vectors, Y (V, M),
+    optional isotropic column sig_iso (M,).  Returns (w (V, nb), ind_subdic (V, nb) int32,
+    min_obj (V,), ok (V,) bool); voxels whose peak breaks the protocol's assumptions (reference
+    AssertionError, e.g. a fascicle lying in the gradient plane) have ok = False and zero outputs."""
+    sig = np.ascontiguousarray(sig, dtype=np.float64)
+    if sig.ndim != 2 or np.asarray(Y).shape[1] != sig.shape[0]:
+        raise ValueError("sig should be (M, N) and Y (V, M)")
+    proto = _Protocol2D(sch_mat, refdir, DIFF)
+    return _solve_rotated_batch(proto.table(sig), lambda d: proto.plan(d, strict=False), sig.shape[1], peaks, Y,
+                                sig_iso, chunk, device)
+
+
+def solve_rotated_batch(sig, sch_mat, ordir, peaks, Y, DIFF, S0, sig_iso=None, chunk=256, device=0):
+    """The same pipeline for HARDI-like protocols, i.e. the reference's test_hcp_dict sequence
+    (tests/integration/test_exhaustive_fingerprinting.py:163-249) for many voxels:
+
+        D_k = rotate_atom(sig, sch_mat, ordir, peaks[v, k], DIFF, S0)               k = 0, 1
+        solve_exhaustive_posweights([D_0, D_1 (, sig_iso)], Y[v], [N, N (, 1)])
+
+    Returns (w, ind_subdic, min_obj, ok) like solve_rotated_2Dprotocol_batch (ok is all True:
+    rotate_atom has no per-direction failure mode)."""
+    sig = np.ascontiguousarray(sig, dtype=np.float64)
+    S0 = np.asarray(S0, dtype=np.float64)
+    if S0.ndim == 1:
+        S0 = S0[:, np.newaxis]
+    if sig.ndim != 2 or np.asarray(Y).shape[1] != sig.shape[0]:
+        raise ValueError("sig should be (M, N) and Y (V, M)")
+    if not isinstance(DIFF, np.ndarray):
+        DIFF = np.array([[DIFF]])
+    ordir = np.asarray(ordir, dtype=np.float64)
+    sch_mat = np.asarray(sch_mat, dtype=np.float64)
+    # the table does not depend on the directions: build it once from a dummy direction
+    table = _rotate_atom_plan(sig, sch_mat, ordir, ordir.reshape(1, 3), DIFF, S0, warnings=False)[0]
+
+    def plan_fn(dirs):
+        _, rl, rh, wl, wh = _rotate_atom_plan(sig, sch_mat, ordir, dirs, DIFF, S0, warnings=False)
+        return rl, rh, wl, wh, None, np.ones(dirs.shape[0], dtype=bool)
+    return _solve_rotated_batch(table, plan_fn, sig.shape[1], peaks, Y, sig_iso, chunk, device)
 
 
 # ----------------------------------------------------------------------------------

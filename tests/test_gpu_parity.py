@@ -697,3 +697,35 @@ def test_solve_fuzz_vs_oracle():
         for v in range(V):
             wo, subo, toto, objo, _ = orc.solve(A, Y[v], sizes)
             assert np.array_equal(sub[v], subo) and np.array_equal(w[v], wo) and obj[v] == objo, (case, sizes, M, v)
+
+
+def test_hcp_pipeline_batched(lowlevel):
+    """solve_rotated_batch (rotate_atom x 2 + CSF column + 3-block search for many voxels, plans
+    on the host, dictionaries assembled and searched on the GPU) equals the per-voxel sequence of
+    the reference's test_hcp_dict."""
+    g = lowlevel
+    ref = np.array([0.0, 0.0, 1.0])
+    sig, sch, DIFF, S0 = g["hcp_sig"], g["hcp_sch"], float(g["hcp_DIFF"]), g["hcp_S0"]
+    n = sig.shape[1]
+    rng = np.random.default_rng(3)
+    V = 9
+    peaks = rng.standard_normal((V, 2, 3))
+    peaks /= np.linalg.norm(peaks, axis=2, keepdims=True)
+    peaks[0, 0], peaks[0, 1] = g["hcp_dirs"][1], g["hcp_dirs"][2]
+    Y = np.zeros((V, sig.shape[0]))
+    truth = rng.integers(0, n, (V, 2))
+    Ds = []
+    for v in range(V):
+        D = np.zeros((sig.shape[0], 2 * n + 1))
+        for k in range(2):
+            D[:, k * n:(k + 1) * n] = mfu.rotate_atom(sig, sch, ref, peaks[v, k], DIFF, S0, warnings=False)
+        D[:, -1] = g["hcp_sig_csf"]
+        Ds.append(D)
+        Y[v] = 0.5 * D[:, truth[v, 0]] + 0.3 * D[:, n + truth[v, 1]] + 0.2 * D[:, -1]
+    Y[0] = g["hcp_y"]
+    w, sub, obj, ok = mfu.solve_rotated_batch(sig, sch, ref, peaks, Y, DIFF, S0, sig_iso=g["hcp_sig_csf"], chunk=4)
+    assert ok.all()
+    assert np.array_equal(sub[0], g["hcp_sub"]) and np.allclose(w[0], g["hcp_w"], rtol=1e-9)
+    for v in range(V):
+        w1, sub1, tot1, obj1, _ = mfu.solve_exhaustive_posweights(Ds[v], Y[v].copy(), np.array([n, n, 1]))
+        assert np.array_equal(sub[v], sub1) and np.array_equal(w[v], w1) and obj[v] == obj1
