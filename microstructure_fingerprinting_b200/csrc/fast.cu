@@ -39,9 +39,6 @@ namespace mfb {
 #define FT_NPAR 8          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu, single-solution gain
 #define FT_VP 12           // per-voxel scalars (voxp): see FastArgs
 
-// 1 - rho^2 below which a pair is tracked as ill-conditioned (its screening error bound
-// c0 / det is no longer small against typical gaps between competing pairs)
-static constexpr double kIllDet = 1e-4;
 // A competitive pair / tuple whose (refined) error bound exceeds kIllTol * c0 is tracked as
 // ill-conditioned: it can win only through the exact tier.
 static constexpr double kIllTol = 64.0;
