@@ -34,6 +34,7 @@ namespace mfb {
 #define FT_PROD 128         // producer threads (4 gather warps)
 #define FT_THREADS (FT_CONS + FT_PROD)
 #define FT_NS 3             // stages of the i2-tile ring
+#define FT_CQ (2 * FT_NS)   // slots of the per-atom parameter ring (outlives the tile's stage)
 #define FT_S1 (FT_TI + 4)  // row strides: == 4 mod 16 doubles -> conflict-free fragment loads
 #define FT_S2 (FT_TJ + 4)
 #define FT_NPAR 8          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu, single-solution gain
@@ -401,8 +402,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const int N1 = a.N1, N2 = a.N2;
     double *D1s = smem;                                   // [Mp][FT_S1]
     double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS][Mp][FT_S2]
-    double *colq = D2s + (size_t)FT_NS * Mp * FT_S2;      // [FT_NS][5][FT_TJ]  z, beta, kappa, gamma, zu
-    double *w1l = colq + FT_NS * 5 * FT_TJ;               // [Mp] plan of fascicle 1
+    double *colq = D2s + (size_t)FT_NS * Mp * FT_S2;      // [FT_CQ][5][FT_TJ]  z, beta, kappa, gamma, zu
+    double *w1l = colq + FT_CQ * 5 * FT_TJ;               // [Mp] plan of fascicle 1
     double *w1h = w1l + Mp;
     double *w2l = w1h + Mp;                               // [Mp] plan of fascicle 2
     double *w2h = w2l + Mp;
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 }
             }
             for (int e = pt; e < 5 * FT_TJ; e += FT_PROD)
-                colq[(st * 5 + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
+                colq[((jt % FT_CQ) * 5 + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
                     __ldg(cp2 + (size_t)(e / FT_TJ + 2) * a.Npad + jr * FT_TJ + (e % FT_TJ));
             mbar_arrive(&s_full[st]);
         }
@@ -637,7 +638,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 
         // ---- closed-form NNLS screening, branch-free over the thread's 16 pairs ----
         // (num + c0)/det >= thr  <=>  fma(-thr, det, num) >= -c0
-        const double *cq = colq + st * 5 * FT_TJ;
+        // the stage's D2 tile is consumed: release it before the scalar epilogue (the per-atom
+        // parameters live in a ring twice as deep, so the producers may run ahead meanwhile)
+        mbar_arrive(&s_empty[st]);
+        const double *cq = colq + (jt % FT_CQ) * 5 * FT_TJ;
         unsigned hit = 0;
         if (a.debug & 1) {
             double sacc = 0.0;
@@ -763,7 +767,6 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 }
             }
         }
-        mbar_arrive(&s_empty[st]);
     }
 
     // ---- reduction over the consumer threads: best gain, tie -> lower index ----
@@ -1741,7 +1744,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         }
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     } else {
-        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_NS * 5 * FT_TJ +
+        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_CQ * 5 * FT_TJ +
                                               5 * a.Mp + 64) + sizeof(int) * 4 * a.Mp;
         if (smem + 64 > 227 * 1024) {
             set_error("fast tier: tile does not fit in shared memory");
