@@ -13,6 +13,7 @@ from microstructure_fingerprinting_b200 import _lib, mf_utils as mfu  # noqa: E4
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+CHUNK = int(sys.argv[3]) if len(sys.argv) > 3 else 96
 g = np.load("tests/golden/lowlevel_rotation.npz")
 sch = g["ax_sch"]
 M = sch.shape[0]
@@ -47,7 +48,7 @@ best = 1e30
 for rep in range(2):
     _lib.solve_stats(reset=True)
     t0 = time.perf_counter()
-    w, sub, obj, okv = mfu.solve_rotated_2Dprotocol_batch(sig, sch, ref, peaks, Y, DIFF, chunk=64)
+    w, sub, obj, okv = mfu.solve_rotated_2Dprotocol_batch(sig, sch, ref, peaks, Y, DIFF, chunk=CHUNK)
     best = min(best, time.perf_counter() - t0)
 st = _lib.solve_stats()
 F = 2.0 * M * N * N + 4.0 * M * 2 * N + 25.0 * N * N + 3.0 * M * N * 2
