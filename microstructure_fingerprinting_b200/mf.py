@@ -274,7 +274,10 @@ class MFModel():
         if devices is None:
             devices = list(range(torch.cuda.device_count())) if parallel else [0]
         devices = list(devices)[:max(1, min(len(devices), ROI_size))]
-        y_roi = np.ascontiguousarray(data_arr[in_mask], dtype=np.float64)  # (ROI_size, M)
+        # the ROI signals are gathered chunk by chunk (a worker thread prepares the next chunk
+        # while the GPU fits the current one) instead of one (ROI_size, M) fancy-indexing copy
+        data_2d = data_arr.reshape(-1, data_arr.shape[-1])
+        roi_idx = np.flatnonzero(in_mask.ravel())
         K32 = numfasc_roi.astype(np.int32)
         csf_u8 = csf_roi.astype(np.uint8)
         ear_u8 = ear_roi.astype(np.uint8)
@@ -286,6 +289,10 @@ class MFModel():
             print("Starting estimation in %d voxel(s) on %d GPU(s)." % (ROI_size, len(devices)))
         bounds = shard_bounds(ROI_size, len(devices))
         errors = []
+        host_chunk = 1 << 17
+
+        def gather(lo, hi):
+            return np.ascontiguousarray(data_2d[roi_idx[lo:hi]], dtype=np.float64)
 
         def work(rank, dev):
             lo, hi = int(bounds[rank]), int(bounds[rank + 1])
@@ -294,9 +301,29 @@ class MFModel():
             try:
                 plan = mfu.GpuPlan(self.ms_interpolator, scheme_plan, sig_csf, sig_ear, device=dev)
                 try:
-                    params_in_mask[lo:hi] = plan.fit_host(
-                        y_roi[lo:hi], peaks_c[lo:hi], K32[lo:hi], csf_u8[lo:hi], ear_u8[lo:hi],
-                        maxfasc, csf_on, ear_on, flags=1 if exact else 0)
+                    cuts = list(range(lo, hi, host_chunk)) + [hi]
+                    nxt = {}
+
+                    def prefetch(c):
+                        try:
+                            nxt[c] = gather(cuts[c], cuts[c + 1])
+                        except BaseException as exc:
+                            nxt[c] = exc
+                    prefetch(0)
+                    for c in range(len(cuts) - 1):
+                        y_c = nxt.pop(c)
+                        if isinstance(y_c, BaseException):
+                            raise y_c
+                        th = None
+                        if c + 2 < len(cuts):
+                            th = threading.Thread(target=prefetch, args=(c + 1,))
+                            th.start()
+                        a, b_ = cuts[c], cuts[c + 1]
+                        params_in_mask[a:b_] = plan.fit_host(
+                            y_c, peaks_c[a:b_], K32[a:b_], csf_u8[a:b_], ear_u8[a:b_],
+                            maxfasc, csf_on, ear_on, flags=1 if exact else 0)
+                        if th is not None:
+                            th.join()
                 finally:
                     plan.close()
             except BaseException as exc:  # re-raised in the caller's thread
