@@ -1613,7 +1613,7 @@ static FastGeom fast_geom(int M, int N1, int N2)
 {
     FastGeom g;
     g.Mp = (M + 3) & ~3;
-    g.gemm = g.Mp > 112;
+    g.gemm = g.Mp > 112 || getenv("MFB_FORCE_GEMM") != nullptr;   // env: experiment only
     const int Nmax = N1 > N2 ? N1 : N2;
     const int padto = g.gemm ? GP_TI : FT_TJ;
     g.Npad = (Nmax + padto - 1) / padto * padto;
