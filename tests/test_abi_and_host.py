@@ -143,3 +143,33 @@ def test_cleanup_2fascicles_matches_reference():
         cleanup_2fascicles(None, None, "peaks", g["u1"], g["u2"], g["mask"])
     with pytest.raises(ValueError, match="Unknown peak mode"):
         cleanup_2fascicles(g["f1"], g["f2"], "bogus", g["u1"], g["u2"], g["mask"])
+
+
+def test_2d_protocol_batched_plan_matches_reference_goldens():
+    """Host logic of rotate_atom_2Dprotocol (mf_utils.py:1440-1690): the vectorised plan of
+    _Protocol2D, applied with the NumPy lerp of the oracle, reproduces the outputs of the
+    unmodified reference for the fixture directions, and a fascicle in the gradient plane raises
+    the reference's AssertionError (strict) / is flagged (non-strict)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lowlevel_rotation.npz"))
+    ref = np.array([0.0, 0.0, 1.0])
+    proto = mfu._Protocol2D(g["ax_sch"], ref, float(g["ax_DIFF"]))
+    rl, rh, wl, wh, sc = proto.plan(g["ax_dirs"])
+    got = orc.lerp_rows(proto.table(g["ax_sig"]), rl, rh, wl, wh, sc)
+    assert np.allclose(got, g["ax_rot"], rtol=1e-12, atol=1e-300)
+    bad = np.array([[np.sqrt(0.5), np.sqrt(0.5), 0.0]])
+    with pytest.raises(AssertionError, match="pairs of opposite directions"):
+        proto.plan(bad)
+    out = proto.plan(np.vstack([g["ax_dirs"][:1], bad]), strict=False)
+    assert out[5].tolist() == [True, False] and np.all(out[4][1] == 0.0)
+    assert np.array_equal(out[0][0], rl[0]) and np.array_equal(out[3][0], wh[0])
+
+
+def test_rotate_atom_plan_matches_reference_goldens():
+    """Host plan of rotate_atom (mf_utils.py:1205-1437) + NumPy lerp == reference outputs."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lowlevel_rotation.npz"))
+    ref = np.array([0.0, 0.0, 1.0])
+    S0 = g["hcp_S0"]
+    table, rl, rh, wl, wh = mfu._rotate_atom_plan(g["hcp_sig"], g["hcp_sch"], ref, g["hcp_dirs"],
+                                                  np.array([[float(g["hcp_DIFF"])]]), S0, warnings=False)
+    got = orc.lerp_rows(table, rl, rh, wl, wh)
+    assert np.allclose(got, g["hcp_rot"], rtol=1e-13, atol=0)
