@@ -98,6 +98,11 @@ def solve_stats(reset=False):
     return [int(x) for x in out]
 
 
+def trim(device=0):
+    """Free the device workspace mfb_solve_batch keeps between calls (mfb_trim)."""
+    check(load().mfb_trim(int(device)), "mfb_trim")
+
+
 def launch_count():
     return int(load().mfb_launch_count())
 

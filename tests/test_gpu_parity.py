@@ -729,3 +729,18 @@ def test_hcp_pipeline_batched(lowlevel):
     for v in range(V):
         w1, sub1, tot1, obj1, _ = mfu.solve_exhaustive_posweights(Ds[v], Y[v].copy(), np.array([n, n, 1]))
         assert np.array_equal(sub[v], sub1) and np.array_equal(w[v], w1) and obj[v] == obj1
+
+
+def test_workspace_trim_and_reuse():
+    """mfb_solve_batch keeps its workspace between calls; mfb_trim frees it and the next call
+    allocates it again with identical results."""
+    rng = np.random.default_rng(8)
+    A = rng.random((40, 61)) + 0.05
+    Y = rng.random((6, 40))
+    first = mfu.solve_exhaustive_posweights_batch(A, Y, np.array([30, 30, 1]))
+    _lib.trim(0)
+    again = mfu.solve_exhaustive_posweights_batch(A, Y, np.array([30, 30, 1]))
+    for f, g_ in zip(first, again):
+        assert np.array_equal(f, g_)
+    with pytest.raises(ValueError):
+        _lib.trim(-1)
