@@ -73,7 +73,7 @@ struct FastArgs {
     int ldr[3];
     int64_t r_stride[3];
     // triple scan (k_triples): thread layout, tiles, per-tile results, voxel-wide threshold
-    int tr_txt, tr_tyt, tr_nt1, tr_ntiles;
+    int tr_txt, tr_tyt, tr_nt1, tr_ntiles, tr_kc;
     double *t_gain, *t_tol, *t_ill;
     long long *t_idx;
     int *t_flag;
@@ -1188,7 +1188,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 // 13 FP64 operations, no division; "all weights positive and gain + error bound >= thr" is
 // decided on the sign bits of four doubles with integer instructions.
 // ---------------------------------------------------------------------------------
-#define TR_KC 32
+#define TR_KC_MAX 128        // i3 steps per chunk: as many as fit in shared memory, at most this
 #define TR_MAXTHREADS 384
 
 struct TripleGeom {
@@ -1210,8 +1210,9 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
     extern __shared__ __align__(16) double smem[];
     const int TXT = a.tr_txt, TYT = a.tr_tyt;
     const int T1 = 2 * TXT, T2 = 4 * TYT, rowlen = T1 + T2;
+    const int KC = a.tr_kc;                               // i3 steps per shared-memory chunk (multiple of 4)
     const int N1 = a.Nb[0], N2 = a.Nb[1], N3 = a.Nb[2];
-    double *z3s = smem + (size_t)2 * TR_KC * rowlen;       // [N3]
+    double *z3s = smem + (size_t)2 * KC * rowlen;       // [N3]
     double *red = z3s + ((N3 + 3) & ~3);                   // [64]
     __shared__ unsigned long long s_thr;
     __shared__ double s_tolG;
@@ -1253,16 +1254,16 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
     for (int i = tid; i < ((N3 + 3) & ~3); i += blockDim.x) z3s[i] = i < N3 ? cpz3[i] : -1.0;
 
     // ---- chunk loader: rows i3 of R13^T[:, i1 tile] | R23^T[:, i2 tile] ----
-    const int nchunks = (N3 + TR_KC - 1) / TR_KC;
+    const int nchunks = (N3 + KC - 1) / KC;
     auto load_chunk = [&](int c, double *dst) {
         const int segs = rowlen >> 1;
-        const int rows = min(TR_KC, ((N3 + 3) & ~3) - c * TR_KC);
+        const int rows = min(KC, ((N3 + 3) & ~3) - c * KC);
         for (int e = tid; e < rows * segs; e += blockDim.x) {
             const int r = e / segs, sg = e - r * segs;
-            const int i3 = min(c * TR_KC + r, N3 - 1);
+            const int i3 = min(c * KC + r, N3 - 1);
             double *d = dst + (size_t)r * rowlen + 2 * sg;
             const double *src;
-            bool ok = c * TR_KC + r < N3;
+            bool ok = c * KC + r < N3;
             if (!ok) { d[0] = 0.0; d[1] = 0.0; continue; }
             if (2 * sg < T1) { const int col = i10 + 2 * sg; ok = col + 1 < ld13; src = R13T + (size_t)i3 * ld13 + col; }
             else { const int col = i20 + 2 * sg - T1; ok = col + 1 < ld23; src = R23T + (size_t)i3 * ld23 + col; }
@@ -1317,9 +1318,9 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
         if ((valid >> e & 1u) && c33[e] < 1e-10) gill = INFINITY;
 
     for (int c = 0; c < nchunks; c++) {
-        if (c + 1 < nchunks) load_chunk(c + 1, smem + (size_t)((c + 1) & 1) * TR_KC * rowlen);
-        const double *B = smem + (size_t)(c & 1) * TR_KC * rowlen;
-        const int rows = min(TR_KC, N3 - c * TR_KC);
+        if (c + 1 < nchunks) load_chunk(c + 1, smem + (size_t)((c + 1) & 1) * KC * rowlen);
+        const double *B = smem + (size_t)(c & 1) * KC * rowlen;
+        const int rows = min(KC, N3 - c * KC);
         {   // pick up the voxel-wide threshold raised by other CTAs / warps
             double tn = fmax(__longlong_as_double((long long)s_thr),
                              __longlong_as_double((long long)*(volatile unsigned long long *)vthr));
@@ -1337,7 +1338,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                 const double2 r13v = *reinterpret_cast<const double2 *>(rowp + 2 * tx);
                 const double2 r23a = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty);
                 const double2 r23b = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty + 2);
-                const double z3 = z3s[c * TR_KC + r0 + s4];
+                const double z3 = z3s[c * KC + r0 + s4];
                 const double r13[2] = {r13v.x, r13v.y};
                 const double r23[4] = {r23a.x, r23a.y, r23b.x, r23b.y};
                 int sall = -1;
@@ -1372,7 +1373,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                         if (!(smask >> s4 & 1)) continue;
                         const int r = r0 + s4;
                         const double *rowp = B + (size_t)r * rowlen;
-                        const double z3 = z3s[c * TR_KC + r];
+                        const double z3 = z3s[c * KC + r];
 #pragma unroll 1
                         for (int e = 0; e < 8; e++) {
                             if (!(valid >> e & 1u)) continue;
@@ -1404,7 +1405,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                             if (gq > gb) {
                                 flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
                                 gb = gq; tb = tq;
-                                bidx = ((long long)(c * TR_KC + r) * N1 + (i10 + 2 * tx + p)) * N2 + (i20 + 4 * ty + q);
+                                bidx = ((long long)(c * KC + r) * N1 + (i10 + 2 * tx + p)) * N2 + (i20 + 4 * ty + q);
                             } else if (!(gb > gq + wide)) {
                                 flag = 1;
                             }
@@ -1902,7 +1903,12 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     }
     {
         const int rowlen = L.tg.T1 + L.tg.T2;
-        const size_t smem = sizeof(double) * ((size_t)2 * TR_KC * rowlen + ((bs.size[2] + 3) & ~3) + 64);
+        const size_t fixed = sizeof(double) * (((bs.size[2] + 3) & ~3) + 64);
+        int kc = (int)(((size_t)216 * 1024 - fixed) / (sizeof(double) * 2 * rowlen)) & ~3;
+        kc = kc > TR_KC_MAX ? TR_KC_MAX : kc;
+        if (kc < 4) { set_error("triple scan: third block too large for shared memory"); return MFB_EUNSUPPORTED; }
+        a.tr_kc = kc;
+        const size_t smem = sizeof(double) * (size_t)2 * kc * rowlen + fixed;
         MFB_CUDA_TRY(cudaFuncSetAttribute(k_triples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(k_triples, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
     }
