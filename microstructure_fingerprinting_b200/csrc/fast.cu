@@ -1,25 +1,35 @@
-// fast.cu -- the screening ("fast") tier of libmfb200 for 2-fascicle voxels, sm_100a.
+// fast.cu -- the screening ("fast") tier of libmfb200, sm_100a.
 //
 // For a voxel with two fascicles (optionally + the CSF column) the reference
 // (mf_utils.py:288-392 `_2`, 470-607 `_3`) forms the N x N cross-Gram of the two rotated
 // sub-dictionaries over the M measurements and solves a closed-form 2- or 3-variable NNLS
-// per atom pair.  Here:
-//   k_fast_prep   rotates each sub-dictionary once per voxel to get the per-atom
-//                 statistics (|a|^2, a.y, a.csf), stores the interpolation plan, and
-//                 reduces the best single-atom / atom+CSF gains (the pair-independent
-//                 branches of the NNLS);
-//   k_fast_pairs  one CTA per (voxel, 128-atom i1 tile): the rotated, CSF-projected and
-//                 normalised i1 tile stays resident in shared memory, i2 tiles of 32 atoms
-//                 are gathered from the L2-resident lookup table (register-prefetched,
-//                 double-buffered), the correlation tile is formed with FP64 tensor-core
-//                 DMMA (mma.sync.m8n8k4.f64) and consumed in registers by a division-free
-//                 closed-form NNLS + argmax epilogue;
-//   k_fast_select merges the tiles of a voxel and decides whether the winner is certain.
+// per atom pair; with three searched blocks it does so per atom triple.  Here:
+//   k_fast_prep    rotates each sub-dictionary once per voxel to get the per-atom
+//                  statistics (|a|^2, a.y, a.csf), stores the interpolation plan, and
+//                  reduces the best single-atom / atom+CSF gains (the pair-independent
+//                  branches of the NNLS) and the atoms holding them;
+//   k_fast_seed    seeds the voxel-wide screening threshold with one real pair;
+//   k_fast_pairs   M <= 112.  One CTA per (voxel, 128-atom i1 tile): the rotated,
+//                  CSF-projected and normalised i1 tile stays resident in shared memory, four
+//                  producer warps gather i2 tiles of 32 atoms from the L2-resident lookup table
+//                  (or from explicit dictionaries) into an mbarrier ring, eight consumer warps
+//                  form the correlation tile with FP64 tensor-core DMMA (mma.sync.m8n8k4.f64)
+//                  and consume it in registers by a division-free closed-form NNLS + argmax
+//                  epilogue;
+//   k_normalize + k_gemm_pairs   any M.  Both operands streamed through a k-chunked ring by
+//                  TMA bulk copies (cp.async.bulk + mbarrier complete_tx) from a normalised
+//                  copy of the dictionaries; same epilogue.  With STORE it also writes the
+//                  correlation matrices for the triple scan;
+//   k_triples      three searched blocks: 13 FP64 operations per tuple from the correlation
+//                  matrices, sign-bit test, warp vote every four steps;
+//   k_fast_select / k_select3   merge the tiles of a voxel and decide whether the winner is
+//                  certain; k_fast_select also restricts the reference-order search of voxels
+//                  won by a one-atom solution to the tiles that can hold the minimum.
 // Screening works on gains (|y|^2 - residual) in a different summation order than the
 // reference, so it only *selects*: the winning tuple is re-evaluated in the reference's
 // arithmetic by the exact tier's evaluate kernel, and every voxel whose winner is not
-// separated from the runner-up (or from a pair-independent branch) by more than the
-// screening error bound is handed to the exact tier.
+// separated from the runner-up (or from a solution with fewer active columns) by more than
+// the screening error bounds is handed to the exact tier.
 #include <climits>
 #include <cstdlib>
 #include <cstring>
