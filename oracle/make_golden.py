@@ -189,6 +189,52 @@ def rotation_and_fit_cases():
     print("ukbb_subset written")
 
 
+def fit_protocol_cases():
+    """MFModel.fit of the unmodified reference on a between-shell protocol (gradient strengths
+    that match no dense shell, mfu:1921-1956) and on the 271-row dense protocol (M > 112): the
+    two protocol kinds that the GPU build screens on materialised dictionaries."""
+    dic = ukbb_subset()
+    bvals = np.loadtxt(os.path.join(FIX, "1000521_bvals.txt"))
+    bvecs = np.loadtxt(os.path.join(FIX, "1000521_bvecs.txt"))
+    sch_dense = dic["sch_mat"]
+    sch_exact = mfu.get_PGSE_scheme_from_bval_bvec_dense(sch_dense, bvals, bvecs, 1e-3)
+    gam = mfu.get_gyromagnetic_ratio("H")
+    Del, dlt = sch_dense[0, 4], sch_dense[0, 5]
+    sch_between = sch_exact.copy()
+    sch_between[:, 3] = np.minimum(np.sqrt(bvals * 1e6 / (Del - dlt / 3)) / (gam * dlt), np.max(sch_dense[:, 3]))
+    msi = mfu.init_PGSE_multishell_interp(dic["dictionary"], sch_dense, dic["orientation"])
+    model = refmf.MFModel(dic)
+    rng = np.random.default_rng(77)
+    shape = (5, 4, 1)
+    N = dic["num_atom"]
+    numfasc = rng.integers(1, 3, size=shape)
+    csf = (rng.random(shape) < 0.5).astype(float)
+    mask = np.ones(shape)
+    peaks = rng.standard_normal(shape + (6,))
+    peaks[..., :3] /= np.linalg.norm(peaks[..., :3], axis=-1, keepdims=True)
+    peaks[..., 3:] /= np.linalg.norm(peaks[..., 3:], axis=-1, keepdims=True)
+    out = {"numfasc": numfasc, "csf": csf, "mask": mask, "peaks": peaks, "sch_between": sch_between,
+           "sch_dense": sch_dense}
+    for tag, sch in (("between", sch_between), ("dense", sch_dense)):
+        b = (gam * sch[:, 3] * sch[:, 5]) ** 2 * (sch[:, 4] - sch[:, 5] / 3)
+        sig_csf = np.exp(-sch[:, 6] / dic["T2_csf"]) * np.exp(-b * dic["DIFF_csf"])
+        data = np.zeros(shape + (sch.shape[0],))
+        for idx in np.ndindex(shape):
+            y = np.zeros(sch.shape[0])
+            for k in range(numfasc[idx]):
+                a = mfu.interp_PGSE_from_multishell(sch, peaks[idx][3 * k:3 * k + 3], msinterp=msi)
+                y += rng.uniform(0.2, 0.6) * a[:, rng.integers(0, N)]
+            y += csf[idx] * rng.uniform(0.05, 0.3) * sig_csf
+            data[idx] = 700.0 * y + 700.0 / 30.0 * rng.standard_normal(y.size)
+        ft = model.fit(data, mask, numfasc, peaks=peaks, pgse_scheme=sch, csf_mask=csf, verbose=0, parallel=False)
+        out["data_" + tag] = data
+        for pn in ft.param_names:
+            out["fit_%s_%s" % (tag, pn)] = getattr(ft, pn)
+        out["fit_%s_param_names" % tag] = np.array(ft.param_names)
+        print("fit protocol", tag, sch.shape[0], "rows done")
+    np.savez_compressed(os.path.join(OUT, "fit_protocols.npz"), **out)
+
+
 def reference_test_vectors():
     """Outputs of the reference on its own seeded test (test_synthetic_data,
     tests/integration/test_exhaustive_fingerprinting.py:94-153, shrunk)."""
@@ -361,9 +407,13 @@ def mc_cases():
 
 
 if __name__ == "__main__":
+    if "--only-protocols" in sys.argv:
+        fit_protocol_cases()
+        sys.exit(0)
     mc_cases()
     if "--only-mc" in sys.argv:
         sys.exit(0)
+    fit_protocol_cases()
     cleanup_cases()
     lowlevel_rotation_cases()
     solver_cases()

@@ -744,3 +744,25 @@ def test_workspace_trim_and_reuse():
         assert np.array_equal(f, g_)
     with pytest.raises(ValueError):
         _lib.trim(-1)
+
+
+@pytest.mark.parametrize("tag", ["between", "dense"])
+def test_mfmodel_fit_other_protocols_match_reference_maps(ukbb, tag):
+    """MFModel.fit on a between-shell protocol and on the 271-row dense protocol (both screened on
+    materialised dictionaries) against maps produced by the unmodified reference."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fit_protocols.npz"))
+    model = _ukbb_model(ukbb)
+    fit = model.fit(g["data_" + tag], g["mask"], g["numfasc"], peaks=g["peaks"], pgse_scheme=g["sch_" + tag],
+                    csf_mask=g["csf"], verbose=0)
+    assert list(fit.param_names) == [str(s) for s in g["fit_%s_param_names" % tag]]
+    ysq = np.sum(g["data_" + tag] ** 2, axis=-1) / g["data_" + tag].shape[-1]
+    for p in fit.param_names:
+        got, ref = getattr(fit, p), g["fit_%s_%s" % (tag, p)]
+        assert got.shape == ref.shape, p
+        if p == "MSE":
+            assert np.all(np.abs(got - ref) <= 1e-12 * ysq + 1e-9 * np.abs(ref)), p
+        elif p == "R2":
+            assert np.allclose(got, ref, rtol=1e-9, atol=1e-12), p
+        else:
+            assert np.allclose(got, ref, rtol=1e-9, atol=1e-300), p

@@ -144,3 +144,33 @@ def test_mc_average_oracle_matches_reference():
             got = orc.mc_average(g["phases"][:, :dim], g["pick"], g["gsc"][:, :dim], ds, int(g["n_spin"]))
             # same summation order; libm vs Numba's cos may differ in the last ulp per term
             assert np.allclose(got, g["avg_d%d_s%g" % (dim, ds)], rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("tag", ["between", "dense"])
+def test_fit_rows_match_reference_other_protocols(ukbb, tag):
+    """Oracle _fit_voxel on a between-shell protocol (mfu:1921-1956) and on the 271-row dense
+    protocol against MFModel.fit of the unmodified reference (tests/golden/fit_protocols.npz,
+    oracle/make_golden.py fit_protocol_cases)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fit_protocols.npz"))
+    sch = g["sch_" + tag]
+    tab = orc.init_table(ukbb["dictionary"], ukbb["sch_mat"], ukbb["orientation"])
+    plan = orc.plan_scheme(tab, sch)
+    mask = g["mask"] > 0
+    sig_csf, sig_ear = orc.iso_signals(sch, float(ukbb["T2_csf"]), float(ukbb["DIFF_csf"]),
+                                       float(ukbb["T2_ear"]), ukbb["DIFF_ear"])
+    Kv = g["numfasc"][mask].astype(int)
+    rows = orc.fit_rows(tab, plan, g["data_" + tag][mask], Kv, g["csf"][mask], np.zeros(Kv.size),
+                        g["peaks"][mask][:, :6], sig_csf, sig_ear)
+
+    def ref(name):
+        return g["fit_%s_%s" % (tag, name)][mask]
+    assert np.allclose(rows[:, 0], ref("M0"), rtol=1e-9, atol=0)
+    for k in range(2):
+        assert np.allclose(rows[:, 1 + k], ref("frac_f%d" % k), rtol=1e-9, atol=1e-300)
+        ids = rows[:, 3 + k].astype(int)
+        assert np.array_equal(ukbb["rad"][ids] * (rows[:, 1 + k] > 0), ref("rad_f%d" % k))
+    assert np.allclose(rows[:, 5], ref("frac_csf"), rtol=1e-9, atol=1e-300)
+    ysq = np.sum(g["data_" + tag][mask] ** 2, axis=1) / sch.shape[0]
+    assert np.all(np.abs(rows[:, -2] - ref("MSE")) <= 1e-12 * ysq + 1e-9 * ref("MSE"))
+    assert np.allclose(rows[:, -1], ref("R2"), rtol=1e-9, atol=1e-12)
