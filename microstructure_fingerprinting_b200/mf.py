@@ -18,11 +18,30 @@ from . import mf_utils as mfu
 from . import nifti
 
 
-def shard_bounds(n_items, n_shards):
-    """Contiguous, balanced split of range(n_items) into n_shards spans: returns the
-    n_shards + 1 boundaries.  Used for the per-GPU ROI shards (no data-path collective:
-    voxels are independent given the replicated plan)."""
-    return np.linspace(0, n_items, n_shards + 1).astype(np.int64)
+def shard_bounds(n_items, n_shards, cost=None):
+    """Contiguous split of range(n_items) into n_shards spans: returns the n_shards + 1
+    boundaries.  Used for the per-GPU ROI shards (no data-path collective: voxels are
+    independent given the replicated plan).  Without `cost` the spans hold equal counts; with
+    a per-item cost (n_items,) they hold (nearly) equal total cost, so that GPUs finish together
+    when the fascicle count varies over the ROI."""
+    if cost is None or n_shards <= 1 or n_items == 0:
+        return np.linspace(0, n_items, n_shards + 1).astype(np.int64)
+    csum = np.concatenate(([0.0], np.cumsum(np.asarray(cost, dtype=np.float64))))
+    if not csum[-1] > 0:
+        return np.linspace(0, n_items, n_shards + 1).astype(np.int64)
+    targets = csum[-1] * np.arange(1, n_shards) / n_shards
+    inner = np.searchsorted(csum, targets, side="left")
+    b = np.concatenate(([0], inner, [n_items])).astype(np.int64)
+    return np.maximum.accumulate(b)
+
+
+def voxel_cost(numfasc_roi, csf_roi, ear_roi, n_atoms, n_ear):
+    """Relative cost of fitting a voxel: the number of atom tuples searched (the dominant term
+    of SURVEY 8d's flop count), floored at one unit."""
+    K = np.asarray(numfasc_roi)
+    c = np.where(K >= 2, float(n_atoms) ** 2, np.where(K == 1, float(n_atoms), 1.0))
+    c = c * np.where(np.asarray(ear_roi) > 0, float(max(n_ear, 1)), 1.0)
+    return np.maximum(c * np.where(np.asarray(csf_roi) > 0, 1.3, 1.0), 1.0)
 
 
 def _as_array(x):
@@ -287,7 +306,8 @@ class MFModel():
         st_est = time.time()
         if VRB >= 2:
             print("Starting estimation in %d voxel(s) on %d GPU(s)." % (ROI_size, len(devices)))
-        bounds = shard_bounds(ROI_size, len(devices))
+        bounds = shard_bounds(ROI_size, len(devices),
+                              voxel_cost(numfasc_roi, csf_roi, ear_roi, self.dic['num_atom'], self.dic.get('num_ear', 1)))
         errors = []
         host_chunk = 1 << 17
 

@@ -60,3 +60,19 @@ def test_shard_bounds_cover_everything():
             b = shard_bounds(V, w)
             assert b[0] == 0 and b[-1] == V and np.all(np.diff(b) >= 0)
             assert np.max(np.diff(b)) - np.min(np.diff(b)) <= 1
+
+
+def test_shard_bounds_balance_cost():
+    """Cost-weighted shards: monotone boundaries covering everything, per-shard cost within one
+    item of the ideal share."""
+    from microstructure_fingerprinting_b200.mf import voxel_cost
+    rng = np.random.default_rng(0)
+    K = rng.integers(0, 3, 5000)
+    cost = voxel_cost(K, rng.integers(0, 2, 5000), np.zeros(5000), 1000, 4)
+    for w in (1, 2, 3, 8):
+        b = shard_bounds(5000, w, cost)
+        assert b[0] == 0 and b[-1] == 5000 and np.all(np.diff(b) >= 0) and b.size == w + 1
+        share = np.array([cost[b[i]:b[i + 1]].sum() for i in range(w)])
+        assert np.all(np.abs(share - cost.sum() / w) <= cost.max() + 1e-9)
+    assert np.array_equal(shard_bounds(10, 4, np.zeros(10)), shard_bounds(10, 4))
+    assert np.array_equal(shard_bounds(0, 3, np.zeros(0)), np.zeros(4, dtype=np.int64))
