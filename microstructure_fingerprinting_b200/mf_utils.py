@@ -978,9 +978,9 @@ def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF, return_device=Fal
 def _solve_rotated_batch(table, plan_fn, N, peaks, Y, sig_iso, chunk, device):
     """Chunked rotate + search pipeline shared by solve_rotated_batch (HARDI, rotate_atom) and
     solve_rotated_2Dprotocol_batch: plan_fn(dirs (D, 3)) -> (row_lo, row_hi, w_lo, w_hi, scale or
-    None, ok (D,)) is evaluated on the host in a worker thread for the next chunk while the GPU
-    assembles (mfb_lerp_rows) and searches (mfb_solve_batch) the current one; the rotated
-    dictionaries never leave the GPU."""
+    None, ok (D,)).  A worker thread prepares chunk c + 1 -- host plan, upload, dictionary assembly
+    on the GPU (mfb_lerp_rows) on its own CUDA stream -- while the main thread searches chunk c
+    (mfb_solve_batch); the rotated dictionaries never leave the GPU."""
     import threading
     torch = _lib.require_cuda()
     lib = _lib.load()
@@ -1004,49 +1004,59 @@ def _solve_rotated_batch(table, plan_fn, N, peaks, Y, sig_iso, chunk, device):
     obj_out = np.zeros(V)
     ok_out = np.zeros(V, dtype=bool)
     chunks = [(s0, min(V, s0 + chunk)) for s0 in range(0, V, chunk)]
-    nxt = {}
+    side = torch.cuda.Stream(device=dev)          # assembly stream of the worker
+    ready = {}
 
-    def worker(c):
+    def prepare(c):
+        """plan (host) -> upload -> assemble A (GPU, side stream); leaves (A, Yg, good, event)."""
         try:
             s0, s1 = chunks[c]
-            nxt[c] = plan_fn(peaks[s0:s1].reshape(-1, 3))
-        except Exception as exc:       # re-raised in the main thread
-            nxt[c] = exc
+            nv = s1 - s0
+            rl, rh, wl, wh, sc, ok = plan_fn(peaks[s0:s1].reshape(-1, 3))
+            good = np.where(ok.reshape(nv, K).all(axis=1))[0]
+            with torch.cuda.device(dev), torch.cuda.stream(side):
+                d_pl = [None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev, non_blocking=True)
+                        for x in (rl, rh, wl, wh, sc)]
+                A = torch.empty((nv, M, ntot), dtype=torch.float64, device=dev)
+                if iso:
+                    A[:, :, K * N] = d_iso[None, :]
+                for k in range(K):
+                    # directions are ordered (voxel, fascicle): fascicle k of every voxel is a strided view
+                    pk = [None if x is None else x.view(nv, K, M)[:, k, :].contiguous() for x in d_pl]
+                    rc = lib.mfb_lerp_rows(device, nv, M, N, d_table.data_ptr(), pk[0].data_ptr(), pk[1].data_ptr(),
+                                           pk[2].data_ptr(), pk[3].data_ptr(),
+                                           None if pk[4] is None else pk[4].data_ptr(),
+                                           A.data_ptr() + 8 * k * N, ntot, side.cuda_stream)
+                    _lib.check(rc, "mfb_lerp_rows")
+                if good.size != nv:
+                    A = A.index_select(0, torch.from_numpy(good).to(dev)).contiguous()
+                Yg = torch.from_numpy(Y[s0:s1][good]).to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ready[c] = (A, Yg, good, ev)
+        except BaseException as exc:       # re-raised in the main thread
+            ready[c] = exc
+
     if chunks:
-        worker(0)
-    st = torch.cuda.current_stream(dev).cuda_stream
+        prepare(0)
+    main_stream = torch.cuda.current_stream(dev)
     for c, (s0, s1) in enumerate(chunks):
-        plan = nxt.pop(c)
-        if isinstance(plan, Exception):
-            raise plan
+        item = ready.pop(c)
+        if isinstance(item, BaseException):
+            raise item
         th = None
         if c + 1 < len(chunks):
-            th = threading.Thread(target=worker, args=(c + 1,))
+            th = threading.Thread(target=prepare, args=(c + 1,))
             th.start()
-        nv = s1 - s0
-        rl, rh, wl, wh, sc, ok = plan
-        okv = ok.reshape(nv, K).all(axis=1)
-        d_pl = [None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (rl, rh, wl, wh, sc)]
-        A = torch.empty((nv, M, ntot), dtype=torch.float64, device=dev)
-        if iso:
-            A[:, :, K * N] = d_iso[None, :]
-        with torch.cuda.device(dev):
-            for k in range(K):
-                # directions are ordered (voxel, fascicle): fascicle k of every voxel is a strided view
-                pk = [None if x is None else x.view(nv, K, M)[:, k, :].contiguous() for x in d_pl]
-                rc = lib.mfb_lerp_rows(device, nv, M, N, d_table.data_ptr(), pk[0].data_ptr(), pk[1].data_ptr(),
-                                       pk[2].data_ptr(), pk[3].data_ptr(),
-                                       None if pk[4] is None else pk[4].data_ptr(),
-                                       A.data_ptr() + 8 * k * N, ntot, st)
-                _lib.check(rc, "mfb_lerp_rows")
-        good = np.where(okv)[0]
+        A, Yg, good, ev = item
+        main_stream.wait_event(ev)
         if good.size:
-            gi = torch.from_numpy(good).to(dev)
-            Ag = A if good.size == nv else A.index_select(0, gi).contiguous()
-            Yg = torch.from_numpy(Y[s0:s1][good]).to(dev)
-            w, sub, tot, obj, _ = solve_exhaustive_posweights_batch(Ag, Yg, sizes, device=device, return_device=True)
+            A.record_stream(main_stream)
+            Yg.record_stream(main_stream)
+            w, sub, tot, obj, _ = solve_exhaustive_posweights_batch(A, Yg, sizes, device=device, return_device=True)
             w_out[s0 + good], sub_out[s0 + good], obj_out[s0 + good] = w.cpu().numpy(), sub.cpu().numpy(), obj.cpu().numpy()
             ok_out[s0 + good] = True
+        del A, Yg
         if th is not None:
             th.join()
     return w_out, sub_out, obj_out, ok_out
