@@ -766,3 +766,44 @@ def test_mfmodel_fit_other_protocols_match_reference_maps(ukbb, tag):
             assert np.allclose(got, ref, rtol=1e-9, atol=1e-12), p
         else:
             assert np.allclose(got, ref, rtol=1e-9, atol=1e-300), p
+
+
+def test_c_abi_rejects_bad_arguments():
+    """The C ABI never throws: bad arguments come back as MFB_EINVAL with a message, which the
+    Python mirror turns into ValueError (include/mfb200.h conventions)."""
+    import ctypes
+    import torch
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    A = torch.rand((10, 6), dtype=torch.float64, device=dev)
+    y = torch.rand((2, 10), dtype=torch.float64, device=dev)
+    w = torch.zeros((2, 2), dtype=torch.float64, device=dev)
+    sub = torch.zeros((2, 2), dtype=torch.int32, device=dev)
+    obj = torch.zeros(2, dtype=torch.float64, device=dev)
+    sizes = np.array([3, 3], dtype=np.int64)
+    p = sizes.ctypes.data_as(ctypes.c_void_p)
+
+    def call(nb, lda, sz=p, Aptr=A.data_ptr()):
+        return lib.mfb_solve_batch(0, 2, 10, nb, sz, Aptr, lda, 0, y.data_ptr(), w.data_ptr(), sub.data_ptr(),
+                                   obj.data_ptr(), None, None)
+    assert call(2, 6) == 0
+    assert call(2, 5) == _lib.MFB_EINVAL and b"lda" in lib.mfb_last_error()
+    assert call(6, 6) == _lib.MFB_EINVAL
+    assert call(2, 6, Aptr=None) == _lib.MFB_EINVAL
+    bad = np.array([3, 0], dtype=np.int64)
+    assert call(2, 6, sz=bad.ctypes.data_as(ctypes.c_void_p)) == _lib.MFB_EINVAL
+    assert lib.mfb_fit(None, 1, None, None, None, None, None, 2, 0, 0, None, 0, None) == _lib.MFB_EINVAL
+    assert lib.mfb_mc_average(0, 10, 9, A.data_ptr(), 1, A.data_ptr(), A.data_ptr(), 1.0, 5, A.data_ptr(), None) == _lib.MFB_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(_lib.MFB_EINVAL, "x")
+    ph = make_phantom(n_atoms=16, n_vox=4, seed=1)
+    msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), None, None)
+    try:
+        # a CSF voxel on a plan without a CSF column, and more than two fascicles
+        with pytest.raises(ValueError):
+            plan.fit_host(ph.Y, ph.peaks, ph.K, np.ones(4, np.uint8), None, ph.maxfasc, True, False)
+        with pytest.raises(ValueError):
+            plan.fit_host(ph.Y, np.zeros((4, 9)), np.full(4, 3, np.int32), None, None, 3, False, False)
+    finally:
+        plan.close()
