@@ -136,17 +136,47 @@ k_rotate_assemble(DevPlan p, const int32_t *vox_list, const double *peaks, int p
     }
     __syncthreads();
     double *out = Av + (size_t)k * N;
-    for (int m = 0; m < M; m++) {
+    // one warp per measurement row; lanes stream the row with 16-byte accesses when the row
+    // starts of the table and of the output are 16-byte aligned (N, lda, k*N even)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const bool vec = (N % 2 == 0) && (lda % 2 == 0) && ((((size_t)k * N) & 1) == 0) &&
+                     ((reinterpret_cast<size_t>(p.table) & 15) == 0) && ((reinterpret_cast<size_t>(Av) & 15) == 0);
+    for (int m = warp; m < M; m += nwarp) {
         Lerp a, b;
         a.rl = rl[m]; a.rh = rh[m]; a.wl = wl[m]; a.wh = wh[m];
         const bool between = rl2[m] >= 0;
         double gwl = 0.0, gwh = 0.0;
+        b = a;
         if (between) {
             b.rl = rl2[m]; b.rh = rh2[m]; b.wl = wl2[m]; b.wh = wh2[m];
             gwl = p.gw_lo[m]; gwh = p.gw_hi[m];
         }
-        for (int j = threadIdx.x; j < N; j += blockDim.x)
-            out[(size_t)m * lda + j] = rot_entry(p, a, b, between, gwl, gwh, j);
+        double *orow = out + (size_t)m * lda;
+        if (vec) {
+            const double2 *Tl = reinterpret_cast<const double2 *>(p.table + (size_t)a.rl * N);
+            const double2 *Th = reinterpret_cast<const double2 *>(p.table + (size_t)a.rh * N);
+            const double2 *Tl2 = reinterpret_cast<const double2 *>(p.table + (size_t)b.rl * N);
+            const double2 *Th2 = reinterpret_cast<const double2 *>(p.table + (size_t)b.rh * N);
+            double2 *o2 = reinterpret_cast<double2 *>(orow);
+            const int n2 = N >> 1;
+#pragma unroll 4
+            for (int j = lane; j < n2; j += 32) {
+                const double2 lo = __ldg(Tl + j), hi = __ldg(Th + j);
+                double2 d;
+                d.x = DA(DM(a.wh, hi.x), DM(a.wl, lo.x));
+                d.y = DA(DM(a.wh, hi.y), DM(a.wl, lo.y));
+                if (between) {
+                    const double2 lo2 = __ldg(Tl2 + j), hi2 = __ldg(Th2 + j);
+                    const double hx = DA(DM(b.wh, hi2.x), DM(b.wl, lo2.x));
+                    const double hy = DA(DM(b.wh, hi2.y), DM(b.wl, lo2.y));
+                    d.x = DA(DM(gwh, hx), DM(gwl, d.x));
+                    d.y = DA(DM(gwh, hy), DM(gwl, d.y));
+                }
+                o2[j] = d;
+            }
+        } else {
+            for (int j = lane; j < N; j += 32) orow[j] = rot_entry(p, a, b, between, gwl, gwh, j);
+        }
     }
 }
 
@@ -180,8 +210,21 @@ k_lerp_rows(int M, int N, const double *table, const int32_t *row_lo, const int3
     const double *tl = table + (size_t)row_lo[o] * N, *th = table + (size_t)row_hi[o] * N;
     const double wl = w_lo[o], wh = w_hi[o];
     double *dst = out + (v * M + m) * ldd;
-    if (scale) {
-        const double sc = scale[o];
+    const double sc = scale ? scale[o] : 1.0;
+    const bool vec = (N % 2 == 0) && (ldd % 2 == 0) && ((reinterpret_cast<size_t>(table) & 15) == 0) &&
+                     ((reinterpret_cast<size_t>(out) & 15) == 0);
+    if (vec) {      // 16-byte accesses
+        const double2 *tl2 = reinterpret_cast<const double2 *>(tl), *th2 = reinterpret_cast<const double2 *>(th);
+        double2 *d2 = reinterpret_cast<double2 *>(dst);
+        for (int j = threadIdx.x; j < (N >> 1); j += blockDim.x) {
+            const double2 lo = __ldg(tl2 + j), hi = __ldg(th2 + j);
+            double2 r;
+            r.x = DA(DM(wh, hi.x), DM(wl, lo.x));
+            r.y = DA(DM(wh, hi.y), DM(wl, lo.y));
+            if (scale) { r.x = DM(sc, r.x); r.y = DM(sc, r.y); }
+            d2[j] = r;
+        }
+    } else if (scale) {
         for (int j = threadIdx.x; j < N; j += blockDim.x) dst[j] = DM(sc, DA(DM(wh, th[j]), DM(wl, tl[j])));
     } else {
         for (int j = threadIdx.x; j < N; j += blockDim.x) dst[j] = DA(DM(wh, th[j]), DM(wl, tl[j]));
