@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(32) k_fast_seed(FastArgs a)
 }
 
 // Warp-specialised pair scan.  Warps 0..7 (consumers): DMMA correlation tile + closed-form
-// epilogue; warps 8..9 (producers): gather the next i2 tiles from the L2-resident lookup
+// epilogue; warps 8..11 (producers): gather the next i2 tiles from the L2-resident lookup
 // table, rotate / project / normalise them and fill a 3-stage shared-memory ring.  full[] /
 // empty[] mbarriers are the only synchronisation inside the tile loop, so consumer warps
 // drift apart and one warp's scalar epilogue overlaps another warp's DMMA stream.
