@@ -50,8 +50,14 @@ extern "C" {
 
 typedef struct mfb_plan mfb_plan;
 
-/* ABI version (bumped on any signature change). */
+/* ABI version (bumped on any signature change); mfb_version() returns the value the
+ * library was built with, the Python binding refuses a library whose version differs. */
+#define MFB_ABI_VERSION 3
 int mfb_version(void);
+
+/* element types of the host volume handed to mfb_fit_volume */
+#define MFB_F64 0
+#define MFB_F32 1
 
 /* Message of the last error raised on this thread ("" if none). */
 const char *mfb_last_error(void);
@@ -117,12 +123,14 @@ int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *table,
  * 1-3 blocks reproduce the reference's arithmetic exactly (summation order,
  * no FMA, loop-order tie-break); 4-5 blocks use closed-form support
  * enumeration, which agrees with scipy.optimize.nnls to rounding.
+ * flags: bit 0 = force the exact (reference-order) tier for every voxel (verification;
+ * results are the same by construction).
  */
 int mfb_solve_batch(int device, int64_t V, int M, int nblocks,
                     const int64_t *sizes, const double *A, int64_t lda,
                     int64_t strideA, const double *y, double *w,
                     int32_t *idx_sub, double *min_obj, double *y_rec,
-                    void *stream);
+                    int flags, void *stream);
 
 /*
  * Monte-Carlo signal synthesis, mfu.monte_carlo_average (mf_utils.py:2758-2812):
@@ -159,12 +167,30 @@ int mfb_fit(mfb_plan *plan, int64_t V, const double *y, const double *peaks,
             int maxfasc, int csf_on, int ear_on, double *params_out,
             int flags, void *stream);
 
-/* Same with HOST buffers: chunked H2D / compute / D2H on the plan's own stream
- * (copies are < 1 % of the fit time).  This is the call a non-PyTorch host binds. */
+/* Same with HOST buffers (pageable or page-locked): chunks of voxels are staged into the
+ * plan's page-locked slots by a helper thread, uploaded, searched and downloaded on three
+ * streams so that staging, H2D, compute and D2H overlap.  This is the call a non-PyTorch
+ * host binds.  Returns when params_out is complete. */
 int mfb_fit_host(mfb_plan *plan, int64_t V, const double *y, const double *peaks,
                  const int32_t *K, const uint8_t *csf, const uint8_t *ear,
                  int maxfasc, int csf_on, int ear_on, double *params_out,
                  int flags);
+
+/*
+ * The voxel loop of MFModel.fit over ROI voxels scattered in a host volume: replaces
+ * `data_arr[mask > 0]` (mf:644) + the loop (mf:978-1028) without materialising the
+ * (ROI_size, M) copy.  Measurement m of voxel v is element
+ *     voxel_offset[v] + m * meas_stride        (voxel_offset != NULL)
+ *     v * row_stride + m * meas_stride         (voxel_offset == NULL)
+ * of the host array `data` of element type `dtype` (MFB_F64 / MFB_F32; float32 volumes are
+ * widened on the fly).  The gather runs in the library's helper thread, overlapped with the
+ * GPU.  peaks / K / csf / ear / params_out are host arrays in ROI order as for mfb_fit_host.
+ */
+int mfb_fit_volume(mfb_plan *plan, int64_t V, const void *data, int dtype,
+                   const int64_t *voxel_offset, int64_t row_stride, int64_t meas_stride,
+                   const double *peaks, const int32_t *K, const uint8_t *csf,
+                   const uint8_t *ear, int maxfasc, int csf_on, int ear_on,
+                   double *params_out, int flags);
 
 /* Per-plan counters of the last mfb_fit / mfb_fit_host call, out[8]:
  *   [0] voxels accepted by the fast (DMMA screening) tier, [1] voxels solved by the exact

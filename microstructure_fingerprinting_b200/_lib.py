@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MFB_LIB") or os.path.join(_HERE, "libmfb200.so")   # MFB_LIB: A/B builds
 
 MFB_OK, MFB_EINVAL, MFB_ECUDA, MFB_ENOMEM, MFB_EUNSUPPORTED = 0, -1, -2, -3, -4
+MFB_ABI_VERSION = 3          # include/mfb200.h; a library built from other sources is refused
+MFB_F64, MFB_F32 = 0, 1
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int32)
@@ -31,11 +33,14 @@ SYMBOLS = {
                                      c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp]),
     "mfb_solve_batch": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_vp,
                                        c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp, c_vp,
-                                       c_vp, c_vp]),
+                                       c_vp, ctypes.c_int, c_vp]),
     "mfb_fit": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
                                ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_vp]),
     "mfb_fit_host": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int]),
+    "mfb_fit_volume": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, ctypes.c_int, c_vp, ctypes.c_int64,
+                                      ctypes.c_int64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, c_vp, ctypes.c_int]),
     "mfb_fit_stats": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "mfb_solve_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "mfb_trim": (ctypes.c_int, [ctypes.c_int]),
@@ -65,6 +70,11 @@ def load():
                 "`python -m microstructure_fingerprinting_b200.build`; this package has no "
                 "CPU fallback." % (exc,))
     lib = ctypes.CDLL(LIB_PATH)
+    lib.mfb_version.restype = ctypes.c_int
+    if lib.mfb_version() != MFB_ABI_VERSION:
+        raise MFBError("%s was built for ABI version %d, this package binds version %d: rebuild it "
+                       "(`python -m microstructure_fingerprinting_b200.build --force`)."
+                       % (LIB_PATH, lib.mfb_version(), MFB_ABI_VERSION))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -3,8 +3,10 @@
 // tier where it applies and the exact (reference-order) tier elsewhere, evaluate the
 // winning tuple in the reference's arithmetic, pack the params rows.
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -41,6 +43,43 @@ struct Buf {
     template <typename T> T *as() { return (T *)p; }
 };
 
+// page-locked host buffer (staging slots of the host pipeline)
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return MFB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            set_error("page-locked host allocation of " + std::to_string(bytes) + " bytes failed");
+            return MFB_ENOMEM;
+        }
+        cap = bytes;
+        return MFB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Every entry point runs on its plan's (or the requested) device and puts the caller's
+// current device back on return: a library call must not move the host thread to another GPU.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != device) err = cudaSetDevice(device); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define MFB_ON_DEVICE(dev)                 \
+    ::mfb::DeviceGuard guard__(dev);       \
+    MFB_CUDA_TRY(guard__.err)
+
 static BlockSpec make_spec(int nb, const int64_t *sizes)
 {
     BlockSpec bs;
@@ -72,8 +111,11 @@ struct mfb_plan {
     std::vector<void *> owned;
     // per-chunk workspace
     Buf type, nbv, lists, counts, tuple, asmall, idx5, w5, obj, yrec, abuf, scratch, fscratch, redo, redomask;
-    // host staging for mfb_fit_host
-    Buf d_y, d_peaks, d_K, d_csf, d_ear, d_params;
+    // host pipeline of mfb_fit_host / mfb_fit_volume: page-locked and device slots, streams, events
+    PinBuf h_in[3], h_out[2];
+    Buf d_in[2], d_out[2];
+    cudaStream_t s_copy = nullptr, s_d2h = nullptr;
+    cudaEvent_t pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> events;  // pairs bracketing the dominant kernel (flags bit 1)
     size_t events_used = 0;
@@ -95,7 +137,7 @@ extern "C" int mfb_trim(int device)
     SolveCache &c = g_solve_cache[device];
     std::lock_guard<std::mutex> lock(c.mu);
     if (c.scratch.p || c.tuple.p) {
-        MFB_CUDA_TRY(cudaSetDevice(device));
+        MFB_ON_DEVICE(device);
         Buf *bufs[] = {&c.scratch, &c.tuple, &c.asmall, &c.idx5, &c.w5, &c.redo, &c.redomask};
         for (Buf *b : bufs) b->release();
     }
@@ -107,7 +149,7 @@ extern "C" int mfb_trim(int device)
 // competitor, near tie, branch with fewer active columns)
 static std::atomic<long long> g_solve_stats[6];
 
-extern "C" int mfb_version(void) { return 2; }
+extern "C" int mfb_version(void) { return MFB_ABI_VERSION; }
 extern "C" int mfb_solve_stats(int64_t *out, int n, int reset)
 {
     if (!out && n > 0) { set_error("mfb_solve_stats: invalid argument"); return MFB_EINVAL; }
@@ -135,7 +177,6 @@ static int plan_build(mfb_plan *pl, int device, int M, int N, int R, int n_shell
                       const double *gw_lo, const double *gw_hi, const double *sig_csf,
                       const double *sig_ear, int E)
 {
-    MFB_CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     MFB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
@@ -185,6 +226,12 @@ extern "C" mfb_plan *mfb_plan_create(int device, int M, int N, int R, int n_shel
         set_error("mfb_plan_create: invalid argument");
         return nullptr;
     }
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) {
+        set_error(std::string("mfb_plan_create: cudaSetDevice: ") + cudaGetErrorString(guard.err));
+        cudaGetLastError();
+        return nullptr;
+    }
     mfb_plan *pl = new (std::nothrow) mfb_plan();
     if (!pl) { set_error("out of host memory"); return nullptr; }
     int rc = plan_build(pl, device, M, N, R, n_shells, shell_row_offset, nodes, table, gdir,
@@ -196,12 +243,17 @@ extern "C" mfb_plan *mfb_plan_create(int device, int M, int N, int R, int n_shel
 extern "C" void mfb_plan_destroy(mfb_plan *pl)
 {
     if (!pl) return;
-    cudaSetDevice(pl->device);
+    DeviceGuard guard(pl->device);
     for (void *p : pl->owned) cudaFree(p);
     Buf *bufs[] = {&pl->type, &pl->nbv, &pl->lists, &pl->counts, &pl->tuple, &pl->asmall,
                    &pl->idx5, &pl->w5, &pl->obj, &pl->yrec, &pl->abuf, &pl->scratch, &pl->fscratch, &pl->redo, &pl->redomask,
-                   &pl->d_y, &pl->d_peaks, &pl->d_K, &pl->d_csf, &pl->d_ear, &pl->d_params};
+                   &pl->d_in[0], &pl->d_in[1], &pl->d_out[0], &pl->d_out[1]};
     for (Buf *b : bufs) b->release();
+    for (PinBuf &b : pl->h_in) b.release();
+    for (PinBuf &b : pl->h_out) b.release();
+    for (cudaEvent_t e : pl->pipe_ev) if (e) cudaEventDestroy(e);
+    if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    if (pl->s_d2h) cudaStreamDestroy(pl->s_d2h);
     for (cudaEvent_t e : pl->events) cudaEventDestroy(e);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     delete pl;
@@ -214,7 +266,7 @@ extern "C" int mfb_rotate_multishell(mfb_plan *pl, int64_t V, const double *dirs
         set_error("mfb_rotate_multishell: invalid argument");
         return MFB_EINVAL;
     }
-    MFB_CUDA_TRY(cudaSetDevice(pl->device));
+    MFB_ON_DEVICE(pl->device);
     return launch_rotate_assemble(pl->dp, V, nullptr, dirs, 3, 1, 0, 0, D_out, ldd,
                                   (int64_t)pl->dp.M * ldd, (cudaStream_t)stream);
 }
@@ -228,7 +280,7 @@ extern "C" int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *
         set_error("mfb_lerp_rows: invalid argument");
         return MFB_EINVAL;
     }
-    MFB_CUDA_TRY(cudaSetDevice(device));
+    MFB_ON_DEVICE(device);
     return launch_lerp_rows(V, M, N, table, row_lo, row_hi, w_lo, w_hi, scale, out, ldd, (cudaStream_t)stream);
 }
 
@@ -242,7 +294,7 @@ extern "C" int mfb_mc_average(int device, int64_t n_entries, int dim, const doub
         return MFB_EINVAL;
     }
     if (n_seq == 0) return MFB_OK;
-    MFB_CUDA_TRY(cudaSetDevice(device));
+    MFB_ON_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     const int nsplit = mc_nsplit(n_seq, num_spins);
     double *partial = nullptr;
@@ -259,7 +311,7 @@ extern "C" int mfb_mc_average(int device, int64_t n_entries, int dim, const doub
 extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const int64_t *sizes,
                                const double *A, int64_t lda, int64_t strideA, const double *y,
                                double *w, int32_t *idx_sub, double *min_obj, double *y_rec,
-                               void *stream)
+                               int flags, void *stream)
 {
     if (V < 0 || M <= 0 || nblocks < 1 || nblocks > 5 || !sizes || (V > 0 && (!A || !y || !w || !idx_sub || !min_obj))) {
         set_error("mfb_solve_batch: invalid argument");
@@ -269,12 +321,13 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
         if (sizes[b] <= 0) { set_error("mfb_solve_batch: sizes must be > 0"); return MFB_EINVAL; }
     BlockSpec bs = make_spec(nblocks, sizes);
     if (lda < bs.ntot) { set_error("mfb_solve_batch: lda < sum(sizes)"); return MFB_EINVAL; }
+    if (device < 0 || device >= kMaxDevices) { set_error("mfb_solve_batch: device index out of range"); return MFB_EINVAL; }
     if (V == 0) return MFB_OK;
-    MFB_CUDA_TRY(cudaSetDevice(device));
+    MFB_ON_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     // sub-batches keep the scratch bounded (the general-M fast path holds a normalised copy
     // of every dictionary of the sub-batch)
-    const bool no_fast = getenv("MFB_SOLVE_EXACT") != nullptr;
+    const bool no_fast = (flags & 1) != 0;
     const bool fast = fast_supported_explicit(M, bs) && !no_fast;
     const bool fast3 = !fast && fast3_supported_explicit(M, bs) && !no_fast;
     const int shared_dict = strideA == 0;
@@ -292,7 +345,6 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     sub = std::min(sub, V);
     // workspace of the device, kept between calls (mfb_trim releases it): allocating and
     // freeing gigabytes per call costs milliseconds and synchronises the device
-    if (device < 0 || device >= kMaxDevices) { set_error("mfb_solve_batch: device index out of range"); return MFB_EINVAL; }
     SolveCache &cache = g_solve_cache[device];
     std::lock_guard<std::mutex> lock(cache.mu);
     Buf &scratch = cache.scratch, &tuple = cache.tuple, &asmall = cache.asmall, &idx5 = cache.idx5, &w5 = cache.w5,
@@ -476,9 +528,11 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             MFB_CUDA_TRY(cudaMemcpyAsync(head, redo_count, sizeof(head), cudaMemcpyDeviceToHost, st));
             MFB_CUDA_TRY(cudaStreamSynchronize(st));
             const int32_t n_redo = head[0];
+#ifdef MFB_EXPERIMENTS
             if (getenv("MFB_FAST_DEBUG") && (atoi(getenv("MFB_FAST_DEBUG")) & 8))
                 fprintf(stderr, "[mfb] %lld voxels: %d rare-path warp entries, %d competitive pairs\n",
                         (long long)cnt, head[5], head[6]);
+#endif
             pl->stats[0] += (double)(cnt - n_redo);
             pl->stats[6] += head[2];          // ill-conditioned competitor
             pl->stats[7] += head[3] + 1e-6 * head[4] ;  // near ties (+ 1e-6 * pair-independent branch)
@@ -586,7 +640,7 @@ extern "C" int mfb_fit(mfb_plan *pl, int64_t V, const double *y, const double *p
         set_error("mfb_fit: invalid argument");
         return MFB_EINVAL;
     }
-    MFB_CUDA_TRY(cudaSetDevice(pl->device));
+    MFB_ON_DEVICE(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int P = 1 + 2 * maxfasc + (csf_on ? 1 : 0) + 2 * (ear_on ? 1 : 0) + 2;
     for (int i = 0; i < 8; i++) pl->stats[i] = 0;
@@ -599,50 +653,228 @@ extern "C" int mfb_fit(mfb_plan *pl, int64_t V, const double *y, const double *p
     return MFB_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// Host pipeline of mfb_fit_host / mfb_fit_volume.  Chunks of kFitChunk voxels flow through
+//   helper thread : gather the chunk's signals (and peaks / K / csf / ear) into a page-locked slot
+//   copy stream   : one H2D of the slot into a device slot
+//   compute stream: fit_chunk
+//   d2h stream    : params rows into a page-locked slot, drained to the caller's array by the
+//                   calling thread one chunk later
+// so that the gather of chunk c + 2, the upload of chunk c + 1, the search of chunk c and the
+// download of chunk c - 1 overlap.  Slots and streams belong to the plan and are reused by
+// later calls.
+// ---------------------------------------------------------------------------------
+namespace {
+
+struct SlotLayout {
+    size_t y, peaks, K, csf, ear, total;
+    SlotLayout(int64_t C, int M, int maxfasc)
+    {
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        y = 0;
+        peaks = up(sizeof(double) * C * M);
+        K = peaks + up(sizeof(double) * C * std::max(1, 3 * maxfasc));
+        csf = K + up(sizeof(int32_t) * C);
+        ear = csf + up((size_t)C);
+        total = ear + up((size_t)C);
+    }
+};
+
+struct GatherJob {
+    int64_t V, C;
+    int M, maxfasc, dtype;
+    const void *data;
+    const int64_t *offsets;   // element offset of each voxel's first measurement, or null (v * row_stride)
+    int64_t row_stride, meas_stride;
+    const double *peaks;
+    const int32_t *K;
+    const uint8_t *csf, *ear;
+};
+
+template <typename T>
+static void gather_rows(const GatherJob &j, int64_t v0, int64_t nv, double *dst)
+{
+    const T *base = (const T *)j.data;
+    const int M = j.M;
+    for (int64_t v = 0; v < nv; v++) {
+        const T *src = base + (j.offsets ? j.offsets[v0 + v] : (v0 + v) * j.row_stride);
+        double *d = dst + v * M;
+        if (j.meas_stride == 1) {
+            if (sizeof(T) == sizeof(double)) memcpy(d, src, sizeof(double) * M);
+            else for (int m = 0; m < M; m++) d[m] = (double)src[m];
+        } else {
+            for (int m = 0; m < M; m++) d[m] = (double)src[(int64_t)m * j.meas_stride];
+        }
+    }
+}
+
+static void gather_chunk(const GatherJob &j, int64_t v0, int64_t nv, char *slot, const SlotLayout &L)
+{
+    double *y = (double *)(slot + L.y);
+    if (j.dtype == MFB_F32) gather_rows<float>(j, v0, nv, y);
+    else gather_rows<double>(j, v0, nv, y);
+    if (j.maxfasc > 0) memcpy(slot + L.peaks, j.peaks + v0 * 3 * j.maxfasc, sizeof(double) * nv * 3 * j.maxfasc);
+    memcpy(slot + L.K, j.K + v0, sizeof(int32_t) * nv);
+    if (j.csf) memcpy(slot + L.csf, j.csf + v0, nv);
+    if (j.ear) memcpy(slot + L.ear, j.ear + v0, nv);
+}
+
+struct PipeSync {
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t gathered = 0;   // chunks staged by the helper thread
+    int64_t uploaded = 0;   // chunks whose H2D copy has completed (their host slot is free again)
+    bool abort = false;
+};
+
+static void CUDART_CB slot_uploaded(void *arg)
+{
+    PipeSync *ps = (PipeSync *)arg;
+    { std::lock_guard<std::mutex> lk(ps->mu); ps->uploaded++; }
+    ps->cv.notify_all();
+}
+
+}  // namespace
+
+static const int kHostSlots = 3;
+
+static int fit_pipeline(mfb_plan *pl, const GatherJob &job, int csf_on, int ear_on, double *params_out, int flags)
+{
+    const int M = pl->dp.M, maxfasc = job.maxfasc;
+    const int P = 1 + 2 * maxfasc + (csf_on ? 1 : 0) + 2 * (ear_on ? 1 : 0) + 2;
+    const int64_t V = job.V, C = job.C;
+    const int64_t nchunks = (V + C - 1) / C;
+    for (int i = 0; i < 8; i++) pl->stats[i] = 0;
+    if (V == 0) return MFB_OK;
+    const SlotLayout L(C, M, maxfasc);
+    for (int i = 0; i < kHostSlots; i++) MFB_TRY(pl->h_in[i].ensure(L.total));
+    for (int i = 0; i < 2; i++) {
+        MFB_TRY(pl->d_in[i].ensure(L.total));
+        MFB_TRY(pl->d_out[i].ensure(sizeof(double) * C * P));
+        MFB_TRY(pl->h_out[i].ensure(sizeof(double) * C * P));
+    }
+    if (!pl->s_copy) {
+        MFB_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+        MFB_CUDA_TRY(cudaStreamCreateWithFlags(&pl->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 6; i++) MFB_CUDA_TRY(cudaEventCreateWithFlags(&pl->pipe_ev[i], cudaEventDisableTiming));
+    }
+    cudaEvent_t *ev_h2d = pl->pipe_ev, *ev_done = pl->pipe_ev + 2, *ev_d2h = pl->pipe_ev + 4;
+    cudaStream_t st = pl->stream;
+
+    PipeSync ps;
+    std::thread helper([&]() {
+        for (int64_t c = 0; c < nchunks; c++) {
+            {
+                std::unique_lock<std::mutex> lk(ps.mu);
+                ps.cv.wait(lk, [&] { return ps.abort || c < ps.uploaded + kHostSlots; });
+                if (ps.abort) return;
+            }
+            const int64_t v0 = c * C, nv = std::min(C, V - v0);
+            gather_chunk(job, v0, nv, (char *)pl->h_in[c % kHostSlots].p, L);
+            { std::lock_guard<std::mutex> lk(ps.mu); ps.gathered = c + 1; }
+            ps.cv.notify_all();
+        }
+    });
+
+    auto upload = [&](int64_t c) -> int {
+        {
+            // the helper waits for free slots, which only upload completions release: a failed
+            // device would otherwise leave both threads waiting on each other
+            std::unique_lock<std::mutex> lk(ps.mu);
+            while (!ps.cv.wait_for(lk, std::chrono::milliseconds(200), [&] { return ps.gathered > c; })) {
+                lk.unlock();
+                cudaError_t q = cudaStreamQuery(pl->s_copy);
+                if (q != cudaSuccess && q != cudaErrorNotReady) {
+                    set_error(std::string("mfb_fit_host: upload stream: ") + cudaGetErrorString(q));
+                    return MFB_ECUDA;
+                }
+                lk.lock();
+            }
+        }
+        const int d = (int)(c & 1);
+        // the device slot was last read by the search of chunk c - 2
+        if (c >= 2) MFB_CUDA_TRY(cudaStreamWaitEvent(pl->s_copy, ev_done[d], 0));
+        const int64_t nv = std::min(C, V - c * C);
+        // one copy up to the end of the last array in use
+        const size_t bytes = job.ear ? L.ear + nv : (job.csf ? L.csf + nv : L.K + sizeof(int32_t) * nv);
+        MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_in[d].p, pl->h_in[c % kHostSlots].p, bytes, cudaMemcpyHostToDevice, pl->s_copy));
+        MFB_CUDA_TRY(cudaEventRecord(ev_h2d[d], pl->s_copy));
+        MFB_CUDA_TRY(cudaLaunchHostFunc(pl->s_copy, slot_uploaded, &ps));
+        return MFB_OK;
+    };
+    auto drain = [&](int64_t c) -> int {
+        const int d = (int)(c & 1);
+        MFB_CUDA_TRY(cudaEventSynchronize(ev_d2h[d]));
+        const int64_t nv = std::min(C, V - c * C);
+        memcpy(params_out + c * C * P, pl->h_out[d].p, sizeof(double) * nv * P);
+        return MFB_OK;
+    };
+    auto body = [&]() -> int {
+        MFB_TRY(upload(0));
+        for (int64_t c = 0; c < nchunks; c++) {
+            if (c + 1 < nchunks) MFB_TRY(upload(c + 1));
+            const int d = (int)(c & 1);
+            const int64_t nv = std::min(C, V - c * C);
+            MFB_CUDA_TRY(cudaStreamWaitEvent(st, ev_h2d[d], 0));
+            if (c >= 2) MFB_CUDA_TRY(cudaStreamWaitEvent(st, ev_d2h[d], 0));   // its params slot has been downloaded
+            char *din = (char *)pl->d_in[d].p;
+            MFB_TRY(fit_chunk(pl, nv, (const double *)(din + L.y), (const double *)(din + L.peaks),
+                              (const int32_t *)(din + L.K), job.csf ? (const uint8_t *)(din + L.csf) : nullptr,
+                              job.ear ? (const uint8_t *)(din + L.ear) : nullptr, maxfasc, csf_on ? 1 : 0,
+                              ear_on ? 1 : 0, pl->d_out[d].as<double>(), flags, st));
+            MFB_CUDA_TRY(cudaEventRecord(ev_done[d], st));
+            MFB_CUDA_TRY(cudaStreamWaitEvent(pl->s_d2h, ev_done[d], 0));
+            MFB_CUDA_TRY(cudaMemcpyAsync(pl->h_out[d].p, pl->d_out[d].p, sizeof(double) * nv * P,
+                                         cudaMemcpyDeviceToHost, pl->s_d2h));
+            MFB_CUDA_TRY(cudaEventRecord(ev_d2h[d], pl->s_d2h));
+            if (c >= 1) MFB_TRY(drain(c - 1));
+        }
+        MFB_TRY(drain(nchunks - 1));
+        return MFB_OK;
+    };
+    int rc = body();
+    if (rc != MFB_OK) {
+        { std::lock_guard<std::mutex> lk(ps.mu); ps.abort = true; }
+        ps.cv.notify_all();
+    }
+    helper.join();
+    // nothing of this call may still be in flight when the slots are reused or PipeSync dies
+    cudaError_t e1 = cudaStreamSynchronize(pl->s_copy), e2 = cudaStreamSynchronize(st),
+                e3 = cudaStreamSynchronize(pl->s_d2h);
+    if (rc == MFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+        set_error(std::string("mfb_fit_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        rc = MFB_ECUDA;
+    }
+    return rc;
+}
+
+extern "C" int mfb_fit_volume(mfb_plan *pl, int64_t V, const void *data, int dtype,
+                              const int64_t *voxel_offset, int64_t row_stride, int64_t meas_stride,
+                              const double *peaks, const int32_t *K, const uint8_t *csf,
+                              const uint8_t *ear, int maxfasc, int csf_on, int ear_on,
+                              double *params_out, int flags)
+{
+    if (!pl || V < 0 || maxfasc < 0 || maxfasc > 2 || (V > 0 && (!data || !K || !params_out)) ||
+        (maxfasc > 0 && V > 0 && !peaks) || (dtype != MFB_F64 && dtype != MFB_F32)) {
+        set_error("mfb_fit_volume: invalid argument");
+        return MFB_EINVAL;
+    }
+    MFB_ON_DEVICE(pl->device);
+    GatherJob job;
+    job.V = V; job.C = std::min<int64_t>(kFitChunk, std::max<int64_t>(V, 1));
+    job.M = pl->dp.M; job.maxfasc = maxfasc; job.dtype = dtype;
+    job.data = data; job.offsets = voxel_offset; job.row_stride = row_stride; job.meas_stride = meas_stride;
+    job.peaks = peaks; job.K = K; job.csf = csf; job.ear = ear;
+    return fit_pipeline(pl, job, csf_on, ear_on, params_out, flags);
+}
+
 extern "C" int mfb_fit_host(mfb_plan *pl, int64_t V, const double *y, const double *peaks,
                             const int32_t *K, const uint8_t *csf, const uint8_t *ear, int maxfasc,
                             int csf_on, int ear_on, double *params_out, int flags)
 {
-    if (!pl || V < 0 || maxfasc < 0 || maxfasc > 2 || (V > 0 && (!y || !K || !params_out)) ||
-        (maxfasc > 0 && V > 0 && !peaks)) {
-        set_error("mfb_fit_host: invalid argument");
-        return MFB_EINVAL;
-    }
-    MFB_CUDA_TRY(cudaSetDevice(pl->device));
-    cudaStream_t st = pl->stream;
-    const int M = pl->dp.M;
-    const int P = 1 + 2 * maxfasc + (csf_on ? 1 : 0) + 2 * (ear_on ? 1 : 0) + 2;
-    const int64_t chunk = 4 * kFitChunk;
-    const int64_t nmax = std::min(chunk, std::max<int64_t>(V, 1));
-    MFB_TRY(pl->d_y.ensure(sizeof(double) * nmax * M));
-    MFB_TRY(pl->d_peaks.ensure(sizeof(double) * nmax * std::max(1, 3 * maxfasc)));
-    MFB_TRY(pl->d_K.ensure(sizeof(int32_t) * nmax));
-    MFB_TRY(pl->d_csf.ensure(nmax));
-    MFB_TRY(pl->d_ear.ensure(nmax));
-    MFB_TRY(pl->d_params.ensure(sizeof(double) * nmax * P));
-    for (int i = 0; i < 8; i++) pl->stats[i] = 0;
-    for (int64_t v0 = 0; v0 < V; v0 += chunk) {
-        const int64_t nv = std::min(chunk, V - v0);
-        MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_y.p, y + v0 * M, sizeof(double) * nv * M, cudaMemcpyHostToDevice, st));
-        if (maxfasc > 0)
-            MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_peaks.p, peaks + v0 * 3 * maxfasc,
-                                         sizeof(double) * nv * 3 * maxfasc, cudaMemcpyHostToDevice, st));
-        MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_K.p, K + v0, sizeof(int32_t) * nv, cudaMemcpyHostToDevice, st));
-        if (csf) MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_csf.p, csf + v0, nv, cudaMemcpyHostToDevice, st));
-        if (ear) MFB_CUDA_TRY(cudaMemcpyAsync(pl->d_ear.p, ear + v0, nv, cudaMemcpyHostToDevice, st));
-        for (int64_t c0 = 0; c0 < nv; c0 += kFitChunk) {
-            const int64_t nc = std::min(kFitChunk, nv - c0);
-            MFB_TRY(fit_chunk(pl, nc, pl->d_y.as<double>() + c0 * M,
-                              pl->d_peaks.as<double>() + c0 * 3 * maxfasc, pl->d_K.as<int32_t>() + c0,
-                              csf ? pl->d_csf.as<uint8_t>() + c0 : nullptr,
-                              ear ? pl->d_ear.as<uint8_t>() + c0 : nullptr, maxfasc, csf_on ? 1 : 0,
-                              ear_on ? 1 : 0, pl->d_params.as<double>() + c0 * P, flags, st));
-        }
-        MFB_CUDA_TRY(cudaMemcpyAsync(params_out + v0 * P, pl->d_params.p, sizeof(double) * nv * P,
-                                     cudaMemcpyDeviceToHost, st));
-        MFB_CUDA_TRY(cudaStreamSynchronize(st));
-    }
-    return MFB_OK;
+    if (!pl) { set_error("mfb_fit_host: invalid argument"); return MFB_EINVAL; }
+    return mfb_fit_volume(pl, V, y, MFB_F64, nullptr, pl->dp.M, 1, peaks, K, csf, ear, maxfasc, csf_on,
+                          ear_on, params_out, flags);
 }
 
 extern "C" int mfb_fit_stats(mfb_plan *pl, double *out, int n)

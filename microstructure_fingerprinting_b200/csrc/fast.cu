@@ -53,6 +53,13 @@ namespace mfb {
 // A competitive pair / tuple whose (refined) error bound exceeds kIllTol * c0 is tracked as
 // ill-conditioned: it can win only through the exact tier.
 static constexpr double kIllTol = 64.0;
+// Experiment switches (timing ablations; some produce invalid results) exist only in builds
+// with -DMFB_EXPERIMENTS; the default library has no environment-dependent behaviour.
+#ifdef MFB_EXPERIMENTS
+#define FT_DEBUG(a, bit) (((a).debug & (bit)) != 0)
+#else
+#define FT_DEBUG(a, bit) false
+#endif
 // The screening threshold starts kPreMargin * c0 below the best solution with fewer active
 // columns (single atom, atom + CSF): a voxel without any competitive pair is then certified to
 // be won by such a solution with that margin, and its reference-order search can be
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         for (int jt = 0; jt < ntJ; jt++) {
             const int st = jt % FT_NS;
             if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
-            if ((a.debug & 2) && jt >= FT_NS) { mbar_arrive(&s_full[st]); continue; }
+            if (FT_DEBUG(a, 2) && jt >= FT_NS) { mbar_arrive(&s_full[st]); continue; }
             const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
             if (pt == 0) atomicMax(&s_thr, *(volatile unsigned long long *)vthr);
             const int j = jr * FT_TJ + jj;
@@ -653,7 +660,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         mbar_arrive(&s_empty[st]);
         const double *cq = colq + (jt % FT_CQ) * 5 * FT_TJ;
         unsigned hit = 0;
-        if (a.debug & 1) {
+        if (FT_DEBUG(a, 1)) {
             double sacc = 0.0;
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
@@ -728,7 +735,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         }
         // ---- rare: some lane of the warp has a competitive pair ----
         if (__any_sync(0xffffffffu, hit != 0)) {
-            if (a.debug & 8) {   // experiment: count rare-path entries (warps) and competitive pairs
+            if (FT_DEBUG(a, 8)) {   // experiment: count rare-path entries (warps) and competitive pairs
                 if (lane == 0) atomicAdd(&a.reasons[4], 1);
                 if (hit) atomicAdd(&a.reasons[5], __popc(hit));
             }
@@ -756,7 +763,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                     const double rdet = 1.0 / det;
                     double gq = num * rdet, tq = c0 * rdet;
                     if (!(gq + tq >= thr)) continue;
-                    if (!(a.debug & 4)) refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
+                    if (!FT_DEBUG(a, 4)) refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
                     if (tq > kIllTol * c0) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
                     if (gq > gb) {
                         flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
@@ -1121,7 +1128,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
                     const double rdet = 1.0 / det;
                     double gq = num * rdet, tq = c0 * rdet;
                     if (!(gq + tq >= thr)) continue;
-                    if (!(a.debug & 4)) refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
+                    if (!FT_DEBUG(a, 4)) refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
                     if (tq > kIllTol * c0) gill = fmax(gill, gq + tq);
                     if (gq > gb) {
                         flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
@@ -1624,7 +1631,10 @@ static FastGeom fast_geom(int M, int N1, int N2)
 {
     FastGeom g;
     g.Mp = (M + 3) & ~3;
-    g.gemm = g.Mp > 112 || getenv("MFB_FORCE_GEMM") != nullptr;   // env: experiment only
+    g.gemm = g.Mp > 112;
+#ifdef MFB_EXPERIMENTS
+    if (getenv("MFB_FORCE_GEMM")) g.gemm = true;
+#endif
     const int Nmax = N1 > N2 ? N1 : N2;
     const int padto = g.gemm ? GP_TI : FT_TJ;
     g.Npad = (Nmax + padto - 1) / padto * padto;
@@ -1691,10 +1701,10 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     a.dnoff[0] = 0; a.dnoff[1] = g.N1pad;
     const bool shared_dict = fp.src && fp.strideA == 0;
     a.dn_stride = shared_dict ? 0 : (int64_t)g.Mp2 * g.ldn;
-    {
-        const char *d = getenv("MFB_FAST_DEBUG");
-        a.debug = d ? atoi(d) : 0;
-    }
+    a.debug = 0;
+#ifdef MFB_EXPERIMENTS
+    if (const char *d = getenv("MFB_FAST_DEBUG")) a.debug = atoi(d);
+#endif
     a.vox_list = vox_list; a.peaks = peaks; a.peaks_ld = peaks_ld; a.y = y;
     char *q = (char *)scratch;
     if (!fp.src) {

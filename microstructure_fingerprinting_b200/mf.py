@@ -7,6 +7,7 @@ same ROI ordering (np.where(mask > 0)), same params-row layout, same exception t
 `parallel=True` keeps its keyword and now means "shard the ROI over all visible GPUs"
 (contiguous chunks, no collective) instead of a multiprocessing.Pool.
 """
+import contextlib
 import os
 import threading
 import time
@@ -90,10 +91,40 @@ class MFModel():
                              " Matlab-like mat file or a Python dictionary.")
         self.ms_interpolator = mfu.init_PGSE_multishell_interp(
             self.dic['dictionary'], self.dic['sch_mat'], self.dic['orientation'])
+        self._plans = {}                      # (shard, device) -> {'lock', 'key', 'plan'}
+        self._plans_lock = threading.Lock()
         print("Initiated model based on dictionary with %d single-fascicle"
               " fingerprint(s) and %d fingerprint(s) for the extra-axonal"
               " restricted (EAR) compartment." %
               (self.dic['num_atom'], self.dic['num_ear']))
+
+    # ------------------------------------------------------------------
+    @contextlib.contextmanager
+    def _plan(self, slot, dev, key, scheme_plan, sig_csf, sig_ear):
+        """The mfb_plan of shard `slot` on device `dev` for this protocol / CSF / EAR columns,
+        kept between fit() calls (lookup table, workspace and page-locked staging slots stay
+        allocated); one fit at a time per plan."""
+        with self._plans_lock:
+            entry = self._plans.get((slot, dev))
+            if entry is None:
+                entry = self._plans[(slot, dev)] = {'lock': threading.Lock(), 'key': None, 'plan': None}
+        with entry['lock']:
+            if entry['key'] != key:
+                if entry['plan'] is not None:
+                    entry['plan'].close()
+                    entry['plan'] = None
+                entry['plan'] = mfu.GpuPlan(self.ms_interpolator, scheme_plan, sig_csf, sig_ear, device=dev)
+                entry['key'] = key
+            yield entry['plan']
+
+    def close(self):
+        """Release the GPU plans (device memory, page-locked staging) this model holds."""
+        with self._plans_lock:
+            for entry in self._plans.values():
+                with entry['lock']:
+                    if entry['plan'] is not None:
+                        entry['plan'].close()
+                        entry['plan'], entry['key'] = None, None
 
     # ------------------------------------------------------------------
     def _peaks_in_roi(self, peaks, colat_longit, tensors, img_shape, in_mask, ROI_size,
@@ -180,7 +211,7 @@ class MFModel():
 
         img_shape = mask_arr.shape
         in_mask = mask_arr > 0
-        ROI_size = int(np.sum(in_mask))
+        ROI_size = int(np.count_nonzero(in_mask))
         if ROI_size == 0:
             raise ValueError("No voxel detected in mask. Please provide "
                              "a non-empty mask.")
@@ -221,15 +252,20 @@ class MFModel():
         # hoisted in front of the launch)
         for i in range(maxfasc):
             present = numfasc_roi >= i + 1
-            pk = peaks_roi[present, 3 * i:3 * i + 3]
-            num_0 = np.sum(np.sum(np.abs(pk), axis=1) == 0)
+            pk = peaks_roi[:, 3 * i:3 * i + 3]
+            if not present.all():
+                pk = pk[present]
+            sq = np.einsum('ij,ij->i', pk, pk)
+            num_0 = int(np.count_nonzero(sq == 0))
+            if num_0 > 0:
+                num_0 = int(np.sum(np.sum(np.abs(pk), axis=1) == 0))
             if num_0 > 0:
                 raise ValueError("Detected %d voxel(s) in which the main "
                                  "orientation of axon population %d/%d was "
                                  "a zero vector, although numfasc "
                                  "specifies the presence of that "
                                  "population." % (num_0, i + 1, maxfasc))
-            nrm = np.sqrt(np.sum(pk ** 2, axis=1))
+            nrm = np.sqrt(sq)
             bad = np.abs(1 - nrm) > 1e-3
             if np.any(bad):
                 raise ValueError("Orientation vector of the new signal must have unit norm."
@@ -266,7 +302,9 @@ class MFModel():
         csf_on = bool(np.any(csf_roi))
         ear_on = bool(np.any(ear_roi))
 
-        n_empty = np.sum((numfasc_roi + csf_roi + ear_roi) == 0)
+        n_empty = 0
+        if VRB >= 2:
+            n_empty = np.sum((numfasc_roi + csf_roi + ear_roi) == 0)
         if n_empty > 0 and VRB >= 2:
             print("WARNING: detected %d voxel(s) in mask with zero "
                   " axon population, no cerebrospinal fluid (CSF) and no"
@@ -293,59 +331,52 @@ class MFModel():
         if devices is None:
             devices = list(range(torch.cuda.device_count())) if parallel else [0]
         devices = list(devices)[:max(1, min(len(devices), ROI_size))]
-        # the ROI signals are gathered chunk by chunk (a worker thread prepares the next chunk
-        # while the GPU fits the current one) instead of one (ROI_size, M) fancy-indexing copy
-        data_2d = data_arr.reshape(-1, data_arr.shape[-1])
-        roi_idx = np.flatnonzero(in_mask.ravel())
+        # The ROI signals are never copied on the Python side (the reference's
+        # data_arr[mask > 0], mf.py:644): every voxel is described by the element offset of
+        # its first measurement in the caller's volume and libmfb200 gathers chunk by chunk
+        # in a helper thread while the GPU fits the previous chunks (mfb_fit_volume).
+        if data_arr.dtype not in (np.float64, np.float32) or not data_arr.dtype.isnative:
+            data_arr = data_arr.astype(np.float64)
+        item = data_arr.itemsize
+        if any(st % item for st in data_arr.strides):
+            data_arr = np.ascontiguousarray(data_arr)
+        meas_stride = data_arr.strides[-1] // item
+        if data_arr.flags.c_contiguous and ROI_size == in_mask.size:
+            vox_off = np.arange(0, ROI_size * num_seq, num_seq, dtype=np.int64)
+        elif data_arr.flags.c_contiguous:
+            vox_off = np.flatnonzero(in_mask.ravel()).astype(np.int64) * num_seq
+        else:
+            vox_off = np.zeros(ROI_size, dtype=np.int64)
+            for d, c in enumerate(np.nonzero(in_mask)):
+                vox_off += c.astype(np.int64) * (data_arr.strides[d] // item)
         K32 = numfasc_roi.astype(np.int32)
-        csf_u8 = csf_roi.astype(np.uint8)
-        ear_u8 = ear_roi.astype(np.uint8)
+        csf_u8 = csf_roi.view(np.uint8) if csf_on else None
+        ear_u8 = ear_roi.view(np.uint8) if ear_on else None
         peaks_c = np.ascontiguousarray(peaks_roi[:, :3 * maxfasc], dtype=np.float64)
         num_params = 1 + maxfasc * 2 + csf_on * 1 + ear_on * 2 + 2
-        params_in_mask = np.zeros((ROI_size, num_params))
+        params_in_mask = np.empty((ROI_size, num_params))
         st_est = time.time()
         if VRB >= 2:
             print("Starting estimation in %d voxel(s) on %d GPU(s)." % (ROI_size, len(devices)))
-        bounds = shard_bounds(ROI_size, len(devices),
-                              voxel_cost(numfasc_roi, csf_roi, ear_roi, self.dic['num_atom'], self.dic.get('num_ear', 1)))
+        cost = None
+        if len(devices) > 1:
+            cost = voxel_cost(numfasc_roi, csf_roi, ear_roi, self.dic['num_atom'], self.dic.get('num_ear', 1))
+        bounds = shard_bounds(ROI_size, len(devices), cost)
         errors = []
-        host_chunk = 1 << 17
-
-        def gather(lo, hi):
-            return np.ascontiguousarray(data_2d[roi_idx[lo:hi]], dtype=np.float64)
+        plan_key = (pgse_scheme.tobytes(), None if sig_csf is None else sig_csf.tobytes(),
+                    None if sig_ear is None else sig_ear.tobytes())
 
         def work(rank, dev):
             lo, hi = int(bounds[rank]), int(bounds[rank + 1])
             if hi <= lo:
                 return
             try:
-                plan = mfu.GpuPlan(self.ms_interpolator, scheme_plan, sig_csf, sig_ear, device=dev)
-                try:
-                    cuts = list(range(lo, hi, host_chunk)) + [hi]
-                    nxt = {}
-
-                    def prefetch(c):
-                        try:
-                            nxt[c] = gather(cuts[c], cuts[c + 1])
-                        except BaseException as exc:
-                            nxt[c] = exc
-                    prefetch(0)
-                    for c in range(len(cuts) - 1):
-                        y_c = nxt.pop(c)
-                        if isinstance(y_c, BaseException):
-                            raise y_c
-                        th = None
-                        if c + 2 < len(cuts):
-                            th = threading.Thread(target=prefetch, args=(c + 1,))
-                            th.start()
-                        a, b_ = cuts[c], cuts[c + 1]
-                        params_in_mask[a:b_] = plan.fit_host(
-                            y_c, peaks_c[a:b_], K32[a:b_], csf_u8[a:b_], ear_u8[a:b_],
-                            maxfasc, csf_on, ear_on, flags=1 if exact else 0)
-                        if th is not None:
-                            th.join()
-                finally:
-                    plan.close()
+                with self._plan(rank, dev, plan_key, scheme_plan, sig_csf, sig_ear) as plan:
+                    plan.fit_volume(data_arr, vox_off[lo:hi], meas_stride, peaks_c[lo:hi], K32[lo:hi],
+                                    None if csf_u8 is None else csf_u8[lo:hi],
+                                    None if ear_u8 is None else ear_u8[lo:hi],
+                                    maxfasc, csf_on, ear_on, params_in_mask[lo:hi],
+                                    flags=1 if exact else 0)
             except BaseException as exc:  # re-raised in the caller's thread
                 errors.append(exc)
 
@@ -385,39 +416,76 @@ class MFModelFit():
         mask = fitinfo['mask']
         in_mask = mask > 0
         ROI_size = model_params.shape[0]
-        assert ROI_size == np.sum(in_mask), 'Inconsistent mask and model parameter array'
-        names = []
+        assert ROI_size == np.count_nonzero(in_mask), 'Inconsistent mask and model parameter array'
+        # ROI rows -> volumes.  Every map is described by a function of a span of params rows;
+        # spans are filled by a few threads (NumPy releases the GIL in the copies, gathers and
+        # products involved), each writing its own part of every volume.  A full mask needs no
+        # scatter index at all.
+        full = ROI_size == in_mask.size
+        roi_flat = None if full else np.flatnonzero(in_mask.ravel())
+        peaks_roi = fitinfo['peaks_roi']
+        specs = []   # (name, trailing shape, f(rows, lo, hi) -> values of the span)
 
-        def put(name, values, trailing=()):
-            vol = np.zeros(mask.shape + trailing)
-            vol[in_mask] = values
-            setattr(self, name, vol)
-            names.append(name)
+        def col(c):
+            return lambda rows, lo, hi: rows[:, c]
 
-        put('M0', model_params[:, 0])
+        def prop_of(values, k):
+            def f(rows, lo, hi):   # zero where the fascicle got no weight
+                return values[rows[:, 1 + numfasc + k].astype(np.intp)] * (rows[:, k + 1] > 0)
+            return f
+
+        def total_of(values):
+            def f(rows, lo, hi):
+                tot = np.zeros(hi - lo)
+                for k in range(numfasc):
+                    tot += rows[:, k + 1] * prop_of(values, k)(rows, lo, hi)
+                return tot
+            return f
+
+        specs.append(('M0', (), col(0)))
         for k in range(numfasc):
-            put('frac_f%d' % k, model_params[:, k + 1])
-            put('peak_f%d' % k, fitinfo['peaks_roi'][:, 3 * k:3 * (k + 1)], (3,))
+            specs.append(('frac_f%d' % k, (), col(k + 1)))
+            specs.append(('peak_f%d' % k, (3,), lambda rows, lo, hi, k=k: peaks_roi[lo:hi, 3 * k:3 * (k + 1)]))
         # fascicle-specific properties and their fraction-weighted voxel totals
         for prop in fitinfo['fasc_propnames']:
             values = np.asarray(fitinfo['_dict_' + prop])
-            total = np.zeros(ROI_size)
             for k in range(numfasc):
-                nu_k = model_params[:, k + 1]
-                ID_k = model_params[:, 1 + numfasc + k].astype(int)
-                prop_k = values[ID_k] * (nu_k > 0)  # zero where the fascicle got no weight
-                total += nu_k * prop_k
-                put(prop + '_f%d' % k, prop_k)
-            put(prop + '_tot', total)
+                specs.append((prop + '_f%d' % k, (), prop_of(values, k)))
+            specs.append((prop + '_tot', (), total_of(values)))
         if csf_on:
-            put('frac_csf', model_params[:, 2 * numfasc + 1])
+            specs.append(('frac_csf', (), col(2 * numfasc + 1)))
         if ear_on:
-            nu_ear = model_params[:, 2 * numfasc + csf_on + 1]
-            put('frac_ear', nu_ear)
-            ID_ear = model_params[:, 2 * numfasc + csf_on + 2].astype(int)
-            put('D_ear', fitinfo['DIFF_ear'][ID_ear] * (nu_ear > 0))
-        put('MSE', model_params[:, -2])
-        put('R2', model_params[:, -1])
+            c_ear = 2 * numfasc + csf_on + 1
+            DIFF_ear = fitinfo['DIFF_ear']
+            specs.append(('frac_ear', (), col(c_ear)))
+            specs.append(('D_ear', (), lambda rows, lo, hi: DIFF_ear[rows[:, c_ear + 1].astype(np.intp)]
+                          * (rows[:, c_ear] > 0)))
+        specs.append(('MSE', (), col(model_params.shape[1] - 2)))
+        specs.append(('R2', (), col(model_params.shape[1] - 1)))
+
+        alloc = np.empty if full else np.zeros
+        flat = {}
+        for name, trailing, _ in specs:
+            vol = alloc(mask.shape + trailing)
+            setattr(self, name, vol)
+            flat[name] = vol.reshape((-1,) + trailing)
+
+        def fill(lo, hi):
+            rows = model_params[lo:hi]
+            where = slice(lo, hi) if full else roi_flat[lo:hi]
+            for name, _, f in specs:
+                flat[name][where] = f(rows, lo, hi)
+
+        span = 1 << 16
+        cuts = list(range(0, ROI_size, span)) + [ROI_size]
+        n_thr = min(8, os.cpu_count() or 1, len(cuts) - 1)
+        if n_thr <= 1:
+            fill(0, ROI_size)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(n_thr) as ex:
+                list(ex.map(lambda i: fill(cuts[i], cuts[i + 1]), range(len(cuts) - 1)))
+        names = [name for name, _, _ in specs]
         self.param_names = names
         if verbose >= 2:
             print("Microstructure Fingerprinting fit object constructed. "

@@ -387,6 +387,28 @@ class GpuPlan(object):
         _lib.check(rc, "mfb_fit_host")
         return out
 
+    def fit_volume(self, data, voxel_offset, meas_stride, peaks, K, csf, ear, maxfasc, csf_on,
+                   ear_on, out, flags=0):
+        """ROI voxels scattered in the host volume `data` (float64 / float32, any strides):
+        voxel v's signal starts at element voxel_offset[v] of data's buffer, measurements are
+        meas_stride elements apart.  The library gathers, uploads, fits and writes the params
+        rows into out (V, P) (mfb_fit_volume); nothing is copied on the Python side."""
+        V = int(voxel_offset.shape[0])
+        P = 1 + 2 * maxfasc + int(csf_on) + 2 * int(ear_on) + 2
+        assert out.shape == (V, P) and out.dtype == np.float64 and out.flags.c_contiguous
+        assert voxel_offset.dtype == np.int64 and voxel_offset.flags.c_contiguous
+        dtype = {np.dtype(np.float64): _lib.MFB_F64, np.dtype(np.float32): _lib.MFB_F32}[data.dtype]
+        K = np.ascontiguousarray(K, dtype=np.int32)
+        peaks = None if maxfasc == 0 else np.ascontiguousarray(peaks, dtype=np.float64)
+        csf = None if csf is None else np.ascontiguousarray(csf, dtype=np.uint8)
+        ear = None if ear is None else np.ascontiguousarray(ear, dtype=np.uint8)
+        rc = _lib.load().mfb_fit_volume(self.handle, V, ctypes.c_void_p(data.ctypes.data), dtype,
+                                        _ptr(voxel_offset), 0, int(meas_stride), _ptr(peaks), _ptr(K),
+                                        _ptr(csf), _ptr(ear), int(maxfasc), int(csf_on), int(ear_on),
+                                        _ptr(out), int(flags))
+        _lib.check(rc, "mfb_fit_volume")
+        return out
+
     def fit_device(self, y, peaks, K, csf, ear, maxfasc, csf_on, ear_on, flags=0, out=None):
         """torch.cuda tensors in / out (mfb_fit); inputs must live on this plan's GPU."""
         torch = _lib.require_cuda()
@@ -466,10 +488,11 @@ def interp_PGSE_from_multishell(sch_mat, newdir, sig_ms=None, sch_mat_ms=None, o
 # exhaustive combinatorial NNLS
 # ----------------------------------------------------------------------------------
 
-def solve_exhaustive_posweights_batch(A, Y, dicsizes, device=0, return_device=False):
+def solve_exhaustive_posweights_batch(A, Y, dicsizes, device=0, return_device=False, exact=False):
     """Batched form of solve_exhaustive_posweights: Y is (V, M); A is (M, Ntot) (shared by
     all voxels) or (V, M, Ntot).  Returns (w (V,K), ind_subdic (V,K), ind_totdic (V,K),
-    min_obj (V,), y_recons (V,M))."""
+    min_obj (V,), y_recons (V,M)).  `exact=True` forces the reference-order tier for every
+    voxel (verification; the results are the same by construction)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = torch.device('cuda', device)
@@ -497,7 +520,7 @@ def solve_exhaustive_posweights_batch(A, Y, dicsizes, device=0, return_device=Fa
     with torch.cuda.device(dev):
         rc = lib.mfb_solve_batch(device, V, M, nb, _ptr(sizes), dA.data_ptr(), ntot, strideA,
                                  dY.data_ptr(), w.data_ptr(), sub.data_ptr(), obj.data_ptr(),
-                                 yrec.data_ptr(), st)
+                                 yrec.data_ptr(), 1 if exact else 0, st)
     _lib.check(rc, "mfb_solve_batch")
     starts = torch.from_numpy(np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)).to(dev)
     tot = sub + starts[None, :]

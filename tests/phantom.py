@@ -78,12 +78,23 @@ def _rotate_shell(shells, s, xv, atoms):
     return w_hi * ys[j, a] + w_lo * ys[j - 1, a]
 
 
-def rotate_columns(dic, sch, dirs, atoms):
+def rotate_columns(dic, sch, dirs, atoms, table=None):
     """Signals of atom `atoms[v]` rotated to `dirs[v]` for every voxel: (V, M).  Gradient
     strengths between two dense shells are blended linearly in G (reference
-    mf_utils.py:1921-1956)."""
-    Gun, shells = host_table(dic)
+    mf_utils.py:1921-1956).  Large batches are split over threads by voxel blocks (the
+    result does not depend on the split)."""
+    Gun, shells = table if table is not None else host_table(dic)
     V, M = dirs.shape[0], sch.shape[0]
+    blk = 1 << 15
+    if V > 2 * blk:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        cuts = list(range(0, V, blk)) + [V]
+        with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+            parts = list(ex.map(lambda i: rotate_columns(dic, sch, dirs[cuts[i]:cuts[i + 1]],
+                                                         atoms[cuts[i]:cuts[i + 1]], (Gun, shells)),
+                                range(len(cuts) - 1)))
+        return np.concatenate(parts, axis=0)
     out = np.zeros((V, M))
     x = np.abs(dirs @ sch[:, :3].T)                  # (V, M)
     for G in np.unique(sch[:, 3]):

@@ -19,7 +19,8 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mfb_version() == 2
+    m = re.search(r"#define MFB_ABI_VERSION (\d+)", hdr)
+    assert lib.mfb_version() == int(m.group(1)) == _lib.MFB_ABI_VERSION
     assert lib.mfb_launch_count() >= 0
 
 
@@ -173,3 +174,57 @@ def test_rotate_atom_plan_matches_reference_goldens():
                                                   np.array([[float(g["hcp_DIFF"])]]), S0, warnings=False)
     got = orc.lerp_rows(table, rl, rh, wl, wh)
     assert np.allclose(got, g["hcp_rot"], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("full", [True, False])
+@pytest.mark.parametrize("csf_on,ear_on", [(False, False), (True, False), (True, True)])
+def test_mfmodelfit_maps_match_per_property_restatement(full, csf_on, ear_on):
+    """MFModelFit builds its maps span by span in threads; compare every map with a plain
+    per-property restatement of reference mf.py:1055-1175 on a (partial or full) 3-D mask."""
+    from microstructure_fingerprinting_b200.mf import MFModelFit
+    rng = np.random.default_rng(5)
+    shape = (37, 41, 53)
+    mask = np.ones(shape) if full else (rng.random(shape) < 0.6).astype(float)
+    in_mask = mask > 0
+    V, nf, N, E = int(in_mask.sum()), 2, 50, 4
+    P = 1 + 2 * nf + csf_on + 2 * ear_on + 2
+    rows = rng.random((V, P))
+    rows[:, 1:1 + nf] *= rng.random((V, nf)) < 0.8            # some zero fractions
+    rows[:, 1 + nf:1 + 2 * nf] = rng.integers(0, N, (V, nf))
+    if ear_on:
+        rows[:, 2 * nf + csf_on + 2] = rng.integers(0, E, V)
+        rows[:, 2 * nf + csf_on + 1] *= rng.random(V) < 0.5
+    peaks = rng.standard_normal((V, 3 * nf))
+    info = {'maxfasc': nf, 'csf_on': csf_on, 'ear_on': ear_on, 'affine': np.eye(4), 'mask': mask,
+            'fasc_propnames': ['fvf', 'rad'], 'peaks_roi': peaks, '_dict_fvf': rng.random(N),
+            '_dict_rad': rng.random(N), 'DIFF_ear': rng.random(E)}
+    fit = MFModelFit(info, rows)
+
+    def vol(values, trailing=()):
+        out = np.zeros(shape + trailing)
+        out[in_mask] = values
+        return out
+    expect = {'M0': vol(rows[:, 0]), 'MSE': vol(rows[:, -2]), 'R2': vol(rows[:, -1])}
+    for k in range(nf):
+        expect['frac_f%d' % k] = vol(rows[:, k + 1])
+        expect['peak_f%d' % k] = vol(peaks[:, 3 * k:3 * k + 3], (3,))
+    for prop in ('fvf', 'rad'):
+        tot = np.zeros(V)
+        for k in range(nf):
+            pk = info['_dict_' + prop][rows[:, 1 + nf + k].astype(int)] * (rows[:, k + 1] > 0)
+            tot += rows[:, k + 1] * pk
+            expect['%s_f%d' % (prop, k)] = vol(pk)
+        expect[prop + '_tot'] = vol(tot)
+    if csf_on:
+        expect['frac_csf'] = vol(rows[:, 2 * nf + 1])
+    if ear_on:
+        c = 2 * nf + csf_on + 1
+        expect['frac_ear'] = vol(rows[:, c])
+        expect['D_ear'] = vol(info['DIFF_ear'][rows[:, c + 1].astype(int)] * (rows[:, c] > 0))
+    assert set(fit.param_names) == set(expect)
+    order = ['M0', 'frac_f0', 'peak_f0', 'frac_f1', 'peak_f1', 'fvf_f0', 'fvf_f1', 'fvf_tot', 'rad_f0',
+             'rad_f1', 'rad_tot']
+    assert fit.param_names[:len(order)] == order and fit.param_names[-2:] == ['MSE', 'R2']
+    for name, e in expect.items():
+        got = getattr(fit, name)
+        assert got.shape == e.shape and np.array_equal(got, e), name

@@ -332,6 +332,103 @@ def test_fit_parallel_multi_gpu(ukbb):
         assert np.array_equal(getattr(one, p), getattr(many, p)), p
 
 
+def test_fit_sharded_two_plans_one_gpu():
+    """The multi-GPU path of MFModel.fit (one plan and one host thread per shard,
+    cost-weighted contiguous bounds, disjoint writes into the params array) exercised on ONE
+    device: devices=[0, 0, 0] runs three plans concurrently on GPU 0.  Mixed K / CSF / EAR
+    voxels make the cost-weighted shards uneven.  Rows must equal the single-plan fit."""
+    ph = make_phantom(n_atoms=120, n_vox=2700, seed=37, csf_frac=0.3, ear=True)
+    model = MFModel(ph.dic)
+    rng = np.random.default_rng(1)
+    mask = (rng.random((20, 25, 10)) < 0.5).astype(float)
+    V = int(mask.sum())
+    in_mask = mask > 0
+
+    def vol(a, trailing=()):
+        out = np.zeros(mask.shape + trailing)
+        out[in_mask] = a[:V]
+        return out
+    kw = dict(peaks=vol(ph.peaks, (ph.peaks.shape[1],)), pgse_scheme=ph.sch, csf_mask=vol(ph.csf.astype(float)),
+              ear_mask=vol(ph.ear.astype(float)), verbose=0)
+    data = vol(ph.Y, (ph.Y.shape[1],))
+    one = model.fit(data, mask, vol(ph.K.astype(float)), devices=[0], **kw)
+    many = model.fit(data, mask, vol(ph.K.astype(float)), devices=[0, 0, 0], **kw)
+    exact = model.fit(data, mask, vol(ph.K.astype(float)), devices=[0, 0], exact=True, **kw)
+    for p in one.param_names:
+        assert np.array_equal(getattr(one, p), getattr(many, p)), p
+        assert np.array_equal(getattr(one, p), getattr(exact, p)), p
+    # and against the oracle on a subsample of the ROI
+    idx = np.arange(0, V, 97)
+    ref = oracle_rows(ph, idx)
+    assert np.allclose(one.M0[in_mask][idx], ref[:, 0], rtol=1e-9)
+    assert np.array_equal(one.frac_f0[in_mask][idx] > 0, ref[:, 1] > 0)
+    model.close()
+
+
+@pytest.mark.parametrize("layout", ["c64", "c32", "fortran", "strided", "int16"])
+def test_fit_volume_layouts(layout):
+    """mfb_fit_volume gathers the ROI voxels from the caller's volume whatever its layout:
+    C-contiguous float64 / float32, Fortran-ordered (what a NIfTI file yields), a strided view,
+    an integer volume (converted once on the host).  Maps equal those of a contiguous float64
+    copy of the same values."""
+    ph = make_phantom(n_atoms=64, n_vox=1000, seed=41, csf_frac=0.3)
+    model = MFModel(ph.dic)
+    rng = np.random.default_rng(2)
+    mask = (rng.random((12, 10, 15)) < 0.5).astype(float)
+    V = int(mask.sum())
+    in_mask = mask > 0
+    M = ph.Y.shape[1]
+    base = np.zeros(mask.shape + (M,))
+    Y = ph.Y[:V]
+    if layout == "c32":
+        Y = Y.astype(np.float32).astype(np.float64)
+    if layout == "int16":
+        Y = np.round(Y)
+    base[in_mask] = Y
+    if layout == "c64":
+        data = base
+    elif layout == "c32":
+        data = base.astype(np.float32)
+    elif layout == "fortran":
+        data = np.asfortranarray(base)
+    elif layout == "strided":
+        big = np.zeros((12, 10, 15, 2 * M + 3))
+        big[..., 1:2 * M:2] = base
+        data = big[..., 1:2 * M:2]
+        assert not data.flags.c_contiguous
+    else:
+        data = base.astype(np.int16)
+
+    def vol(a, trailing=()):
+        out = np.zeros(mask.shape + trailing)
+        out[in_mask] = a[:V]
+        return out
+    kw = dict(peaks=vol(ph.peaks, (ph.peaks.shape[1],)), pgse_scheme=ph.sch, csf_mask=vol(ph.csf.astype(float)),
+              verbose=0)
+    ref = model.fit(np.ascontiguousarray(base), mask, vol(ph.K.astype(float)), **kw)
+    got = model.fit(data, mask, vol(ph.K.astype(float)), **kw)
+    for p in ref.param_names:
+        assert np.array_equal(getattr(ref, p), getattr(got, p)), p
+    # ROI rows of the plain C-ABI call with a dense (V, M) host array
+    rows = ph.gpu_rows()[:V] if layout == "c64" else None
+    if rows is not None:
+        assert np.array_equal(ref.M0[in_mask], rows[:, 0])
+    model.close()
+
+
+def test_entry_points_restore_the_current_device():
+    """Every C-ABI entry point runs on its plan's device and puts the caller's current device
+    back (a library call must not move the host thread to another GPU)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ph = make_phantom(n_atoms=64, n_vox=64, seed=43)
+    torch.cuda.set_device(0)
+    rows1 = ph.gpu_rows(device=1)
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(rows1, ph.gpu_rows(device=0))
+
+
 @pytest.fixture(scope="module")
 def lowlevel():
     import os
@@ -405,7 +502,7 @@ def test_rotate_atom_2d_matches_reference(lowlevel):
 
 
 @pytest.mark.parametrize("sizes", [[800, 800], [800, 800, 1], [300, 520]])
-def test_solve_batch_fast_equals_exact(sizes, monkeypatch):
+def test_solve_batch_fast_equals_exact(sizes):
     """BASELINE config 2 shape (M = 100, ~800 atoms per fascicle, explicit per-voxel
     dictionaries): the DMMA screening path of mfb_solve_batch must return exactly what the
     reference-order search returns."""
@@ -418,22 +515,19 @@ def test_solve_batch_fast_equals_exact(sizes, monkeypatch):
                   for v in range(V)])
     Y += 0.02 * rng.standard_normal(Y.shape)
     fast = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
-    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
-    exact = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+    exact = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes), exact=True)
     for f, e in zip(fast, exact):
         assert np.array_equal(f, e)
     # shared dictionary (strideA = 0)
-    monkeypatch.delenv("MFB_SOLVE_EXACT")
     fast = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))
-    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
-    exact = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))
+    exact = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes), exact=True)
     for f, e in zip(fast, exact):
         assert np.array_equal(f, e)
 
 
 @pytest.mark.parametrize("sizes,M", [([300, 260], 150), ([200, 200, 1], 130), ([129, 65], 552),
                                      ([64, 300, 1], 257)])
-def test_solve_batch_general_M_equals_exact(sizes, M, monkeypatch):
+def test_solve_batch_general_M_equals_exact(sizes, M):
     """M > 112 (the i1 tile no longer fits in shared memory): the TMA-fed k-chunked DMMA
     screening path (k_normalize + k_gemm_pairs) must return exactly what the
     reference-order search returns, for per-voxel and for shared dictionaries."""
@@ -446,14 +540,11 @@ def test_solve_batch_general_M_equals_exact(sizes, M, monkeypatch):
                   for v in range(V)])
     Y += 0.02 * rng.standard_normal(Y.shape)
     for dic in (A, A[0]):
-        monkeypatch.delenv("MFB_SOLVE_EXACT", raising=False)
         fast = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes))
-        monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
-        exact = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes))
+        exact = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes), exact=True)
         for f, e in zip(fast, exact):
             assert np.array_equal(f, e)
     # and the single-voxel wrapper against the CPU oracle
-    monkeypatch.delenv("MFB_SOLVE_EXACT")
     for v in range(3):
         w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(A[v], Y[v].copy(), np.asarray(sizes))
         wo, subo, toto, objo, _ = orc.solve(A[v], Y[v], sizes)
@@ -499,7 +590,7 @@ def _triple_problem(sizes, M, V, seed, planted=3, signed=False):
 @pytest.mark.parametrize("sizes,M,planted,signed", [([60, 70, 50], 100, 3, False), ([300, 300, 300], 100, 3, False),
                                                     ([90, 90, 6], 105, 3, False), ([33, 47, 129], 150, 3, False),
                                                     ([64, 64, 64], 60, 2, False), ([50, 40, 30], 80, 3, True)])
-def test_solve_batch_triple_scan_equals_exact(sizes, M, planted, signed, monkeypatch):
+def test_solve_batch_triple_scan_equals_exact(sizes, M, planted, signed):
     """Three searched blocks (reference `_3`, mf_utils.py:470-607; BASELINE config 4 shape
     [300, 300, 300]): the DMMA + FP64 triple scan must return exactly what the
     reference-order search returns, and decide most 3-compartment voxels itself."""
@@ -508,20 +599,16 @@ def test_solve_batch_triple_scan_equals_exact(sizes, M, planted, signed, monkeyp
     _lib.solve_stats(reset=True)
     fast = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
     stats = _lib.solve_stats(reset=True)
-    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
-    exact = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+    exact = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes), exact=True)
     for f, e in zip(fast, exact):
         assert np.array_equal(f, e)
     assert stats[0] + stats[1] == V
     if planted == 3 and not signed:
         assert stats[0] >= 0.8 * V, stats
-    monkeypatch.delenv("MFB_SOLVE_EXACT")
     fast = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))     # shared dictionary
-    monkeypatch.setenv("MFB_SOLVE_EXACT", "1")
-    exact = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes))
+    exact = mfu.solve_exhaustive_posweights_batch(A[0], Y, np.asarray(sizes), exact=True)
     for f, e in zip(fast, exact):
         assert np.array_equal(f, e)
-    monkeypatch.delenv("MFB_SOLVE_EXACT")
     if sizes[0] < 100:
         for v in range(3):
             w, sub, tot, obj, yrec = mfu.solve_exhaustive_posweights(A[v], Y[v].copy(), np.asarray(sizes))
@@ -785,7 +872,7 @@ def test_c_abi_rejects_bad_arguments():
 
     def call(nb, lda, sz=p, Aptr=A.data_ptr()):
         return lib.mfb_solve_batch(0, 2, 10, nb, sz, Aptr, lda, 0, y.data_ptr(), w.data_ptr(), sub.data_ptr(),
-                                   obj.data_ptr(), None, None)
+                                   obj.data_ptr(), None, 0, None)
     assert call(2, 6) == 0
     assert call(2, 5) == _lib.MFB_EINVAL and b"lda" in lib.mfb_last_error()
     assert call(6, 6) == _lib.MFB_EINVAL

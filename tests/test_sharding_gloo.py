@@ -76,3 +76,23 @@ def test_shard_bounds_balance_cost():
         assert np.all(np.abs(share - cost.sum() / w) <= cost.max() + 1e-9)
     assert np.array_equal(shard_bounds(10, 4, np.zeros(10)), shard_bounds(10, 4))
     assert np.array_equal(shard_bounds(0, 3, np.zeros(0)), np.zeros(4, dtype=np.int64))
+
+
+def test_shard_bounds_edge_cases():
+    """Equal costs reduce to the equal-count split; one huge voxel gets a shard of its own
+    and leaves empty shards rather than overlapping ones; more shards than items."""
+    V = 1000
+    b = shard_bounds(V, 4, np.full(V, 7.0))
+    assert np.max(np.abs(b - shard_bounds(V, 4))) <= 1
+    cost = np.ones(100)
+    cost[40] = 1e9
+    b = shard_bounds(100, 4, cost)
+    assert b[0] == 0 and b[-1] == 100 and np.all(np.diff(b) >= 0)
+    owner = np.searchsorted(b, 40, side="right") - 1
+    assert b[owner] <= 40 < b[owner + 1]
+    spans = [(int(b[i]), int(b[i + 1])) for i in range(4)]
+    assert sum(hi - lo for lo, hi in spans) == 100
+    b = shard_bounds(3, 8, np.ones(3))
+    assert b[0] == 0 and b[-1] == 3 and b.size == 9 and np.all(np.diff(b) >= 0) and np.all(np.diff(b) <= 1)
+    b = shard_bounds(3, 8)
+    assert b[0] == 0 and b[-1] == 3 and b.size == 9 and np.all(np.diff(b) >= 0)

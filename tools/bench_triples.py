@@ -43,11 +43,10 @@ print("sizes %s V %d: %.1f voxels/s; %.2f TFLOP/s at the reference's 65 flop/tup
       % (sizes.tolist(), V, V / best, F_ref * V / best / 1e12, F_own * V / best / 1e12,
          100 * F_own * V / best / 37.1e12, st[0], st[1], st[2:], rec))
 if os.environ.get("BENCH_EXACT"):
-    os.environ["MFB_SOLVE_EXACT"] = "1"
     n = min(V, 64)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out2 = mfu.solve_exhaustive_posweights_batch(A[:n], Y[:n], sizes, return_device=True)
+    out2 = mfu.solve_exhaustive_posweights_batch(A[:n], Y[:n], sizes, return_device=True, exact=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print("reference-order tier: %.1f voxels/s; identical: %s" % (n / dt, all(bool(torch.equal(a[:n], b)) for a, b in zip(out, out2))))

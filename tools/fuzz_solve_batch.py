@@ -41,13 +41,10 @@ def one_case(rng, verbose):
     if rng.random() < 0.2:
         Y[0] = 0.0
     dic = A[0] if shared else A
-    os.environ.pop("MFB_SOLVE_EXACT", None)
     _lib.solve_stats(reset=True)
     fast = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes))
     stats = _lib.solve_stats()
-    os.environ["MFB_SOLVE_EXACT"] = "1"
-    exact = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes))
-    os.environ.pop("MFB_SOLVE_EXACT", None)
+    exact = mfu.solve_exhaustive_posweights_batch(dic, Y, np.asarray(sizes), exact=True)
     ok = all(np.array_equal(f, e) for f, e in zip(fast, exact))
     if verbose or not ok:
         print("%-8s M %3d sizes %-16s V %2d signed %d shared %d: screened %2d redone %2d %s" %
