@@ -205,6 +205,56 @@ def solve(A, y, dicsizes):
 # _fit_voxel / fit loop
 # --------------------------------------------------------------------------
 
+def solve2_gram(A, y, dicsizes):
+    """Two-block solve_exhaustive_posweights (`_2`, mfu:288-392) with the Gram terms formed by
+    BLAS and the four sign branches evaluated for all (i1, i2) at once in NumPy.  Same branch
+    logic, same residual formula, first minimum in (i1, i2) loop order; only the summation
+    order of the dot products differs from the reference, so indices agree except where two
+    residuals tie to rounding.  For shapes where the strided C / Numba Gram takes minutes
+    (M = 1776, N = 2000: BASELINE config 5).  Returns (w (2,), idx_sub (2,), min_obj)."""
+    A = np.asarray(A, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    N1, N2 = int(dicsizes[0]), int(dicsizes[1])
+    A1, A2 = A[:, :N1], A[:, N1:N1 + N2]
+    A11 = np.einsum('mi,mi->i', A1, A1)[:, None]
+    A22 = np.einsum('mi,mi->i', A2, A2)[None, :]
+    A12 = A1.T @ A2
+    Y1 = (A1.T @ y)[:, None]
+    Y2 = (A2.T @ y)[None, :]
+    y_sq = float(y @ y)
+    w1d = A22 * Y1 - A12 * Y2                                   # mfu:331-332
+    w2d = A11 * Y2 - A12 * Y1
+    Det = A11 * A22 - A12 ** 2
+    with np.errstate(divide='ignore', invalid='ignore'):
+        w0, w1 = w1d / Det, w2d / Det
+        both = y_sq + w0 ** 2 * A11 + w1 ** 2 * A22 + 2 * (w0 * w1 * A12 - w0 * Y1 - w1 * Y2)   # mfu:341-345
+        only1 = np.broadcast_to(y_sq - Y1 ** 2 / A11, A12.shape)    # w = Y1/A11
+        only2 = np.broadcast_to(y_sq - Y2 ** 2 / A22, A12.shape)
+    res = np.full(A12.shape, np.inf)
+    pp = (w1d > 0) & (w2d > 0)
+    res[pp] = both[pp]
+    c1 = (w1d >= 0) & (w2d <= 0) & ~pp & (Y1 >= 0)              # mfu:348-357
+    res[c1] = only1[c1]
+    c2 = (w1d <= 0) & (w2d >= 0) & ~pp & ~((w1d >= 0) & (w2d <= 0)) & (Y2 >= 0)   # mfu:358-367
+    res[c2] = only2[c2]
+    nn = (w1d < 0) & (w2d < 0)                                  # mfu:368-381
+    c3 = nn & (Y1 > 0)
+    res[c3] = only1[c3]
+    c4 = nn & ~(Y1 > 0) & (Y2 > 0)
+    res[c4] = only2[c4]
+    flat = int(np.argmin(res))                                  # first minimum in (i1, i2) order
+    i1, i2 = divmod(flat, N2)
+    if not res[i1, i2] < y_sq:                                  # strict < from min_obj = y_sq
+        return np.zeros(2), np.zeros(2, dtype=np.int64), y_sq
+    if pp[i1, i2]:
+        w = np.array([w0[i1, i2], w1[i1, i2]])
+    elif c1[i1, i2] or c3[i1, i2]:
+        w = np.array([Y1[i1, 0] / A11[i1, 0], 0.0])
+    else:
+        w = np.array([0.0, Y2[0, i2] / A22[0, i2]])
+    return w, np.array([i1, i2], dtype=np.int64), float(res[i1, i2])
+
+
 def fit_voxel(tab, plan, y, K, csf_i, ear_i, peaks_i, maxfasc, csf_on, ear_on,
               sig_csf=None, sig_ear=None, D=None):
     """_fit_voxel (mf:340-461): returns the params row."""

@@ -174,3 +174,20 @@ def test_fit_rows_match_reference_other_protocols(ukbb, tag):
     ysq = np.sum(g["data_" + tag][mask] ** 2, axis=1) / sch.shape[0]
     assert np.all(np.abs(rows[:, -2] - ref("MSE")) <= 1e-12 * ysq + 1e-9 * ref("MSE"))
     assert np.allclose(rows[:, -1], ref("R2"), rtol=1e-9, atol=1e-12)
+
+
+def test_solve2_gram_matches_reference_order_solver():
+    """oracle.solve2_gram (BLAS Gram + vectorised branches, used for index checks at shapes
+    where the strided Gram takes minutes) against the reference-order C restatement."""
+    rng = np.random.default_rng(77)
+    for trial in range(20):
+        M, n1, n2 = int(rng.integers(8, 60)), int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        signed = trial % 3 == 0
+        A = rng.standard_normal((M, n1 + n2)) if signed else rng.random((M, n1 + n2)) + 0.05
+        y = A[:, [rng.integers(0, n1), n1 + rng.integers(0, n2)]] @ rng.random(2) + 0.05 * rng.standard_normal(M)
+        if trial % 5 == 4:
+            y = -np.abs(y)
+        w, sub, tot, obj, yrec = orc.solve(A, y, [n1, n2])
+        wg, subg, objg = orc.solve2_gram(A, y, [n1, n2])
+        assert np.array_equal(sub, subg), trial
+        assert np.allclose(w, wg, rtol=1e-9, atol=1e-12) and abs(obj - objg) <= 1e-10 * float(y @ y)
