@@ -47,12 +47,17 @@ namespace mfb {
 #define FT_CQ (2 * FT_NS)   // slots of the per-atom parameter ring (outlives the tile's stage)
 #define FT_S1 (FT_TI + 4)  // row strides: == 4 mod 16 doubles -> conflict-free fragment loads
 #define FT_S2 (FT_TJ + 4)
+#define FT_NQ 6            // rows of a colq slot: z, beta, kappa, gamma, zu, alpha2 (folded screen)
 #define FT_NPAR 8          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu, single-solution gain
 #define FT_VP 12           // per-voxel scalars (voxp): see FastArgs
 
 // A competitive pair / tuple whose (refined) error bound exceeds kIllTol * c0 is tracked as
 // ill-conditioned: it can win only through the exact tier.
 static constexpr double kIllTol = 64.0;
+// c0 = kC0 (M + 8) eps |y|^2: bound on the error of the screening quantity
+// T = z1^2 + z2^2 - 2 rho z1 z2 - thr (1 - rho^2) caused by the rounding of its inputs (rho, z from
+// normalised FMA / DMMA dot products of M terms) and of its own evaluation.
+static constexpr double kC0 = 8.0;
 // Experiment switches (timing ablations; some produce invalid results) exist only in builds
 // with -DMFB_EXPERIMENTS; the default library has no environment-dependent behaviour.
 #ifdef MFB_EXPERIMENTS
@@ -65,6 +70,11 @@ static constexpr double kIllTol = 64.0;
 // be won by such a solution with that margin, and its reference-order search can be
 // restricted to the rows / columns of the atoms that can hold it (k_fast_select).
 static constexpr double kPreMargin = 32.0;
+// The screen is folded into the DMMA stream only while the (CSF-reduced) threshold is at least
+// 1 / kFoldMax of the (projected) signal energy: the folded quantities grow like that ratio.
+static constexpr double kFoldMax = 8.0;
+// evaluation error of the folded form, in units of (thr' + |y'|^2)^2 / thr' 
+static constexpr double kFoldEps = 16.0 * 2.2204e-16;
 
 struct FastArgs {
     DevPlan p;         // table source: rotation plan; explicit source: only p.M is used
@@ -96,7 +106,7 @@ struct FastArgs {
     int *t_flag;
     unsigned long long *vthr;
     int csf;
-    int Mp;            // M padded to a multiple of 4
+    int Mp;            // M + 1 (the folded-screen row) padded to a multiple of 4
     int Npad;          // max(N1, N2) padded to a multiple of FT_TJ
     int ntI;           // i1 tiles per voxel
     int debug;            // experiments only (MFB_FAST_DEBUG): 1 skip epilogue, 2 skip gathers (timing, results
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
         vp[8 + k] = (double)s_ibest;
         if (k == 0) {
             vp[0] = y_sq; vp[1] = A33; vp[2] = Y3; vp[3] = gain_c3; vp[11] = gain_c;
-            vp[4] = 4.0 * (M + 8) * 2.2204e-16 * y_sq;   // c0: screening error scale
+            vp[4] = kC0 * (M + 8) * 2.2204e-16 * y_sq;   // c0: screening error scale
         }
     }
 }
@@ -419,8 +429,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const int N1 = a.N1, N2 = a.N2;
     double *D1s = smem;                                   // [Mp][FT_S1]
     double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS][Mp][FT_S2]
-    double *colq = D2s + (size_t)FT_NS * Mp * FT_S2;      // [FT_CQ][5][FT_TJ]  z, beta, kappa, gamma, zu
-    double *w1l = colq + FT_CQ * 5 * FT_TJ;               // [Mp] plan of fascicle 1
+    double *colq = D2s + (size_t)FT_NS * Mp * FT_S2;      // [FT_CQ][FT_NQ][FT_TJ]  z, beta, kappa, gamma, zu, alpha2
+    double *tq = colq + FT_CQ * FT_NQ * FT_TJ;            // [FT_CQ][2]  threshold folded into the tile, its reciprocal
+    double *w1l = tq + FT_CQ * 2;                         // [Mp] plan of fascicle 1
     double *w1h = w1l + Mp;
     double *w2l = w1h + Mp;                               // [Mp] plan of fascicle 2
     double *w2h = w2l + Mp;
@@ -441,6 +452,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *vp = a.voxp + v * FT_VP;
     const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
+    const double ysq_p = fmax(vp[0] - gain_c, 0.0);       // energy of y off the CSF column
     const double gpre = fmax(vp[5], vp[6]);
     const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
     const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
@@ -500,6 +512,23 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             const double *Tc = SRC ? Ar + a.start2 + (ok ? j : 0) : p.table + (ok ? j : 0);
             const size_t rs = SRC ? (size_t)a.lda : (size_t)N;
             double *dst = D2s + (size_t)st * Mp * FT_S2 + jj;
+            // Folded screen (see the consumers): the warp that owns row M of the tile snapshots the
+            // threshold and writes  -z2_j / thr'  there, so that the DMMA stream itself delivers
+            // rho~ = rho - z1 z2 / thr'  (row M of the resident i1 tile holds z1_i).  thr' is the
+            // threshold minus the CSF share of the gain; when it is too small a fraction of the
+            // (projected) signal energy the fold would amplify rounding errors: the row stays zero
+            // and the consumers run the unfolded closed form on rho.
+            double brow = 0.0;
+            if (mrow0 == M % RS) {
+                const double thr_now = __longlong_as_double((long long)*(volatile unsigned long long *)&s_thr);
+                const double thrp = thr_now - gain_c;
+                const bool fold = thrp * kFoldMax > ysq_p && thrp > 0.0;
+                const double rthr = fold ? 1.0 / thrp : 0.0;
+                const double z2j = ok ? __ldg(cp2 + (size_t)2 * a.Npad + j) : 0.0;
+                brow = -z2j * rthr;
+                colq[((jt % FT_CQ) * FT_NQ + 5) * FT_TJ + jj] = fma(z2j, brow, 1.0);   // alpha2 = 1 - z2^2 / thr'
+                if (jj == 0) { tq[(jt % FT_CQ) * 2] = fold ? thrp : 0.0; tq[(jt % FT_CQ) * 2 + 1] = rthr; }
+            }
             for (int mb = mrow0; mb < Mp; mb += RS * UB) {
                 double lo[UB], hi[UB];
 #pragma unroll
@@ -530,11 +559,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 #pragma unroll
                 for (int q = 0; q < UB; q++) {
                     const int m = mb + RS * q;
-                    if (m < Mp) dst[(size_t)m * FT_S2] = hi[q];
+                    if (m < Mp) dst[(size_t)m * FT_S2] = m == M ? brow : hi[q];
                 }
             }
             for (int e = pt; e < 5 * FT_TJ; e += FT_PROD)
-                colq[((jt % FT_CQ) * 5 + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
+                colq[((jt % FT_CQ) * FT_NQ + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
                     __ldg(cp2 + (size_t)(e / FT_TJ + 2) * a.Npad + jr * FT_TJ + (e % FT_TJ));
             mbar_arrive(&s_full[st]);
         }
@@ -544,7 +573,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     // =============================== consumers ===============================
     const int g = lane >> 2, t4 = lane & 3;
     const double wide = 4.0 * kIllTol * c0;
-    const double c1 = 4.0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
+    const double c1 = kC0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
     const double negc0 = -c0;
     // ---- resident i1 tile: rotate, project out the CSF column, normalise ----
     {
@@ -553,6 +582,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         const bool ok = i < N1;
         const double sc = ok ? cp1[i] : 0.0;
         const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
+        const double z1row = ok ? cp1[(size_t)2 * a.Npad + i] : 0.0;   // row M: the folded-screen row
         const double *Tc = SRC ? Ar + a.start1 + (ok ? i : 0) : p.table + (ok ? i : 0);
         const size_t rs = SRC ? (size_t)a.lda : (size_t)N;
         constexpr int RS = FT_CONS / FT_TI;               // rows per pass (2)
@@ -574,7 +604,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 if (m < Mp) {
                     double d = fma(w1h[m], hi[q], w1l[m] * lo[q]);
                     if (CSF) d = fma(-al, cs[m], d);
-                    D1s[(size_t)m * FT_S1 + ii] = d * sc;
+                    D1s[(size_t)m * FT_S1 + ii] = m == M ? z1row : d * sc;
                 }
             }
         }
@@ -658,9 +688,36 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         // the stage's D2 tile is consumed: release it before the scalar epilogue (the per-atom
         // parameters live in a ring twice as deep, so the producers may run ahead meanwhile)
         mbar_arrive(&s_empty[st]);
-        const double *cq = colq + (jt % FT_CQ) * 5 * FT_TJ;
+        const double *cq = colq + (jt % FT_CQ) * FT_NQ * FT_TJ;
+        const double thr_t = tq[(jt % FT_CQ) * 2], rthr_t = tq[(jt % FT_CQ) * 2 + 1];
         unsigned hit = 0;
-        if (FT_DEBUG(a, 1)) {
+        if (thr_t > 0.0 && !FT_DEBUG(a, 1)) {
+            // Folded screen.  The accumulators hold rho~ = rho - z1 z2 / thr' (row M of the tiles),
+            // and with alpha = 1 - z^2 / thr':
+            //     z1^2 + z2^2 - 2 rho z1 z2 - thr' (1 - rho^2)  =  thr' (rho~^2 - alpha1 alpha2)
+            // The left side >= -margin is NECESSARY for any solution on a subset of the pair's
+            // columns (+ CSF) to reach the threshold: the unconstrained least-squares gain of
+            // all the columns bounds every constrained one.  Two FP64 operations and a sign test
+            // per pair; the signs of the weights and the sub-problems are looked at only for the
+            // (rare) pairs that pass.
+            const double sum = thr_t + ysq_p;
+            const double cm = fma(kFoldEps * sum, sum * rthr_t, c0) * rthr_t;      // margin / thr'
+            double al1[2];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) al1[mt] = fma(-z1[mt] * z1[mt], rthr_t, 1.0);
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const double2 a2v = *reinterpret_cast<const double2 *>(cq + 5 * FT_TJ + 8 * nt + 2 * t4);
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const double rt = acc[mt][nt][e];
+                        const double t = fma(-al1[mt], e ? a2v.y : a2v.x, fma(rt, rt, cm));
+                        if (__double2hiint(t) >= 0) hit |= 1u << (nt * 4 + e * 2 + mt);
+                    }
+            }
+        } else if (FT_DEBUG(a, 1)) {
             double sacc = 0.0;
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
@@ -755,10 +812,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                     const int nt = q >> 2, e = (q >> 1) & 1, mt = q & 1;
                     const int c = 8 * nt + 2 * t4 + e;
                     double num, det, re, za, zb, gadd;
-                    pair_gain<CSF>(rcopy[q], mt ? z1[1] : z1[0], cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
-                                   mt ? k1[1] : k1[0], cq[2 * FT_TJ + c], mt ? g1[1] : g1[0],
-                                   cq[3 * FT_TJ + c], mt ? zu1[1] : zu1[0], cq[4 * FT_TJ + c], Y3, gain_c,
-                                   num, det, re, za, zb, gadd);
+                    const double z1q = mt ? z1[1] : z1[0];
+                    // folded tile: rho = rho~ + z1 z2 / thr', with the very product the tile row holds
+                    const double rho_q = fma(z1q, cq[c] * rthr_t, rcopy[q]);
+                    if (!pair_gain<CSF>(rho_q, z1q, cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
+                                        mt ? k1[1] : k1[0], cq[2 * FT_TJ + c], mt ? g1[1] : g1[0],
+                                        cq[3 * FT_TJ + c], mt ? zu1[1] : zu1[0], cq[4 * FT_TJ + c], Y3, gain_c,
+                                        num, det, re, za, zb, gadd))
+                        continue;    // no both-positive closed form: the pair's best solution is in gpre
                     if (!(det > 1e-12)) { gill = INFINITY; continue; }   // numerically singular
                     const double rdet = 1.0 / det;
                     double gq = num * rdet, tq = c0 * rdet;
@@ -954,7 +1015,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
     // ===================================== consumers =====================================
     const int g = lane >> 2, t4 = lane & 3;
     const double wide = 4.0 * kIllTol * c0;
-    const double c1 = 4.0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
+    const double c1 = kC0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
     const double negc0 = -c0;
     const int wrow = warp * 16;
     double *cq = colq + warp * 5 * GP_TJ;
@@ -1596,7 +1657,7 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 bool fast_supported(const DevPlan &p, int K, int csf, int ear)
 {
-    const int Mp = (p.M + 3) & ~3;
+    const int Mp = (p.M + 4) & ~3;     // + the folded-screen row
     return K == 2 && !ear && !p.has_between && Mp <= 112 && p.N >= 8 && p.N <= 46000 &&
            (csf == 0 || p.sig_csf);
 }
@@ -1630,7 +1691,7 @@ struct FastGeom {
 static FastGeom fast_geom(int M, int N1, int N2)
 {
     FastGeom g;
-    g.Mp = (M + 3) & ~3;
+    g.Mp = (M + 4) & ~3;               // M + 1 (the folded-screen row of k_fast_pairs) padded to 4
     g.gemm = g.Mp > 112;
 #ifdef MFB_EXPERIMENTS
     if (getenv("MFB_FORCE_GEMM")) g.gemm = true;
@@ -1765,8 +1826,8 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         }
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     } else {
-        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_CQ * 5 * FT_TJ +
-                                              5 * a.Mp + 64) + sizeof(int) * 4 * a.Mp;
+        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_CQ * FT_NQ * FT_TJ +
+                                              FT_CQ * 2 + 5 * a.Mp + 64) + sizeof(int) * 4 * a.Mp;
         if (smem + 64 > 227 * 1024) {
             set_error("fast tier: tile does not fit in shared memory");
             return MFB_EUNSUPPORTED;
