@@ -29,8 +29,11 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, experiments=False):
+    """experiments=True builds libmfb200_exp.so with -DMFB_EXPERIMENTS (timing ablations and
+    counters steered by environment variables; never loaded unless MFB_LIB points at it)."""
+    lib = LIB.replace(".so", "_exp.so") if experiments else LIB
+    if not force and not experiments and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
@@ -38,17 +41,19 @@ def build(force=False, verbose=False):
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", "_exp.o" if experiments else ".o"))
+        if experiments:
+            extra = extra + ["-DMFB_EXPERIMENTS"]
         cmd = [nvcc] + ARCH + COMMON + extra + ["-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

@@ -530,8 +530,8 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             const int32_t n_redo = head[0];
 #ifdef MFB_EXPERIMENTS
             if (getenv("MFB_FAST_DEBUG") && (atoi(getenv("MFB_FAST_DEBUG")) & 8))
-                fprintf(stderr, "[mfb] %lld voxels: %d rare-path warp entries, %d competitive pairs\n",
-                        (long long)cnt, head[5], head[6]);
+                fprintf(stderr, "[mfb] %lld voxels: %d rare-path warp entries, %d competitive pairs, %d level-2 warp entries\n",
+                        (long long)cnt, head[5], head[6], head[7]);
 #endif
             pl->stats[0] += (double)(cnt - n_redo);
             pl->stats[6] += head[2];          // ill-conditioned competitor

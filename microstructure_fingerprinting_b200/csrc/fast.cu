@@ -49,7 +49,7 @@ namespace mfb {
 #define FT_S2 (FT_TJ + 4)
 #define FT_NQ 6            // rows of a colq slot: z, beta, kappa, gamma, zu, alpha2 (folded screen)
 #define FT_NPAR 8          // per-atom parameters: scale, alpha, z, beta, kappa, gamma, zu, single-solution gain
-#define FT_VP 12           // per-voxel scalars (voxp): see FastArgs
+#define FT_VP 16           // per-voxel scalars (voxp): see FastArgs
 
 // A competitive pair / tuple whose (refined) error bound exceeds kIllTol * c0 is tracked as
 // ill-conditioned: it can win only through the exact tier.
@@ -70,6 +70,12 @@ static constexpr double kC0 = 8.0;
 // be won by such a solution with that margin, and its reference-order search can be
 // restricted to the rows / columns of the atoms that can hold it (k_fast_select).
 static constexpr double kPreMargin = 32.0;
+// The reference's three-block solver accepts the unconstrained Cramer solution when its
+// numerators D_i >= -tol with an ABSOLUTE tol = 2.2204e-14 (mf_utils.py:562): on data of tiny
+// magnitude (|a|^4 |a.y| approaching tol) it takes solutions with negative weights, which the
+// screening tier (strictly positive weights) would never certify.  Voxels whose numerators can
+// be that small are handed to the reference-order tier, which reproduces the tolerance.
+static constexpr double kCramerScaleMin = 2.2204e-14 * 1e6;
 // The screen is folded into the DMMA stream only while the (CSF-reduced) threshold is at least
 // 1 / kFoldMax of the (projected) signal energy: the folded quantities grow like that ratio.
 static constexpr double kFoldMax = 8.0;
@@ -117,8 +123,16 @@ struct FastArgs {
     const double *y;
     int *ip_rows;      // [v][2][M][2]  rl, rh
     double *ip_w;      // [v][2][M][2]  wl, wh
+    // tile-major prepared copies for k_fast_tiles (written by k_fast_prep): per voxel, the
+    // rotated / CSF-projected / normalised atoms laid out exactly as the kernel's shared-memory
+    // tiles, so that one TMA bulk copy moves a whole tile
+    double *D1c;       // [v][i1 tile][Mp][FT_S1]
+    double *D2c;       // [v][i2 tile][Mp][FT_S2] + [FT_NQ][FT_TJ] per-atom parameters
+    int64_t d1c_stride, d2c_stride;   // doubles per voxel
+    int nt2;           // i2 tiles per voxel
     double *colp;      // [v][2][FT_NPAR][Npad]
-    double *voxp;      // [v][FT_VP]  y_sq, A33, Y3, gain_c3 (CSF projection), c0, Gpre(block 0..2), best single atom
+    double *voxp;      // [v][FT_VP]  (slots 12..14: magnitude of the Cramer numerators of block 0..2, see kCramerScaleMin)
+                       //             y_sq, A33, Y3, gain_c3 (CSF projection), c0, Gpre(block 0..2), best single atom
                        //             of block 0..2, gain of the CSF-only solution
     double *cta_gain;  // [v][ntI]
     double *cta_tol;   // [v][ntI]
@@ -219,9 +233,11 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     const double gain_c3 = a.csf ? Y3 * Y3 / A33 : 0.0;
     const double gain_c = (a.csf && Y3 > 0) ? gain_c3 : 0.0;
     double *cp = a.colp + (v * a.nblk + k) * (int64_t)FT_NPAR * a.Npad;
-    double gbest = 0.0;
+    double gbest = 0.0, sqmax = 0.0, dymax = 0.0;
     int ibest = 0;
-    for (int i = threadIdx.x; i < a.Npad; i += blockDim.x) {
+    // atoms up to the end of the block's last tile (the prepared copies hold whole tiles)
+    const int iend = !a.D1c ? a.Npad : (k == 0 ? a.ntI * FT_TI : a.nt2 * FT_TJ);
+    for (int i = threadIdx.x; i < iend; i += blockDim.x) {
         double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (i < Nk) {
             double sq = 0.0, dy = 0.0, d3 = 0.0;
@@ -233,6 +249,8 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
                 dy = fma(d, ys[m], dy);
                 d3 = fma(d, cs[m], d3);
             }
+            sqmax = fmax(sqmax, sq);
+            dymax = fmax(dymax, fabs(dy));
             const double r = rsqrt(sq);
             if (!a.csf) {
                 par[0] = r;            // scale
@@ -258,10 +276,40 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
                 if (gi > gbest) { gbest = gi; ibest = i; }
             }
         }
-        for (int q = 0; q < FT_NPAR; q++) cp[(size_t)q * a.Npad + i] = par[q];
+        if (i < a.Npad)
+            for (int q = 0; q < FT_NPAR; q++) cp[(size_t)q * a.Npad + i] = par[q];
+        if (a.D1c && k < 2) {
+            // second pass over the measurements: the atom as the pair kernel multiplies it
+            // (rotated, off the CSF column, unit norm), written into its tile; rows M.. of a
+            // tile: the folded-screen row (-z for the streamed block, filled per warp in shared
+            // memory for the resident block) and zero padding
+            const int T = k == 0 ? FT_TI : FT_TJ, S = k == 0 ? FT_S1 : FT_S2;
+            const size_t rec = (size_t)a.Mp * S + (k == 0 ? 0 : FT_NQ * FT_TJ);
+            double *dc = (k == 0 ? a.D1c + v * a.d1c_stride : a.D2c + v * a.d2c_stride) + (size_t)(i / T) * rec + (i % T);
+            const double *Ac = a.src ? Ar + a.startb[k] + i : nullptr;
+            const double scl = par[0], al = par[1];
+            for (int m = 0; m < M; m++) {
+                double val = 0.0;
+                if (i < Nk) {
+                    double d = a.src ? Ac[(size_t)m * a.lda]
+                                     : fma(wh[m], p.table[(size_t)rh[m] * p.N + i], wl[m] * p.table[(size_t)rl[m] * p.N + i]);
+                    if (a.csf) d = fma(-al, cs[m], d);
+                    val = d * scl;
+                }
+                dc[(size_t)m * S] = val;
+            }
+            for (int m = M; m < a.Mp; m++) dc[(size_t)m * S] = (m == M && k == 1) ? -par[2] : 0.0;
+            if (k == 1) {
+                double *pq = dc + (size_t)a.Mp * S;      // [FT_NQ][FT_TJ]: z, beta, kappa, gamma, zu, z^2
+                for (int q = 0; q < 5; q++) pq[q * FT_TJ] = par[2 + q];
+                pq[5 * FT_TJ] = par[2] * par[2];
+            }
+        }
     }
     const double gmine = gbest;
     gbest = block_max(gbest, red);
+    sqmax = block_max(sqmax, red);
+    dymax = block_max(dymax, red);
     // atom holding the best single-column gain (lowest index on ties): the pair scan starts there
     __shared__ int s_ibest;
     if (threadIdx.x == 0) s_ibest = INT_MAX;
@@ -272,6 +320,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
         double *vp = a.voxp + v * FT_VP;
         vp[5 + k] = fmax(gbest, gain_c);   // slots 5, 6, 7: blocks 0, 1, 2
         vp[8 + k] = (double)s_ibest;
+        vp[12 + k] = fmax(sqmax, a.csf ? A33 : 0.0) * fmax(sqmax, a.csf ? A33 : 0.0) * fmax(dymax, a.csf ? fabs(Y3) : 0.0);
         if (k == 0) {
             vp[0] = y_sq; vp[1] = A33; vp[2] = Y3; vp[3] = gain_c3; vp[11] = gain_c;
             vp[4] = kC0 * (M + 8) * 2.2204e-16 * y_sq;   // c0: screening error scale
@@ -351,6 +400,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                      " selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(b) : "memory");
 }
 __device__ __forceinline__ void consumer_sync()
 {
@@ -500,8 +562,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         constexpr int UB = 14;                            // (lo, hi) pairs in flight per thread
         for (int jt = 0; jt < ntJ; jt++) {
             const int st = jt % FT_NS;
-            if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
-            if (FT_DEBUG(a, 2) && jt >= FT_NS) { mbar_arrive(&s_full[st]); continue; }
+            if (FT_DEBUG(a, 2) && jt >= FT_NS) {
+                mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
+                mbar_arrive(&s_full[st]);
+                continue;
+            }
+            // The fold row's values are prepared BEFORE waiting for the stage to be released (their
+            // latency overlaps the consumers' work on the previous tiles) and stored after the
+            // tile's own rows by a separate store: the tile loop below is latency-critical -- a
+            // select inside its store pass alone costs 12 % of the kernel -- and stays untouched.
             const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
             if (pt == 0) atomicMax(&s_thr, *(volatile unsigned long long *)vthr);
             const int j = jr * FT_TJ + jj;
@@ -522,13 +591,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
             if (mrow0 == M % RS) {
                 const double thr_now = __longlong_as_double((long long)*(volatile unsigned long long *)&s_thr);
                 const double thrp = thr_now - gain_c;
-                const bool fold = thrp * kFoldMax > ysq_p && thrp > 0.0;
+                const bool fold = thrp * kFoldMax > ysq_p && thrp > 0.0 && !FT_DEBUG(a, 16);
                 const double rthr = fold ? 1.0 / thrp : 0.0;
                 const double z2j = ok ? __ldg(cp2 + (size_t)2 * a.Npad + j) : 0.0;
                 brow = -z2j * rthr;
+                // (the slots of the parameter ring were released two stage generations ago)
                 colq[((jt % FT_CQ) * FT_NQ + 5) * FT_TJ + jj] = fma(z2j, brow, 1.0);   // alpha2 = 1 - z2^2 / thr'
                 if (jj == 0) { tq[(jt % FT_CQ) * 2] = fold ? thrp : 0.0; tq[(jt % FT_CQ) * 2 + 1] = rthr; }
             }
+            if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
             for (int mb = mrow0; mb < Mp; mb += RS * UB) {
                 double lo[UB], hi[UB];
 #pragma unroll
@@ -559,9 +630,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
 #pragma unroll
                 for (int q = 0; q < UB; q++) {
                     const int m = mb + RS * q;
-                    if (m < Mp) dst[(size_t)m * FT_S2] = m == M ? brow : hi[q];
+                    if (m < Mp) dst[(size_t)m * FT_S2] = hi[q];
                 }
             }
+            if (mrow0 == M % RS) dst[(size_t)M * FT_S2] = brow;      // after this thread's zero for row M
             for (int e = pt; e < 5 * FT_TJ; e += FT_PROD)
                 colq[((jt % FT_CQ) * FT_NQ + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
                     __ldg(cp2 + (size_t)(e / FT_TJ + 2) * a.Npad + jr * FT_TJ + (e % FT_TJ));
@@ -690,21 +762,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
         mbar_arrive(&s_empty[st]);
         const double *cq = colq + (jt % FT_CQ) * FT_NQ * FT_TJ;
         const double thr_t = tq[(jt % FT_CQ) * 2], rthr_t = tq[(jt % FT_CQ) * 2 + 1];
-        unsigned hit = 0;
-        if (thr_t > 0.0 && !FT_DEBUG(a, 1)) {
-            // Folded screen.  The accumulators hold rho~ = rho - z1 z2 / thr' (row M of the tiles),
-            // and with alpha = 1 - z^2 / thr':
+        unsigned hit = 0, hit1 = ~0u;
+        if (thr_t > 0.0) {
+            // Level 1, folded screen.  The accumulators hold rho~ = rho - z1 z2 / thr' (row M of
+            // the tiles), and with alpha = 1 - z^2 / thr':
             //     z1^2 + z2^2 - 2 rho z1 z2 - thr' (1 - rho^2)  =  thr' (rho~^2 - alpha1 alpha2)
             // The left side >= -margin is NECESSARY for any solution on a subset of the pair's
             // columns (+ CSF) to reach the threshold: the unconstrained least-squares gain of
             // all the columns bounds every constrained one.  Two FP64 operations and a sign test
-            // per pair; the signs of the weights and the sub-problems are looked at only for the
-            // (rare) pairs that pass.
+            // per pair.  thr' is the producer's snapshot (<= the current threshold: conservative).
             const double sum = thr_t + ysq_p;
             const double cm = fma(kFoldEps * sum, sum * rthr_t, c0) * rthr_t;      // margin / thr'
             double al1[2];
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) al1[mt] = fma(-z1[mt] * z1[mt], rthr_t, 1.0);
+            hit1 = 0;
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
                 const double2 a2v = *reinterpret_cast<const double2 *>(cq + 5 * FT_TJ + 8 * nt + 2 * t4);
@@ -714,10 +786,28 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                     for (int mt = 0; mt < 2; mt++) {
                         const double rt = acc[mt][nt][e];
                         const double t = fma(-al1[mt], e ? a2v.y : a2v.x, fma(rt, rt, cm));
-                        if (__double2hiint(t) >= 0) hit |= 1u << (nt * 4 + e * 2 + mt);
+                        if (__double2hiint(t) >= 0) hit1 |= 1u << (nt * 4 + e * 2 + mt);
                     }
             }
-        } else if (FT_DEBUG(a, 1)) {
+        }
+        // Level 2 (only when some lane of the warp passed level 1; always on unfolded tiles):
+        // the closed-form NNLS screen with the signs of the weights, the 2-column sub-problems
+        // and the CURRENT threshold, straight-line over the thread's 16 pairs, on rho recovered
+        // with the very product the tile row holds.
+        if (!__any_sync(0xffffffffu, hit1 != 0)) continue;
+        if (FT_DEBUG(a, 8) && lane == 0) atomicAdd(&a.reasons[6], 1);   // experiment: level-2 entries (warps)
+        if (thr_t > 0.0) {
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++)
+                        acc[mt][nt][e] = fma(z1[mt], (e ? z2v.y : z2v.x) * rthr_t, acc[mt][nt][e]);
+            }
+        }
+        if (FT_DEBUG(a, 1)) {
             double sacc = 0.0;
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
@@ -813,9 +903,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                     const int c = 8 * nt + 2 * t4 + e;
                     double num, det, re, za, zb, gadd;
                     const double z1q = mt ? z1[1] : z1[0];
-                    // folded tile: rho = rho~ + z1 z2 / thr', with the very product the tile row holds
-                    const double rho_q = fma(z1q, cq[c] * rthr_t, rcopy[q]);
-                    if (!pair_gain<CSF>(rho_q, z1q, cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
+                    if (!pair_gain<CSF>(rcopy[q], z1q, cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
                                         mt ? k1[1] : k1[0], cq[2 * FT_TJ + c], mt ? g1[1] : g1[0],
                                         cq[3 * FT_TJ + c], mt ? zu1[1] : zu1[0], cq[4 * FT_TJ + c], Y3, gain_c,
                                         num, det, re, za, zb, gadd))
@@ -845,6 +933,371 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 }
             }
         }
+    }
+
+    // ---- reduction over the consumer threads: best gain, tie -> lower index ----
+    const double gt = bidx >= 0 ? gb : -1.0;
+    const double tolt = bidx >= 0 ? tb : 0.0;
+    double gm = gt;
+    int im = bidx >= 0 ? bidx : INT_MAX;
+    for (int o = 16; o > 0; o >>= 1) {
+        double og = __shfl_xor_sync(0xffffffffu, gm, o);
+        int oi = __shfl_xor_sync(0xffffffffu, im, o);
+        if (og > gm || (og == gm && oi < im)) { gm = og; im = oi; }
+    }
+    for (int o = 16; o > 0; o >>= 1) gill = fmax(gill, __shfl_xor_sync(0xffffffffu, gill, o));
+    double *redg = red, *redl = red + 16;
+    int *redi = (int *)(red + 8);
+    if (lane == 0) { redg[warp] = gm; redi[warp] = im; redl[warp] = gill; }
+    consumer_sync();
+    double G = redg[0], Gill = redl[0];
+    int I = redi[0];
+    for (int w = 1; w < FT_CONS / 32; w++) {
+        if (redg[w] > G || (redg[w] == G && redi[w] < I)) { G = redg[w]; I = redi[w]; }
+        Gill = fmax(Gill, redl[w]);
+    }
+    if (bidx >= 0 && bidx == I) s_tolG = tolt;
+    consumer_sync();
+    const double tolG = I != INT_MAX ? s_tolG : 0.0;
+    if (bidx >= 0) {
+        const bool winner = bidx == I;
+        const bool close = gt + tolt >= G - tolG;
+        if ((winner && flag) || (!winner && close)) atomicOr(&s_flag, 1);
+    }
+    consumer_sync();
+    if (tid == 0) {
+        const int64_t o = v * a.ntI + tI;
+        a.cta_gain[o] = G;
+        a.cta_tol[o] = tolG;
+        a.cta_idx[o] = I == INT_MAX ? -1 : I;
+        a.cta_flag[o] = s_flag;
+        a.cta_ill[o] = Gill;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// k_fast_tiles: the pair scan for M <= 111 on the tile-major prepared copies (k_fast_prep).
+// Same decomposition as k_fast_pairs -- one CTA per (voxel, 128-atom i1 tile), the i1 tile
+// resident in shared memory, 32-atom i2 tiles streamed through a 3-stage ring, eight consumer
+// warps (16 x 32 correlation tile each, DMMA m8n8k4) -- but
+//   * nothing is gathered or computed on the producer side: ONE elected thread moves every tile
+//     (and its per-atom parameters) with one TMA bulk copy (cp.async.bulk + mbarrier
+//     complete_tx) from the prepared copy, which the 8 CTAs of a voxel share through the L2;
+//   * the screen is folded into the DMMA stream with a WARP-PRIVATE threshold: row M of the
+//     streamed tiles holds -z2_j, and every consumer warp keeps z1_i / thr' in ITS 16 columns
+//     of row M of the resident tile (no other warp reads those columns), rewriting them
+//     whenever it adopts a higher threshold.  The accumulators then deliver
+//     rho~ = rho - z1 z2 / thr' and, with alpha = 1 - z^2 / thr',
+//         z1^2 + z2^2 - 2 rho z1 z2 - thr' (1 - rho^2)  =  thr' (rho~^2 - alpha1 alpha2),
+//     the unconstrained least-squares gain test of the pair's columns (+ CSF), which is
+//     NECESSARY for any solution on a subset of those columns to reach the threshold: about
+//     2.5 FP64 operations and a sign test per pair.  Only warps in which some pair passes run
+//     the closed-form NNLS screen of k_fast_pairs (signs of the weights, 2-column sub-problems)
+//     on the recovered rho, and from there the competitive-pair path.
+// ---------------------------------------------------------------------------------
+#define FT2_THREADS (FT_CONS + 32)
+#define FT2_REC(Mp) ((size_t)(Mp) * FT_S2 + FT_NQ * FT_TJ)      // doubles per streamed tile record
+
+template <int CSF>
+__global__ void __launch_bounds__(FT2_THREADS, 1) k_fast_tiles(FastArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int M = a.p.M, Mp = a.Mp;
+    const int N1 = a.N1, N2 = a.N2;
+    const size_t rec = FT2_REC(Mp);
+    double *D1s = smem;                                   // [Mp][FT_S1]
+    double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS] records: [Mp][FT_S2] | [FT_NQ][FT_TJ]
+    double *red = D2s + (size_t)FT_NS * rec;              // [64]
+    __shared__ unsigned long long s_thr;                  // CTA-wide lower bound on the winning gain
+    __shared__ unsigned long long s_full[FT_NS], s_empty[FT_NS], s_d1;
+    __shared__ double s_tolG;
+    __shared__ int s_flag;
+
+    const int64_t v = blockIdx.y;
+    const int tI = blockIdx.x;
+    const int i0 = tI * FT_TI;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *vp = a.voxp + v * FT_VP;
+    const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
+    const double ysq_p = fmax(vp[0] - gain_c, 0.0);       // energy of y off the CSF column
+    const double gpre = fmax(vp[5], vp[6]);
+    const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
+    const int ntJ = a.nt2;
+    const int jt0 = min(ntJ - 1, max(0, (int)vp[9]) / FT_TJ);   // scan starts at block 2's best single atom
+    unsigned long long *vthr = a.vthr + v;
+
+    if (tid == 0) {
+        s_thr = max((unsigned long long)__double_as_longlong(fmax(gpre - kPreMargin * c0, 0.0)),
+                    *(volatile unsigned long long *)vthr);
+        s_flag = 0;
+        mbar_init(&s_d1, 1);
+        for (int st = 0; st < FT_NS; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], FT_CONS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= FT_CONS) {
+        // ============ producer: one thread, one bulk copy per tile ============
+        if (lane == 0) {
+            const double *src1 = a.D1c + v * a.d1c_stride + (size_t)tI * Mp * FT_S1;
+            const unsigned rows_per_copy = 32, nrow = (unsigned)Mp;
+            mbar_expect_tx(&s_d1, (unsigned)(nrow * FT_S1 * sizeof(double)));
+            for (unsigned r = 0; r < nrow; r += rows_per_copy) {
+                const unsigned nr = min(rows_per_copy, nrow - r);
+                bulk_g2s(D1s + (size_t)r * FT_S1, src1 + (size_t)r * FT_S1, nr * FT_S1 * (unsigned)sizeof(double), &s_d1);
+            }
+            const double *src2 = a.D2c + v * a.d2c_stride;
+            for (int jt = 0; jt < ntJ; jt++) {
+                const int st = jt % FT_NS;
+                if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
+                const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
+                atomicMax(&s_thr, *(volatile unsigned long long *)vthr);   // thresholds of the voxel's other CTAs
+                mbar_expect_tx(&s_full[st], (unsigned)(rec * sizeof(double)));
+                bulk_g2s(D2s + (size_t)st * rec, src2 + (size_t)jr * rec, (unsigned)(rec * sizeof(double)), &s_full[st]);
+            }
+        }
+        return;
+    }
+
+    // =============================== consumers ===============================
+    const int g = lane >> 2, t4 = lane & 3;
+    const double wide = 4.0 * kIllTol * c0;
+    const double c1 = kC0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
+    const double negc0 = -c0;
+    const int wrow = warp * 16;
+    double z1[2], b1[2], k1[2], g1[2], zu1[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int i = i0 + wrow + 8 * mt + g;
+        const bool ok = i < N1;
+        z1[mt] = ok ? cp1[(size_t)2 * a.Npad + i] : 0.0;
+        b1[mt] = (CSF && ok) ? cp1[(size_t)3 * a.Npad + i] : 0.0;
+        k1[mt] = (CSF && ok) ? cp1[(size_t)4 * a.Npad + i] : 0.0;
+        g1[mt] = (CSF && ok) ? cp1[(size_t)5 * a.Npad + i] : 0.0;
+        zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
+    }
+    // z of the row whose fold entry this lane maintains (lanes 0..15: rows wrow + lane)
+    const double z1own = (lane < 16 && i0 + wrow + lane < N1) ? cp1[(size_t)2 * a.Npad + i0 + wrow + lane] : 0.0;
+    const int mtv = max(0, min(2, (N1 - (i0 + wrow) + 7) >> 3));   // valid 8-row blocks of this warp
+
+    double gb = -1.0, tb = 0.0, thr = fmax(gpre - kPreMargin * c0, 0.0), gill = -1.0;
+    int bidx = -1, flag = 0;
+    // the warp's folded threshold: thr_f = thr' of the fold entries in shared memory (0: unfolded)
+    double thr_w = -1.0, thr_f = 0.0, rthr = 0.0, cm = 0.0, al1[2] = {1.0, 1.0};
+
+    mbar_wait(&s_d1, 0u);
+
+    for (int jt = 0; jt < ntJ; jt++) {
+        const int st = jt % FT_NS;
+        const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
+        thr = fmax(thr, __longlong_as_double((long long)*(volatile unsigned long long *)&s_thr));
+        if (thr != thr_w) {
+            // adopt the threshold: this warp's 16 entries of row M of the resident tile
+            thr_w = thr;
+            const double thrp = thr - gain_c;
+            const bool fold = thrp * kFoldMax > ysq_p && thrp > 0.0;
+            rthr = fold ? 1.0 / thrp : 0.0;
+            thr_f = fold ? thrp : 0.0;
+            if (lane < 16) D1s[(size_t)M * FT_S1 + wrow + lane] = z1own * rthr;
+            const double sum = thrp + ysq_p;
+            cm = fma(kFoldEps * sum, sum * rthr, c0) * rthr;               // margin / thr'
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) al1[mt] = fma(-z1[mt] * z1[mt], rthr, 1.0);
+            __syncwarp();
+        }
+        mbar_wait(&s_full[st], (unsigned)(jt / FT_NS) & 1u);
+
+        // ---- correlation tile: 16 x 32 per warp, DMMA m8n8k4 over k ----
+        double acc[2][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+        const double *A_ = D1s + (size_t)t4 * FT_S1 + wrow + g;
+        const double *B_ = D2s + (size_t)st * rec + (size_t)t4 * FT_S2 + g;
+        const int ntv = min(4, (N2 - jr * FT_TJ + 7) >> 3);
+        if (ntv == 4 && mtv == 2) {
+#pragma unroll 3
+            for (int ks = 0; ks < Mp / 4; ks++) {
+                double af[2], bf[4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                     : "d"(af[mt]), "d"(bf[nt]));
+            }
+        } else {
+#pragma unroll 1
+            for (int ks = 0; ks < Mp / 4; ks++) {
+                double af[2], bf[4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+                        if (mt < mtv && nt < ntv)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                         : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                                         : "d"(af[mt]), "d"(bf[nt]));
+            }
+        }
+
+        const double *cq = D2s + (size_t)st * rec + (size_t)Mp * FT_S2;     // the tile's per-atom parameters
+        unsigned hit = 0, hit1 = ~0u;
+        if (thr_f > 0.0) {
+            // ---- level 1: folded screen, thr' (rho~^2 - alpha1 alpha2) >= -margin ----
+            hit1 = 0;
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const double2 zq = *reinterpret_cast<const double2 *>(cq + 5 * FT_TJ + 8 * nt + 2 * t4);
+                const double a2[2] = {fma(-zq.x, rthr, 1.0), fma(-zq.y, rthr, 1.0)};
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        const double rt = acc[mt][nt][e];
+                        const double t = fma(-al1[mt], a2[e], fma(rt, rt, cm));
+                        if (__double2hiint(t) >= 0) hit1 |= 1u << (nt * 4 + e * 2 + mt);
+                    }
+            }
+        }
+        if (__any_sync(0xffffffffu, hit1 != 0)) {
+            // ---- level 2: closed-form NNLS screen on rho recovered with the very products the
+            // fold rows hold, current threshold, straight-line over the thread's 16 pairs ----
+            if (thr_f > 0.0) {
+                const double bz[2] = {z1[0] * rthr, z1[1] * rthr};
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++)
+                            acc[mt][nt][e] = fma(bz[mt], e ? z2v.y : z2v.x, acc[mt][nt][e]);
+                }
+            }
+            if (!CSF) {
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) {
+                            const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x;
+                            const double w1 = fma(-rho, z2, z1[mt]);
+                            const double w2 = fma(-rho, z1[mt], z2);
+                            const double det = fma(-rho, rho, 1.0);
+                            const double num = fma(z1[mt], w1, z2 * w2);
+                            const bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
+                            if (pos && fma(-thr, det, num) >= negc0) hit |= 1u << (nt * 4 + e * 2 + mt);
+                        }
+                }
+            } else {
+                unsigned fb = 0;   // pairs whose 3-variable solution has a non-positive weight
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
+                    const double2 b2v = *reinterpret_cast<const double2 *>(cq + FT_TJ + 8 * nt + 2 * t4);
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) {
+                            const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x, b2 = e ? b2v.y : b2v.x;
+                            const double w1 = fma(-rho, z2, z1[mt]);
+                            const double w2 = fma(-rho, z1[mt], z2);
+                            const double det = fma(-rho, rho, 1.0);
+                            const double w3 = fma(-b2, w2, fma(-b1[mt], w1, Y3 * det));
+                            const double num = fma(gain_c, det, fma(z1[mt], w1, z2 * w2));
+                            const bool pos = min(min(__double2hiint(w1), __double2hiint(w2)), __double2hiint(w3)) > 0;
+                            const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
+                            if (!pos) fb |= bit;
+                            else if (fma(-thr, det, num) >= negc0) hit |= bit;
+                        }
+                }
+                if (__any_sync(0xffffffffu, fb != 0)) {
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+                        const double2 k2v = *reinterpret_cast<const double2 *>(cq + 2 * FT_TJ + 8 * nt + 2 * t4);
+                        const double2 g2v = *reinterpret_cast<const double2 *>(cq + 3 * FT_TJ + 8 * nt + 2 * t4);
+                        const double2 zu2v = *reinterpret_cast<const double2 *>(cq + 4 * FT_TJ + 8 * nt + 2 * t4);
+#pragma unroll
+                        for (int e = 0; e < 2; e++)
+#pragma unroll
+                            for (int mt = 0; mt < 2; mt++) {
+                                const double rho = acc[mt][nt][e];
+                                const double zu2 = e ? zu2v.y : zu2v.x;
+                                const double r = fma(rho * k1[mt], e ? k2v.y : k2v.x, g1[mt] * (e ? g2v.y : g2v.x));
+                                const double v1 = fma(-r, zu2, zu1[mt]);
+                                const double v2 = fma(-r, zu1[mt], zu2);
+                                const double det = fma(-r, r, 1.0);
+                                const double num = fma(zu1[mt], v1, zu2 * v2);
+                                const bool pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
+                                const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
+                                if ((fb & bit) && pos && fma(-thr, det, num) >= negc0) hit |= bit;
+                            }
+                    }
+                }
+            }
+            // ---- rare: some lane of the warp has a competitive pair ----
+            if (__any_sync(0xffffffffu, hit != 0)) {
+                if (hit) {
+                    double rcopy[16];
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++)
+#pragma unroll
+                            for (int mt = 0; mt < 2; mt++) rcopy[nt * 4 + e * 2 + mt] = acc[mt][nt][e];
+#pragma unroll 1
+                    for (int q = 0; q < 16; q++) {
+                        if (!(hit & (1u << q))) continue;
+                        const int nt = q >> 2, e = (q >> 1) & 1, mt = q & 1;
+                        const int c = 8 * nt + 2 * t4 + e;
+                        double num, det, re, za, zb, gadd;
+                        if (!pair_gain<CSF>(rcopy[q], mt ? z1[1] : z1[0], cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
+                                            mt ? k1[1] : k1[0], cq[2 * FT_TJ + c], mt ? g1[1] : g1[0],
+                                            cq[3 * FT_TJ + c], mt ? zu1[1] : zu1[0], cq[4 * FT_TJ + c], Y3, gain_c,
+                                            num, det, re, za, zb, gadd))
+                            continue;
+                        if (!(det > 1e-12)) { gill = INFINITY; continue; }   // numerically singular
+                        const double rdet = 1.0 / det;
+                        double gq = num * rdet, tq = c0 * rdet;
+                        if (!(gq + tq >= thr)) continue;
+                        refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
+                        if (tq > kIllTol * c0) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
+                        if (gq > gb) {
+                            flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
+                            gb = gq; tb = tq;
+                            bidx = (i0 + wrow + 8 * mt + g) * N2 + jr * FT_TJ + c;
+                        } else if (!(gb > gq + wide)) {
+                            flag = 1;
+                        }
+                    }
+                }
+                double lb = bidx >= 0 ? gb - tb : 0.0;               // certified lower bound
+                for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+                if (lb > thr) {
+                    thr = lb;
+                    if (lane == 0) {
+                        atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
+                        atomicMax(vthr, (unsigned long long)__double_as_longlong(lb));
+                    }
+                }
+            }
+        }
+        // the record (tile + parameters) is consumed
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
     }
 
     // ---- reduction over the consumer threads: best gain, tie -> lower index ----
@@ -936,19 +1389,6 @@ __global__ void __launch_bounds__(256) k_normalize(FastArgs a)
     }
 }
 
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(d), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(b) : "memory");
-}
 
 // STORE: also write the normalised correlation tile to R[job] (the triple scan reads it).
 template <int CSF, int STORE>
@@ -1581,6 +2021,7 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
         if (a.t_idx[o] >= 0 && a.t_gain[o] + a.t_tol[o] >= G - tolG) { certain = false; reason = 2; }
     }
     if (certain && !(G - tolG > g2 + 16.0 * c0)) { certain = false; reason = 3; }
+    if (certain && fmax(fmax(vp[12], vp[13]), vp[14]) < kCramerScaleMin) { certain = false; reason = 3; }
     if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     if (certain) {
@@ -1620,6 +2061,8 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
     }
     // pair-independent branches (single atoms, atom + CSF, CSF alone) must be clearly worse
     if (certain && !(G - tolG > gpre + 16.0 * c0)) { certain = false; reason = 3; }
+    // three-block voxels of tiny magnitude: the reference's absolute tolerance decides (kCramerScaleMin)
+    if (certain && a.csf && fmax(vp[12], vp[13]) < kCramerScaleMin) { certain = false; reason = 3; }
     if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     if (certain) {
@@ -1733,6 +2176,10 @@ size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V, int src, int shared_
     s += 3 * al256(sizeof(double) * V * g.ntI);
     s += 2 * al256(sizeof(int) * V * g.ntI);
     if (g.gemm) s += al256(sizeof(double) * (shared_dict ? 1 : V) * (size_t)g.Mp2 * g.ldn);
+    else {      // tile-major prepared copies of k_fast_tiles
+        s += al256(sizeof(double) * V * (size_t)g.ntI * g.Mp * FT_S1);
+        s += al256(sizeof(double) * V * (size_t)((N2 + FT_TJ - 1) / FT_TJ) * FT2_REC(g.Mp));
+    }
     return s;
 }
 
@@ -1781,6 +2228,13 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     a.cta_idx = (int *)q; q += al256(sizeof(int) * V * a.ntI);
     a.cta_flag = (int *)q; q += al256(sizeof(int) * V * a.ntI);
     a.Dn = g.gemm ? (double *)q : nullptr;
+    a.nt2 = (fp.N2 + FT_TJ - 1) / FT_TJ;
+    if (!g.gemm) {
+        a.d1c_stride = (int64_t)g.ntI * g.Mp * FT_S1;
+        a.d2c_stride = (int64_t)a.nt2 * (int64_t)FT2_REC(g.Mp);
+        a.D1c = (double *)q; q += al256(sizeof(double) * V * (size_t)a.d1c_stride);
+        a.D2c = (double *)q; q += al256(sizeof(double) * V * (size_t)a.d2c_stride);
+    }
     a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count; a.reasons = reasons;
 
     const size_t smem_prep = sizeof(double) * (4 * p.M + 32) + sizeof(int) * 2 * p.M;
@@ -1801,6 +2255,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         b.cta_gain += v0 * a.ntI; b.cta_tol += v0 * a.ntI; b.cta_ill += v0 * a.ntI;
         b.cta_idx += v0 * a.ntI; b.cta_flag += v0 * a.ntI;
         if (b.Dn) b.Dn += v0 * a.dn_stride;
+        if (b.D1c) { b.D1c += v0 * a.d1c_stride; b.D2c += v0 * a.d2c_stride; }
         if (vox_list) b.vox_list = vox_list + v0;
         else { b.y = y + v0 * p.M; b.tuple = tuple + v0; }
         if (fp.A && (!vox_list || fp.a_by_local)) b.A = fp.A + v0 * fp.strideA;
@@ -1826,21 +2281,19 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         }
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     } else {
-        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * a.Mp * FT_S2 + FT_CQ * FT_NQ * FT_TJ +
-                                              FT_CQ * 2 + 5 * a.Mp + 64) + sizeof(int) * 4 * a.Mp;
-        if (smem + 64 > 227 * 1024) {
+        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * FT2_REC(a.Mp) + 64);
+        if (smem + 128 > 227 * 1024) {
             set_error("fast tier: tile does not fit in shared memory");
             return MFB_EUNSUPPORTED;
         }
         // per device / context attribute: set on every launch (microseconds)
-        void (*kern)(FastArgs) = fp.csf ? (fp.src ? k_fast_pairs<1, 1> : k_fast_pairs<1, 0>)
-                                        : (fp.src ? k_fast_pairs<0, 1> : k_fast_pairs<0, 0>);
+        void (*kern)(FastArgs) = fp.csf ? k_fast_tiles<1> : k_fast_tiles<0>;
         MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(k_fast_seed, (unsigned)V, 32, 0, st, a);
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
         for (int64_t v0 = 0; v0 < V; v0 += maxy) {
             const int64_t nv = V - v0 < maxy ? V - v0 : maxy;
-            MFB_LAUNCH(kern, dim3(a.ntI, (unsigned)nv), FT_THREADS, smem, st, shifted(v0));
+            MFB_LAUNCH(kern, dim3(a.ntI, (unsigned)nv), FT2_THREADS, smem, st, shifted(v0));
         }
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     }

@@ -587,6 +587,24 @@ def _triple_problem(sizes, M, V, seed, planted=3, signed=False):
     return A, Y
 
 
+@pytest.mark.parametrize("sizes,M", [([40, 36, 1], 60), ([30, 28, 26], 60), ([140, 120, 1], 130)])
+@pytest.mark.parametrize("scale", [1e-4, 1e-3])
+def test_solve_batch_tiny_magnitude_follows_reference_tolerance(sizes, M, scale):
+    """The reference's three-block solver accepts Cramer numerators D_i >= -tol with an ABSOLUTE
+    tol = 2.2204e-14 (mf_utils.py:562): when A and y are scaled down so that |a|^4 |a.y|
+    approaches tol it returns solutions with negative weights.  The screening tiers must hand
+    such voxels to the reference-order tier: results equal the exact tier and the CPU oracle."""
+    A, Y = _triple_problem(sizes, M, 10, 1000 + sum(sizes), planted=2, signed=True)
+    A, Y = A * scale, Y * scale
+    fast = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes))
+    exact = mfu.solve_exhaustive_posweights_batch(A, Y, np.asarray(sizes), exact=True)
+    for f, e in zip(fast, exact):
+        assert np.array_equal(f, e)
+    for v in range(4):
+        wo, subo, toto, objo, _ = orc.solve(A[v], Y[v], sizes)
+        assert np.array_equal(fast[1][v], subo) and np.array_equal(fast[0][v], wo) and fast[3][v] == objo
+
+
 @pytest.mark.parametrize("sizes,M,planted,signed", [([60, 70, 50], 100, 3, False), ([300, 300, 300], 100, 3, False),
                                                     ([90, 90, 6], 105, 3, False), ([33, 47, 129], 150, 3, False),
                                                     ([64, 64, 64], 60, 2, False), ([50, 40, 30], 80, 3, True)])
