@@ -9,13 +9,14 @@
 //                  reduces the best single-atom / atom+CSF gains (the pair-independent
 //                  branches of the NNLS) and the atoms holding them;
 //   k_fast_seed    seeds the voxel-wide screening threshold with one real pair;
-//   k_fast_pairs   M <= 112.  One CTA per (voxel, 128-atom i1 tile): the rotated,
-//                  CSF-projected and normalised i1 tile stays resident in shared memory, four
-//                  producer warps gather i2 tiles of 32 atoms from the L2-resident lookup table
-//                  (or from explicit dictionaries) into an mbarrier ring, eight consumer warps
-//                  form the correlation tile with FP64 tensor-core DMMA (mma.sync.m8n8k4.f64)
-//                  and consume it in registers by a division-free closed-form NNLS + argmax
-//                  epilogue;
+//   k_fast_tiles   M <= 111.  One CTA per (voxel, 128-atom i1 tile): the rotated, CSF-projected and
+//                  normalised i1 tile is built once in shared memory; the i2 tiles of 32 atoms come
+//                  from a tile-major copy prepared by k_fast_prep and are moved by ONE elected
+//                  thread with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a
+//                  3-stage ring; eight consumer warps form the correlation tile with FP64
+//                  tensor-core DMMA (mma.sync.m8n8k4.f64) and screen it in registers: the
+//                  unconstrained-gain test is folded into the DMMA stream (row M of the tiles), the
+//                  closed-form NNLS + argmax epilogue runs only for warps with a passing pair;
 //   k_normalize + k_gemm_pairs   any M.  Both operands streamed through a k-chunked ring by
 //                  TMA bulk copies (cp.async.bulk + mbarrier complete_tx) from a normalised
 //                  copy of the dictionaries; same epilogue.  With STORE it also writes the
@@ -41,10 +42,7 @@ namespace mfb {
 #define FT_TI 128
 #define FT_TJ 32
 #define FT_CONS 256         // consumer threads (8 DMMA warps)
-#define FT_PROD 128         // producer threads (4 gather warps)
-#define FT_THREADS (FT_CONS + FT_PROD)
 #define FT_NS 3             // stages of the i2-tile ring
-#define FT_CQ (2 * FT_NS)   // slots of the per-atom parameter ring (outlives the tile's stage)
 #define FT_S1 (FT_TI + 4)  // row strides: == 4 mod 16 doubles -> conflict-free fragment loads
 #define FT_S2 (FT_TJ + 4)
 #define FT_NQ 6            // rows of a colq slot: z, beta, kappa, gamma, zu, alpha2 (folded screen)
@@ -123,12 +121,13 @@ struct FastArgs {
     const double *y;
     int *ip_rows;      // [v][2][M][2]  rl, rh
     double *ip_w;      // [v][2][M][2]  wl, wh
-    // tile-major prepared copies for k_fast_tiles (written by k_fast_prep): per voxel, the
-    // rotated / CSF-projected / normalised atoms laid out exactly as the kernel's shared-memory
-    // tiles, so that one TMA bulk copy moves a whole tile
-    double *D1c;       // [v][i1 tile][Mp][FT_S1]
+    // tile-major prepared copy of the STREAMED block for k_fast_tiles (written by k_fast_prep):
+    // per voxel, the rotated / CSF-projected / normalised atoms of block 2 laid out exactly as
+    // the kernel's shared-memory tiles, so that one TMA bulk copy moves a whole tile; the 8 CTAs
+    // of a voxel read it through the L2.  (The resident i1 tile is used by ONE CTA: it is built
+    // in place by that CTA, a prepared copy would only add HBM traffic.)
     double *D2c;       // [v][i2 tile][Mp][FT_S2] + [FT_NQ][FT_TJ] per-atom parameters
-    int64_t d1c_stride, d2c_stride;   // doubles per voxel
+    int64_t d2c_stride;   // doubles per voxel
     int nt2;           // i2 tiles per voxel
     double *colp;      // [v][2][FT_NPAR][Npad]
     double *voxp;      // [v][FT_VP]  (slots 12..14: magnitude of the Cramer numerators of block 0..2, see kCramerScaleMin)
@@ -236,7 +235,7 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
     double gbest = 0.0, sqmax = 0.0, dymax = 0.0;
     int ibest = 0;
     // atoms up to the end of the block's last tile (the prepared copies hold whole tiles)
-    const int iend = !a.D1c ? a.Npad : (k == 0 ? a.ntI * FT_TI : a.nt2 * FT_TJ);
+    const int iend = (a.D2c && k == 1) ? a.nt2 * FT_TJ : a.Npad;
     for (int i = threadIdx.x; i < iend; i += blockDim.x) {
         double par[FT_NPAR] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (i < Nk) {
@@ -278,14 +277,12 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
         }
         if (i < a.Npad)
             for (int q = 0; q < FT_NPAR; q++) cp[(size_t)q * a.Npad + i] = par[q];
-        if (a.D1c && k < 2) {
+        if (a.D2c && k == 1) {
             // second pass over the measurements: the atom as the pair kernel multiplies it
             // (rotated, off the CSF column, unit norm), written into its tile; rows M.. of a
-            // tile: the folded-screen row (-z for the streamed block, filled per warp in shared
-            // memory for the resident block) and zero padding
-            const int T = k == 0 ? FT_TI : FT_TJ, S = k == 0 ? FT_S1 : FT_S2;
-            const size_t rec = (size_t)a.Mp * S + (k == 0 ? 0 : FT_NQ * FT_TJ);
-            double *dc = (k == 0 ? a.D1c + v * a.d1c_stride : a.D2c + v * a.d2c_stride) + (size_t)(i / T) * rec + (i % T);
+            // tile: the folded-screen row (-z) and zero padding; then the tile's parameters
+            const size_t rec = (size_t)a.Mp * FT_S2 + FT_NQ * FT_TJ;
+            double *dc = a.D2c + v * a.d2c_stride + (size_t)(i / FT_TJ) * rec + (i % FT_TJ);
             const double *Ac = a.src ? Ar + a.startb[k] + i : nullptr;
             const double scl = par[0], al = par[1];
             for (int m = 0; m < M; m++) {
@@ -296,14 +293,12 @@ __global__ void __launch_bounds__(256) k_fast_prep(FastArgs a)
                     if (a.csf) d = fma(-al, cs[m], d);
                     val = d * scl;
                 }
-                dc[(size_t)m * S] = val;
+                dc[(size_t)m * FT_S2] = val;
             }
-            for (int m = M; m < a.Mp; m++) dc[(size_t)m * S] = (m == M && k == 1) ? -par[2] : 0.0;
-            if (k == 1) {
-                double *pq = dc + (size_t)a.Mp * S;      // [FT_NQ][FT_TJ]: z, beta, kappa, gamma, zu, z^2
-                for (int q = 0; q < 5; q++) pq[q * FT_TJ] = par[2 + q];
-                pq[5 * FT_TJ] = par[2] * par[2];
-            }
+            for (int m = M; m < a.Mp; m++) dc[(size_t)m * FT_S2] = m == M ? -par[2] : 0.0;
+            double *pq = dc + (size_t)a.Mp * FT_S2;      // [FT_NQ][FT_TJ]: z, beta, kappa, gamma, zu, z^2
+            for (int q = 0; q < 5; q++) pq[q * FT_TJ] = par[2 + q];
+            pq[5 * FT_TJ] = par[2] * par[2];
         }
     }
     const double gmine = gbest;
@@ -477,32 +472,50 @@ __global__ void __launch_bounds__(32) k_fast_seed(FastArgs a)
     }
 }
 
-// Warp-specialised pair scan.  Warps 0..7 (consumers): DMMA correlation tile + closed-form
-// epilogue; warps 8..11 (producers): gather the next i2 tiles from the L2-resident lookup
-// table, rotate / project / normalise them and fill a 3-stage shared-memory ring.  full[] /
-// empty[] mbarriers are the only synchronisation inside the tile loop, so consumer warps
-// drift apart and one warp's scalar epilogue overlaps another warp's DMMA stream.
+// ---------------------------------------------------------------------------------
+// k_fast_tiles: the pair scan for M <= 111.  One CTA per (voxel, 128-atom i1 tile); the i1 tile
+// (rotated from the L2-resident lookup table or read from explicit dictionaries, projected off
+// the CSF column, unit-normalised) is built once in shared memory by the CTA that uses it; the
+// 32-atom i2 tiles are streamed through a 3-stage ring; eight consumer warps form a 16 x 32
+// correlation tile each with FP64 tensor-core DMMA (m8n8k4, 27 k-steps at M = 105).
+//   * Nothing is gathered or computed on the producer side: ONE elected thread moves every i2
+//     tile and its per-atom parameters with one TMA bulk copy (cp.async.bulk + mbarrier
+//     complete_tx) from the tile-major copy k_fast_prep wrote, which the 8 CTAs of a voxel
+//     share through the L2.  (The round-1 kernel gathered and blended the i2 tiles with four
+//     producer warps in every CTA: a select added to their store pass cost 12 % of the kernel,
+//     DESIGN.md section 8 -- the producers, not the DMMA stream, set its pace.)
+//   * The screen is folded into the DMMA stream with a WARP-PRIVATE threshold: row M of the
+//     streamed tiles holds -z2_j, and every consumer warp keeps z1_i / thr' in ITS 16 columns
+//     of row M of the resident tile (no other warp reads those columns), rewriting them
+//     whenever it adopts a higher threshold.  The accumulators then deliver
+//     rho~ = rho - z1 z2 / thr' and, with alpha = 1 - z^2 / thr',
+//         z1^2 + z2^2 - 2 rho z1 z2 - thr' (1 - rho^2)  =  thr' (rho~^2 - alpha1 alpha2),
+//     the unconstrained least-squares gain test of the pair's columns (+ CSF), which is
+//     NECESSARY for any solution on a subset of those columns to reach the threshold: about
+//     2.5 FP64 operations and a sign test per pair (the round-1 screen: 7 to 11).  Only warps in
+//     which some pair passes run the closed-form NNLS screen (signs of the weights, 2-column
+//     sub-problems, current threshold) on the recovered rho, and from there the
+//     competitive-pair path (refined error bounds, certified lower bound -> threshold).
+// ---------------------------------------------------------------------------------
+#define FT2_THREADS (FT_CONS + 32)
+#define FT2_REC(Mp) ((size_t)(Mp) * FT_S2 + FT_NQ * FT_TJ)      // doubles per streamed tile record
+
 template <int CSF, int SRC>
-__global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
+__global__ void __launch_bounds__(FT2_THREADS, 1) k_fast_tiles(FastArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     const DevPlan &p = a.p;
     const int M = p.M, N = p.N, Mp = a.Mp;
     const int N1 = a.N1, N2 = a.N2;
+    const size_t rec = FT2_REC(Mp);
     double *D1s = smem;                                   // [Mp][FT_S1]
-    double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS][Mp][FT_S2]
-    double *colq = D2s + (size_t)FT_NS * Mp * FT_S2;      // [FT_CQ][FT_NQ][FT_TJ]  z, beta, kappa, gamma, zu, alpha2
-    double *tq = colq + FT_CQ * FT_NQ * FT_TJ;            // [FT_CQ][2]  threshold folded into the tile, its reciprocal
-    double *w1l = tq + FT_CQ * 2;                         // [Mp] plan of fascicle 1
+    double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS] records: [Mp][FT_S2] | [FT_NQ][FT_TJ]
+    double *w1l = D2s + (size_t)FT_NS * rec;              // [Mp] plan of fascicle 1
     double *w1h = w1l + Mp;
-    double *w2l = w1h + Mp;                               // [Mp] plan of fascicle 2
-    double *w2h = w2l + Mp;
-    double *cs = w2h + Mp;                                // [Mp] csf column
+    double *cs = w1h + Mp;                                // [Mp] csf column
     double *red = cs + Mp;                                // [64]
     int *r1l = (int *)(red + 64);
     int *r1h = r1l + Mp;
-    int *r2l = r1h + Mp;
-    int *r2h = r2l + Mp;
     __shared__ unsigned long long s_thr;                  // CTA-wide lower bound on the winning gain
     __shared__ unsigned long long s_full[FT_NS], s_empty[FT_NS];
     __shared__ double s_tolG;
@@ -517,127 +530,49 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const double ysq_p = fmax(vp[0] - gain_c, 0.0);       // energy of y off the CSF column
     const double gpre = fmax(vp[5], vp[6]);
     const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
-    const double *cp2 = a.colp + (v * 2 + 1) * (int64_t)FT_NPAR * a.Npad;
-    const int ntJ = (N2 + FT_TJ - 1) / FT_TJ;
-    // the i2 scan starts at the tile of block 2's best single atom and wraps around: on smooth
-    // dictionaries strong pairs are met early, the screening threshold rises at once and the
-    // competitive-pair path stays rare
-    const int jt0 = min(ntJ - 1, max(0, (int)vp[9]) / FT_TJ);
-    unsigned long long *vthr = a.vthr + v;                // threshold shared by the voxel's CTAs
+    const int ntJ = a.nt2;
+    const int jt0 = min(ntJ - 1, max(0, (int)vp[9]) / FT_TJ);   // scan starts at block 2's best single atom
+    unsigned long long *vthr = a.vthr + v;
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     const double *Ar = SRC ? a.A + (a.a_by_local ? v : row) * a.strideA : nullptr;
 
-    for (int m = tid; m < Mp; m += FT_THREADS) {
+    for (int m = tid; m < Mp; m += FT2_THREADS) {
         if (m < M && SRC) {
             // explicit dictionaries: rows are read directly (weights 1 / 0, row index = m)
-            r1l[m] = r1h[m] = r2l[m] = r2h[m] = m;
-            w1l[m] = w2l[m] = 0.0; w1h[m] = w2h[m] = 1.0;
+            r1l[m] = r1h[m] = m;
+            w1l[m] = 0.0; w1h[m] = 1.0;
             cs[m] = CSF ? Ar[(size_t)m * a.lda + a.start3] : 0.0;
         } else if (m < M) {
-            int64_t o = ((v * 2 + 0) * M + m) * 2, o2 = ((v * 2 + 1) * M + m) * 2;
+            const int64_t o = ((v * 2 + 0) * M + m) * 2;
             r1l[m] = a.ip_rows[o]; r1h[m] = a.ip_rows[o + 1];
             w1l[m] = a.ip_w[o]; w1h[m] = a.ip_w[o + 1];
-            r2l[m] = a.ip_rows[o2]; r2h[m] = a.ip_rows[o2 + 1];
-            w2l[m] = a.ip_w[o2]; w2h[m] = a.ip_w[o2 + 1];
             cs[m] = CSF ? p.sig_csf[m] : 0.0;
         } else {
-            r1l[m] = r1h[m] = r2l[m] = r2h[m] = 0;
-            w1l[m] = w1h[m] = w2l[m] = w2h[m] = 0.0; cs[m] = 0.0;
+            r1l[m] = r1h[m] = 0;
+            w1l[m] = w1h[m] = 0.0; cs[m] = 0.0;
         }
     }
     if (tid == 0) {
         s_thr = max((unsigned long long)__double_as_longlong(fmax(gpre - kPreMargin * c0, 0.0)),
                     *(volatile unsigned long long *)vthr);
         s_flag = 0;
-        for (int st = 0; st < FT_NS; st++) { mbar_init(&s_full[st], FT_PROD); mbar_init(&s_empty[st], FT_CONS); }
+        for (int st = 0; st < FT_NS; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], FT_CONS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (tid >= FT_CONS) {
-        // =========================== producers ===========================
-        const int pt = tid - FT_CONS;
-        const int jj = pt & (FT_TJ - 1);
-        const int mrow0 = pt / FT_TJ;                     // 0..FT_PROD/32-1
-        constexpr int RS = FT_PROD / FT_TJ;               // rows per pass
-        constexpr int UB = 14;                            // (lo, hi) pairs in flight per thread
-        for (int jt = 0; jt < ntJ; jt++) {
-            const int st = jt % FT_NS;
-            if (FT_DEBUG(a, 2) && jt >= FT_NS) {
-                mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
-                mbar_arrive(&s_full[st]);
-                continue;
+        // ============ producer: one thread, one bulk copy per tile ============
+        if (lane == 0) {
+            const double *src2 = a.D2c + v * a.d2c_stride;
+            for (int jt = 0; jt < ntJ; jt++) {
+                const int st = jt % FT_NS;
+                if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
+                const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
+                atomicMax(&s_thr, *(volatile unsigned long long *)vthr);   // thresholds of the voxel's other CTAs
+                mbar_expect_tx(&s_full[st], (unsigned)(rec * sizeof(double)));
+                bulk_g2s(D2s + (size_t)st * rec, src2 + (size_t)jr * rec, (unsigned)(rec * sizeof(double)), &s_full[st]);
             }
-            // The fold row's values are prepared BEFORE waiting for the stage to be released (their
-            // latency overlaps the consumers' work on the previous tiles) and stored after the
-            // tile's own rows by a separate store: the tile loop below is latency-critical -- a
-            // select inside its store pass alone costs 12 % of the kernel -- and stays untouched.
-            const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
-            if (pt == 0) atomicMax(&s_thr, *(volatile unsigned long long *)vthr);
-            const int j = jr * FT_TJ + jj;
-            const bool ok = j < N2;
-            const double csc = ok ? __ldg(cp2 + j) : 0.0;
-            const double cal = (CSF && ok) ? __ldg(cp2 + (size_t)a.Npad + j) : 0.0;
-            // source rows: lookup table (stride N) or this voxel's dictionary (stride lda)
-            const double *Tc = SRC ? Ar + a.start2 + (ok ? j : 0) : p.table + (ok ? j : 0);
-            const size_t rs = SRC ? (size_t)a.lda : (size_t)N;
-            double *dst = D2s + (size_t)st * Mp * FT_S2 + jj;
-            // Folded screen (see the consumers): the warp that owns row M of the tile snapshots the
-            // threshold and writes  -z2_j / thr'  there, so that the DMMA stream itself delivers
-            // rho~ = rho - z1 z2 / thr'  (row M of the resident i1 tile holds z1_i).  thr' is the
-            // threshold minus the CSF share of the gain; when it is too small a fraction of the
-            // (projected) signal energy the fold would amplify rounding errors: the row stays zero
-            // and the consumers run the unfolded closed form on rho.
-            double brow = 0.0;
-            if (mrow0 == M % RS) {
-                const double thr_now = __longlong_as_double((long long)*(volatile unsigned long long *)&s_thr);
-                const double thrp = thr_now - gain_c;
-                const bool fold = thrp * kFoldMax > ysq_p && thrp > 0.0 && !FT_DEBUG(a, 16);
-                const double rthr = fold ? 1.0 / thrp : 0.0;
-                const double z2j = ok ? __ldg(cp2 + (size_t)2 * a.Npad + j) : 0.0;
-                brow = -z2j * rthr;
-                // (the slots of the parameter ring were released two stage generations ago)
-                colq[((jt % FT_CQ) * FT_NQ + 5) * FT_TJ + jj] = fma(z2j, brow, 1.0);   // alpha2 = 1 - z2^2 / thr'
-                if (jj == 0) { tq[(jt % FT_CQ) * 2] = fold ? thrp : 0.0; tq[(jt % FT_CQ) * 2 + 1] = rthr; }
-            }
-            if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
-            for (int mb = mrow0; mb < Mp; mb += RS * UB) {
-                double lo[UB], hi[UB];
-#pragma unroll
-                for (int q = 0; q < UB; q++) {
-                    const int m = min(mb + RS * q, Mp - 1);   // rows >= M carry zero weights
-                    if (SRC) {                                 // explicit dictionary: row m itself
-                        lo[q] = 0.0;
-                        hi[q] = __ldg(Tc + (size_t)min(m, M - 1) * rs);
-                    } else {
-                        lo[q] = __ldg(Tc + (size_t)r2l[m] * rs);
-                        hi[q] = __ldg(Tc + (size_t)r2h[m] * rs);
-                    }
-                }
-                // three passes of independent FP64 ops (the FP64 pipe is shared with the
-                // consumers' DMMA stream: dependent chains would serialise on its latency)
-                if (!SRC) {
-#pragma unroll
-                    for (int q = 0; q < UB; q++) lo[q] *= w2l[min(mb + RS * q, Mp - 1)];
-                }
-#pragma unroll
-                for (int q = 0; q < UB; q++) {
-                    const int m = min(mb + RS * q, Mp - 1);
-                    hi[q] = SRC ? w2h[m] * hi[q] : fma(w2h[m], hi[q], lo[q]);   // w2h = 0 on padding rows
-                    if (CSF) hi[q] = fma(-cal, cs[m], hi[q]);
-                }
-#pragma unroll
-                for (int q = 0; q < UB; q++) hi[q] *= csc;
-#pragma unroll
-                for (int q = 0; q < UB; q++) {
-                    const int m = mb + RS * q;
-                    if (m < Mp) dst[(size_t)m * FT_S2] = hi[q];
-                }
-            }
-            if (mrow0 == M % RS) dst[(size_t)M * FT_S2] = brow;      // after this thread's zero for row M
-            for (int e = pt; e < 5 * FT_TJ; e += FT_PROD)
-                colq[((jt % FT_CQ) * FT_NQ + e / FT_TJ) * FT_TJ + (e % FT_TJ)] =
-                    __ldg(cp2 + (size_t)(e / FT_TJ + 2) * a.Npad + jr * FT_TJ + (e % FT_TJ));
-            mbar_arrive(&s_full[st]);
         }
         return;
     }
@@ -647,14 +582,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
     const double wide = 4.0 * kIllTol * c0;
     const double c1 = kC0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
     const double negc0 = -c0;
-    // ---- resident i1 tile: rotate, project out the CSF column, normalise ----
+    // ---- resident i1 tile: rotate, project out the CSF column, normalise (rows >= M: zero; the
+    // warps fill their entries of row M when they adopt a threshold) ----
     {
         const int ii = tid & (FT_TI - 1);
         const int i = i0 + ii;
         const bool ok = i < N1;
         const double sc = ok ? cp1[i] : 0.0;
         const double al = (CSF && ok) ? cp1[(size_t)a.Npad + i] : 0.0;
-        const double z1row = ok ? cp1[(size_t)2 * a.Npad + i] : 0.0;   // row M: the folded-screen row
         const double *Tc = SRC ? Ar + a.start1 + (ok ? i : 0) : p.table + (ok ? i : 0);
         const size_t rs = SRC ? (size_t)a.lda : (size_t)N;
         constexpr int RS = FT_CONS / FT_TI;               // rows per pass (2)
@@ -676,394 +611,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fast_pairs(FastArgs a)
                 if (m < Mp) {
                     double d = fma(w1h[m], hi[q], w1l[m] * lo[q]);
                     if (CSF) d = fma(-al, cs[m], d);
-                    D1s[(size_t)m * FT_S1 + ii] = m == M ? z1row : d * sc;
+                    D1s[(size_t)m * FT_S1 + ii] = d * sc;
                 }
             }
         }
     }
     consumer_sync();
-
-    // ---- per-thread row constants (rows g and g+8 of the warp's 16-row slab) ----
-    const int wrow = warp * 16;
-    double z1[2], b1[2], k1[2], g1[2], zu1[2];
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++) {
-        const int i = i0 + wrow + 8 * mt + g;
-        const bool ok = i < N1;
-        z1[mt] = ok ? cp1[(size_t)2 * a.Npad + i] : 0.0;
-        b1[mt] = (CSF && ok) ? cp1[(size_t)3 * a.Npad + i] : 0.0;
-        k1[mt] = (CSF && ok) ? cp1[(size_t)4 * a.Npad + i] : 0.0;
-        g1[mt] = (CSF && ok) ? cp1[(size_t)5 * a.Npad + i] : 0.0;
-        zu1[mt] = (CSF && ok) ? cp1[(size_t)6 * a.Npad + i] : 0.0;
-    }
-
-    const int mtv = max(0, min(2, (N1 - (i0 + wrow) + 7) >> 3));   // valid 8-row blocks of this warp
-
-    // thread-local best (central gain gb, tolerance tb) and the shared screening threshold
-    double gb = -1.0, tb = 0.0, thr = fmax(gpre - kPreMargin * c0, 0.0), gill = -1.0;
-    int bidx = -1, flag = 0;
-
-    for (int jt = 0; jt < ntJ; jt++) {
-        const int st = jt % FT_NS;
-        const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
-        mbar_wait(&s_full[st], (unsigned)(jt / FT_NS) & 1u);
-        thr = fmax(thr, __longlong_as_double((long long)s_thr));
-
-        // ---- correlation tile: 16 x 32 per warp, DMMA m8n8k4 over k ----
-        double acc[2][4][2];
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
-        const double *A_ = D1s + (size_t)t4 * FT_S1 + wrow + g;
-        const double *B_ = D2s + (size_t)st * Mp * FT_S2 + (size_t)t4 * FT_S2 + g;
-        // 8-atom blocks of this tile that hold real atoms (warp-uniform): the last i1 / i2
-        // tiles of a dictionary whose size is not a multiple of the tile are partly empty
-        const int ntv = min(4, (N2 - jr * FT_TJ + 7) >> 3);
-        if (ntv == 4 && mtv == 2) {
-#pragma unroll 3
-            for (int ks = 0; ks < Mp / 4; ks++) {
-                double af[2], bf[4];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 4; nt++)
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                                     : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
-                                     : "d"(af[mt]), "d"(bf[nt]));
-            }
-        } else {
-#pragma unroll 1
-            for (int ks = 0; ks < Mp / 4; ks++) {
-                double af[2], bf[4];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * FT_S1 + 8 * mt];
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) bf[nt] = B_[(size_t)ks * 4 * FT_S2 + 8 * nt];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 4; nt++)
-                        if (mt < mtv && nt < ntv)
-                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                                         : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
-                                         : "d"(af[mt]), "d"(bf[nt]));
-            }
-        }
-
-        // ---- closed-form NNLS screening, branch-free over the thread's 16 pairs ----
-        // (num + c0)/det >= thr  <=>  fma(-thr, det, num) >= -c0
-        // the stage's D2 tile is consumed: release it before the scalar epilogue (the per-atom
-        // parameters live in a ring twice as deep, so the producers may run ahead meanwhile)
-        mbar_arrive(&s_empty[st]);
-        const double *cq = colq + (jt % FT_CQ) * FT_NQ * FT_TJ;
-        const double thr_t = tq[(jt % FT_CQ) * 2], rthr_t = tq[(jt % FT_CQ) * 2 + 1];
-        unsigned hit = 0, hit1 = ~0u;
-        if (thr_t > 0.0) {
-            // Level 1, folded screen.  The accumulators hold rho~ = rho - z1 z2 / thr' (row M of
-            // the tiles), and with alpha = 1 - z^2 / thr':
-            //     z1^2 + z2^2 - 2 rho z1 z2 - thr' (1 - rho^2)  =  thr' (rho~^2 - alpha1 alpha2)
-            // The left side >= -margin is NECESSARY for any solution on a subset of the pair's
-            // columns (+ CSF) to reach the threshold: the unconstrained least-squares gain of
-            // all the columns bounds every constrained one.  Two FP64 operations and a sign test
-            // per pair.  thr' is the producer's snapshot (<= the current threshold: conservative).
-            const double sum = thr_t + ysq_p;
-            const double cm = fma(kFoldEps * sum, sum * rthr_t, c0) * rthr_t;      // margin / thr'
-            double al1[2];
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++) al1[mt] = fma(-z1[mt] * z1[mt], rthr_t, 1.0);
-            hit1 = 0;
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                const double2 a2v = *reinterpret_cast<const double2 *>(cq + 5 * FT_TJ + 8 * nt + 2 * t4);
-#pragma unroll
-                for (int e = 0; e < 2; e++)
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++) {
-                        const double rt = acc[mt][nt][e];
-                        const double t = fma(-al1[mt], e ? a2v.y : a2v.x, fma(rt, rt, cm));
-                        if (__double2hiint(t) >= 0) hit1 |= 1u << (nt * 4 + e * 2 + mt);
-                    }
-            }
-        }
-        // Level 2 (only when some lane of the warp passed level 1; always on unfolded tiles):
-        // the closed-form NNLS screen with the signs of the weights, the 2-column sub-problems
-        // and the CURRENT threshold, straight-line over the thread's 16 pairs, on rho recovered
-        // with the very product the tile row holds.
-        if (!__any_sync(0xffffffffu, hit1 != 0)) continue;
-        if (FT_DEBUG(a, 8) && lane == 0) atomicAdd(&a.reasons[6], 1);   // experiment: level-2 entries (warps)
-        if (thr_t > 0.0) {
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
-#pragma unroll
-                for (int e = 0; e < 2; e++)
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++)
-                        acc[mt][nt][e] = fma(z1[mt], (e ? z2v.y : z2v.x) * rthr_t, acc[mt][nt][e]);
-            }
-        }
-        if (FT_DEBUG(a, 1)) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) sacc += acc[mt][nt][0] + acc[mt][nt][1];
-            if (sacc == 1.2345e300) hit = 1;
-        } else if (!CSF) {
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
-#pragma unroll
-                for (int e = 0; e < 2; e++)
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++) {
-                        const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x;
-                        const double w1 = fma(-rho, z2, z1[mt]);
-                        const double w2 = fma(-rho, z1[mt], z2);
-                        const double det = fma(-rho, rho, 1.0);
-                        const double num = fma(z1[mt], w1, z2 * w2);
-                        const bool pos = min(__double2hiint(w1), __double2hiint(w2)) > 0;
-                        if (pos && fma(-thr, det, num) >= negc0) hit |= 1u << (nt * 4 + e * 2 + mt);
-                    }
-            }
-        } else {
-            // pass 1: three-compartment closed form (fascicle pair projected off the CSF column)
-            unsigned fb = 0;   // pairs whose 3-variable solution has a non-positive weight
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                const double2 z2v = *reinterpret_cast<const double2 *>(cq + 8 * nt + 2 * t4);
-                const double2 b2v = *reinterpret_cast<const double2 *>(cq + FT_TJ + 8 * nt + 2 * t4);
-#pragma unroll
-                for (int e = 0; e < 2; e++)
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++) {
-                        const double rho = acc[mt][nt][e], z2 = e ? z2v.y : z2v.x, b2 = e ? b2v.y : b2v.x;
-                        const double w1 = fma(-rho, z2, z1[mt]);
-                        const double w2 = fma(-rho, z1[mt], z2);
-                        const double det = fma(-rho, rho, 1.0);
-                        const double w3 = fma(-b2, w2, fma(-b1[mt], w1, Y3 * det));
-                        const double num = fma(gain_c, det, fma(z1[mt], w1, z2 * w2));
-                        const bool pos = min(min(__double2hiint(w1), __double2hiint(w2)), __double2hiint(w3)) > 0;
-                        const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
-                        if (!pos) fb |= bit;
-                        else if (fma(-thr, det, num) >= negc0) hit |= bit;
-                    }
-            }
-            // pass 2: best 2-column sub-problem of the pairs that fell back (only the fascicle
-            // pair depends on (i1, i2); the atom + CSF ones are pair-independent, in gpre)
-            if (__any_sync(0xffffffffu, fb != 0)) {
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) {
-                    const double2 k2v = *reinterpret_cast<const double2 *>(cq + 2 * FT_TJ + 8 * nt + 2 * t4);
-                    const double2 g2v = *reinterpret_cast<const double2 *>(cq + 3 * FT_TJ + 8 * nt + 2 * t4);
-                    const double2 zu2v = *reinterpret_cast<const double2 *>(cq + 4 * FT_TJ + 8 * nt + 2 * t4);
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-#pragma unroll
-                        for (int mt = 0; mt < 2; mt++) {
-                            const double rho = acc[mt][nt][e];
-                            const double zu2 = e ? zu2v.y : zu2v.x;
-                            const double r = fma(rho * k1[mt], e ? k2v.y : k2v.x, g1[mt] * (e ? g2v.y : g2v.x));
-                            const double v1 = fma(-r, zu2, zu1[mt]);
-                            const double v2 = fma(-r, zu1[mt], zu2);
-                            const double det = fma(-r, r, 1.0);
-                            const double num = fma(zu1[mt], v1, zu2 * v2);
-                            const bool pos = min(__double2hiint(v1), __double2hiint(v2)) > 0;
-                            const unsigned bit = 1u << (nt * 4 + e * 2 + mt);
-                            if ((fb & bit) && pos && fma(-thr, det, num) >= negc0) hit |= bit;
-                        }
-                }
-            }
-        }
-        // ---- rare: some lane of the warp has a competitive pair ----
-        if (__any_sync(0xffffffffu, hit != 0)) {
-            if (FT_DEBUG(a, 8)) {   // experiment: count rare-path entries (warps) and competitive pairs
-                if (lane == 0) atomicAdd(&a.reasons[4], 1);
-                if (hit) atomicAdd(&a.reasons[5], __popc(hit));
-            }
-            if (hit) {
-                // off the hot path: one instantiation of the closed form, accumulators read
-                // back through a (local-memory) copy indexed at run time
-                double rcopy[16];
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-#pragma unroll
-                        for (int mt = 0; mt < 2; mt++) rcopy[nt * 4 + e * 2 + mt] = acc[mt][nt][e];
-#pragma unroll 1
-                for (int q = 0; q < 16; q++) {
-                    if (!(hit & (1u << q))) continue;
-                    const int nt = q >> 2, e = (q >> 1) & 1, mt = q & 1;
-                    const int c = 8 * nt + 2 * t4 + e;
-                    double num, det, re, za, zb, gadd;
-                    const double z1q = mt ? z1[1] : z1[0];
-                    if (!pair_gain<CSF>(rcopy[q], z1q, cq[c], mt ? b1[1] : b1[0], cq[FT_TJ + c],
-                                        mt ? k1[1] : k1[0], cq[2 * FT_TJ + c], mt ? g1[1] : g1[0],
-                                        cq[3 * FT_TJ + c], mt ? zu1[1] : zu1[0], cq[4 * FT_TJ + c], Y3, gain_c,
-                                        num, det, re, za, zb, gadd))
-                        continue;    // no both-positive closed form: the pair's best solution is in gpre
-                    if (!(det > 1e-12)) { gill = INFINITY; continue; }   // numerically singular
-                    const double rdet = 1.0 / det;
-                    double gq = num * rdet, tq = c0 * rdet;
-                    if (!(gq + tq >= thr)) continue;
-                    if (!FT_DEBUG(a, 4)) refine_pair(re, za, zb, gadd, rdet, c0, c1, vp[0], gq, tq);
-                    if (tq > kIllTol * c0) gill = fmax(gill, gq + tq);  // ill-conditioned: optimistic gain
-                    if (gq > gb) {
-                        flag = (bidx >= 0 && !(gq > gb + wide)) ? 1 : 0;
-                        gb = gq; tb = tq;
-                        bidx = (i0 + wrow + 8 * mt + g) * N2 + jr * FT_TJ + c;
-                    } else if (!(gb > gq + wide)) {
-                        flag = 1;
-                    }
-                }
-            }
-            double lb = bidx >= 0 ? gb - tb : 0.0;               // certified lower bound
-            for (int o = 16; o > 0; o >>= 1) lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, o));
-            if (lb > thr) {
-                thr = lb;
-                if (lane == 0) {
-                    atomicMax(&s_thr, (unsigned long long)__double_as_longlong(lb));
-                    atomicMax(vthr, (unsigned long long)__double_as_longlong(lb));
-                }
-            }
-        }
-    }
-
-    // ---- reduction over the consumer threads: best gain, tie -> lower index ----
-    const double gt = bidx >= 0 ? gb : -1.0;
-    const double tolt = bidx >= 0 ? tb : 0.0;
-    double gm = gt;
-    int im = bidx >= 0 ? bidx : INT_MAX;
-    for (int o = 16; o > 0; o >>= 1) {
-        double og = __shfl_xor_sync(0xffffffffu, gm, o);
-        int oi = __shfl_xor_sync(0xffffffffu, im, o);
-        if (og > gm || (og == gm && oi < im)) { gm = og; im = oi; }
-    }
-    for (int o = 16; o > 0; o >>= 1) gill = fmax(gill, __shfl_xor_sync(0xffffffffu, gill, o));
-    double *redg = red, *redl = red + 16;
-    int *redi = (int *)(red + 8);
-    if (lane == 0) { redg[warp] = gm; redi[warp] = im; redl[warp] = gill; }
-    consumer_sync();
-    double G = redg[0], Gill = redl[0];
-    int I = redi[0];
-    for (int w = 1; w < FT_CONS / 32; w++) {
-        if (redg[w] > G || (redg[w] == G && redi[w] < I)) { G = redg[w]; I = redi[w]; }
-        Gill = fmax(Gill, redl[w]);
-    }
-    if (bidx >= 0 && bidx == I) s_tolG = tolt;
-    consumer_sync();
-    const double tolG = I != INT_MAX ? s_tolG : 0.0;
-    if (bidx >= 0) {
-        const bool winner = bidx == I;
-        const bool close = gt + tolt >= G - tolG;
-        if ((winner && flag) || (!winner && close)) atomicOr(&s_flag, 1);
-    }
-    consumer_sync();
-    if (tid == 0) {
-        const int64_t o = v * a.ntI + tI;
-        a.cta_gain[o] = G;
-        a.cta_tol[o] = tolG;
-        a.cta_idx[o] = I == INT_MAX ? -1 : I;
-        a.cta_flag[o] = s_flag;
-        a.cta_ill[o] = Gill;
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// k_fast_tiles: the pair scan for M <= 111 on the tile-major prepared copies (k_fast_prep).
-// Same decomposition as k_fast_pairs -- one CTA per (voxel, 128-atom i1 tile), the i1 tile
-// resident in shared memory, 32-atom i2 tiles streamed through a 3-stage ring, eight consumer
-// warps (16 x 32 correlation tile each, DMMA m8n8k4) -- but
-//   * nothing is gathered or computed on the producer side: ONE elected thread moves every tile
-//     (and its per-atom parameters) with one TMA bulk copy (cp.async.bulk + mbarrier
-//     complete_tx) from the prepared copy, which the 8 CTAs of a voxel share through the L2;
-//   * the screen is folded into the DMMA stream with a WARP-PRIVATE threshold: row M of the
-//     streamed tiles holds -z2_j, and every consumer warp keeps z1_i / thr' in ITS 16 columns
-//     of row M of the resident tile (no other warp reads those columns), rewriting them
-//     whenever it adopts a higher threshold.  The accumulators then deliver
-//     rho~ = rho - z1 z2 / thr' and, with alpha = 1 - z^2 / thr',
-//         z1^2 + z2^2 - 2 rho z1 z2 - thr' (1 - rho^2)  =  thr' (rho~^2 - alpha1 alpha2),
-//     the unconstrained least-squares gain test of the pair's columns (+ CSF), which is
-//     NECESSARY for any solution on a subset of those columns to reach the threshold: about
-//     2.5 FP64 operations and a sign test per pair.  Only warps in which some pair passes run
-//     the closed-form NNLS screen of k_fast_pairs (signs of the weights, 2-column sub-problems)
-//     on the recovered rho, and from there the competitive-pair path.
-// ---------------------------------------------------------------------------------
-#define FT2_THREADS (FT_CONS + 32)
-#define FT2_REC(Mp) ((size_t)(Mp) * FT_S2 + FT_NQ * FT_TJ)      // doubles per streamed tile record
-
-template <int CSF>
-__global__ void __launch_bounds__(FT2_THREADS, 1) k_fast_tiles(FastArgs a)
-{
-    extern __shared__ __align__(16) double smem[];
-    const int M = a.p.M, Mp = a.Mp;
-    const int N1 = a.N1, N2 = a.N2;
-    const size_t rec = FT2_REC(Mp);
-    double *D1s = smem;                                   // [Mp][FT_S1]
-    double *D2s = D1s + (size_t)Mp * FT_S1;               // [FT_NS] records: [Mp][FT_S2] | [FT_NQ][FT_TJ]
-    double *red = D2s + (size_t)FT_NS * rec;              // [64]
-    __shared__ unsigned long long s_thr;                  // CTA-wide lower bound on the winning gain
-    __shared__ unsigned long long s_full[FT_NS], s_empty[FT_NS], s_d1;
-    __shared__ double s_tolG;
-    __shared__ int s_flag;
-
-    const int64_t v = blockIdx.y;
-    const int tI = blockIdx.x;
-    const int i0 = tI * FT_TI;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double *vp = a.voxp + v * FT_VP;
-    const double gain_c = vp[3], c0 = vp[4], Y3 = vp[2];
-    const double ysq_p = fmax(vp[0] - gain_c, 0.0);       // energy of y off the CSF column
-    const double gpre = fmax(vp[5], vp[6]);
-    const double *cp1 = a.colp + (v * 2 + 0) * (int64_t)FT_NPAR * a.Npad;
-    const int ntJ = a.nt2;
-    const int jt0 = min(ntJ - 1, max(0, (int)vp[9]) / FT_TJ);   // scan starts at block 2's best single atom
-    unsigned long long *vthr = a.vthr + v;
-
-    if (tid == 0) {
-        s_thr = max((unsigned long long)__double_as_longlong(fmax(gpre - kPreMargin * c0, 0.0)),
-                    *(volatile unsigned long long *)vthr);
-        s_flag = 0;
-        mbar_init(&s_d1, 1);
-        for (int st = 0; st < FT_NS; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], FT_CONS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (tid >= FT_CONS) {
-        // ============ producer: one thread, one bulk copy per tile ============
-        if (lane == 0) {
-            const double *src1 = a.D1c + v * a.d1c_stride + (size_t)tI * Mp * FT_S1;
-            const unsigned rows_per_copy = 32, nrow = (unsigned)Mp;
-            mbar_expect_tx(&s_d1, (unsigned)(nrow * FT_S1 * sizeof(double)));
-            for (unsigned r = 0; r < nrow; r += rows_per_copy) {
-                const unsigned nr = min(rows_per_copy, nrow - r);
-                bulk_g2s(D1s + (size_t)r * FT_S1, src1 + (size_t)r * FT_S1, nr * FT_S1 * (unsigned)sizeof(double), &s_d1);
-            }
-            const double *src2 = a.D2c + v * a.d2c_stride;
-            for (int jt = 0; jt < ntJ; jt++) {
-                const int st = jt % FT_NS;
-                if (jt >= FT_NS) mbar_wait(&s_empty[st], (unsigned)((jt / FT_NS) - 1) & 1u);
-                const int jr = jt + jt0 < ntJ ? jt + jt0 : jt + jt0 - ntJ;
-                atomicMax(&s_thr, *(volatile unsigned long long *)vthr);   // thresholds of the voxel's other CTAs
-                mbar_expect_tx(&s_full[st], (unsigned)(rec * sizeof(double)));
-                bulk_g2s(D2s + (size_t)st * rec, src2 + (size_t)jr * rec, (unsigned)(rec * sizeof(double)), &s_full[st]);
-            }
-        }
-        return;
-    }
-
-    // =============================== consumers ===============================
-    const int g = lane >> 2, t4 = lane & 3;
-    const double wide = 4.0 * kIllTol * c0;
-    const double c1 = kC0 * (a.p.M + 8) * 2.2204e-16;     // c0 / |y|^2 (k_fast_prep)
-    const double negc0 = -c0;
     const int wrow = warp * 16;
     double z1[2], b1[2], k1[2], g1[2], zu1[2];
 #pragma unroll
@@ -1084,8 +637,6 @@ __global__ void __launch_bounds__(FT2_THREADS, 1) k_fast_tiles(FastArgs a)
     int bidx = -1, flag = 0;
     // the warp's folded threshold: thr_f = thr' of the fold entries in shared memory (0: unfolded)
     double thr_w = -1.0, thr_f = 0.0, rthr = 0.0, cm = 0.0, al1[2] = {1.0, 1.0};
-
-    mbar_wait(&s_d1, 0u);
 
     for (int jt = 0; jt < ntJ; jt++) {
         const int st = jt % FT_NS;
@@ -1346,7 +897,7 @@ __global__ void __launch_bounds__(FT2_THREADS, 1) k_fast_tiles(FastArgs a)
 // and k_gemm_pairs streams BOTH operands through a k-chunked shared-memory ring filled by
 // TMA bulk copies (cp.async.bulk + mbarrier complete_tx, one producer warp, no FP64 work on
 // the producer side); eight consumer warps accumulate a 16 x 64 correlation tile each over
-// all k chunks with DMMA and then run the same closed-form screening as k_fast_pairs.
+// all k chunks with DMMA and then run the closed-form screening (level 2 of k_fast_tiles).
 // ---------------------------------------------------------------------------------
 #define GP_TI 128
 #define GP_TJ 64
@@ -1539,7 +1090,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
                     *reinterpret_cast<double2 *>(Rv + (size_t)(8 * mt) * a.ldr[job] + 8 * nt) =
                         make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         }
-        // ---- closed-form screening of the thread's 32 pairs (see k_fast_pairs) ----
+        // ---- closed-form screening of the thread's 32 pairs (see k_fast_tiles, level 2) ----
         __syncwarp();
         thr = fmax(thr, __longlong_as_double((long long)s_thr));
         unsigned hit = 0;
@@ -2134,7 +1685,7 @@ struct FastGeom {
 static FastGeom fast_geom(int M, int N1, int N2)
 {
     FastGeom g;
-    g.Mp = (M + 4) & ~3;               // M + 1 (the folded-screen row of k_fast_pairs) padded to 4
+    g.Mp = (M + 4) & ~3;               // M + 1 (the folded-screen row of k_fast_tiles) padded to 4
     g.gemm = g.Mp > 112;
 #ifdef MFB_EXPERIMENTS
     if (getenv("MFB_FORCE_GEMM")) g.gemm = true;
@@ -2176,10 +1727,8 @@ size_t fast_scratch_bytes(int M, int N1, int N2, int64_t V, int src, int shared_
     s += 3 * al256(sizeof(double) * V * g.ntI);
     s += 2 * al256(sizeof(int) * V * g.ntI);
     if (g.gemm) s += al256(sizeof(double) * (shared_dict ? 1 : V) * (size_t)g.Mp2 * g.ldn);
-    else {      // tile-major prepared copies of k_fast_tiles
-        s += al256(sizeof(double) * V * (size_t)g.ntI * g.Mp * FT_S1);
+    else        // tile-major prepared copy of the streamed block (k_fast_tiles)
         s += al256(sizeof(double) * V * (size_t)((N2 + FT_TJ - 1) / FT_TJ) * FT2_REC(g.Mp));
-    }
     return s;
 }
 
@@ -2230,9 +1779,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
     a.Dn = g.gemm ? (double *)q : nullptr;
     a.nt2 = (fp.N2 + FT_TJ - 1) / FT_TJ;
     if (!g.gemm) {
-        a.d1c_stride = (int64_t)g.ntI * g.Mp * FT_S1;
         a.d2c_stride = (int64_t)a.nt2 * (int64_t)FT2_REC(g.Mp);
-        a.D1c = (double *)q; q += al256(sizeof(double) * V * (size_t)a.d1c_stride);
         a.D2c = (double *)q; q += al256(sizeof(double) * V * (size_t)a.d2c_stride);
     }
     a.tuple = tuple; a.redo_list = redo_list; a.redo_count = redo_count; a.reasons = reasons;
@@ -2255,7 +1802,7 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         b.cta_gain += v0 * a.ntI; b.cta_tol += v0 * a.ntI; b.cta_ill += v0 * a.ntI;
         b.cta_idx += v0 * a.ntI; b.cta_flag += v0 * a.ntI;
         if (b.Dn) b.Dn += v0 * a.dn_stride;
-        if (b.D1c) { b.D1c += v0 * a.d1c_stride; b.D2c += v0 * a.d2c_stride; }
+        if (b.D2c) b.D2c += v0 * a.d2c_stride;
         if (vox_list) b.vox_list = vox_list + v0;
         else { b.y = y + v0 * p.M; b.tuple = tuple + v0; }
         if (fp.A && (!vox_list || fp.a_by_local)) b.A = fp.A + v0 * fp.strideA;
@@ -2281,13 +1828,15 @@ int launch_fast_search(const DevPlan &p, const FastProblem &fp, int64_t V, const
         }
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     } else {
-        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * FT2_REC(a.Mp) + 64);
+        const size_t smem = sizeof(double) * ((size_t)a.Mp * FT_S1 + (size_t)FT_NS * FT2_REC(a.Mp) + 3 * a.Mp + 64) +
+                            sizeof(int) * 2 * a.Mp;
         if (smem + 128 > 227 * 1024) {
             set_error("fast tier: tile does not fit in shared memory");
             return MFB_EUNSUPPORTED;
         }
         // per device / context attribute: set on every launch (microseconds)
-        void (*kern)(FastArgs) = fp.csf ? k_fast_tiles<1> : k_fast_tiles<0>;
+        void (*kern)(FastArgs) = fp.csf ? (fp.src ? k_fast_tiles<1, 1> : k_fast_tiles<1, 0>)
+                                        : (fp.src ? k_fast_tiles<0, 1> : k_fast_tiles<0, 0>);
         MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(k_fast_seed, (unsigned)V, 32, 0, st, a);
         if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));

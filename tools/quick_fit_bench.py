@@ -12,6 +12,7 @@ from tests.phantom import make_phantom  # noqa: E402
 
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 csf_frac = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 2     # 2: kernel bracketed by events (single stream); 0: production path
 ph = make_phantom(n_atoms=1000, n_vox=V, seed=100, frac_k=(0, 0, 1), csf_frac=csf_frac)
 msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
 plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, None)
@@ -22,7 +23,7 @@ best, ref = 1e30, None
 for rep in range(3):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    plan.fit_device(d[0], d[1], d[2], d[3], None, 2, True, False, flags=2, out=out)
+    plan.fit_device(d[0], d[1], d[2], d[3], None, 2, True, False, flags=flags, out=out)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if rep:
