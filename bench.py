@@ -87,7 +87,7 @@ def measure_fp64_peak(dev, n=8192, reps=10):
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
     ncu --set full capture (one launch), newest round first."""
-    for name in ("ncu_fast_pairs_r02_summary.txt", "ncu_fast_pairs_r01_summary.txt"):
+    for name in ("ncu_fast_tiles_r02_summary.txt", "ncu_fast_pairs_r01_summary.txt"):
         path = os.path.join(ROOT, "profiles", name)
         try:
             tot, seen = 0.0, 0
@@ -469,7 +469,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "traffic_note": "DRAM bytes of one k_fast_pairs launch (ncu capture profiles/%s); "
+                         "traffic_note": "DRAM bytes of one launch of the pair kernel (ncu capture profiles/%s: the prepared tile copy, 1.04 MB per voxel, read once through the L2); "
                                          "algorithmic HBM bytes are ~1 KB per voxel, the kernel is FP64-pipe "
                                          "bound" % traffic_src,
                          "kernel": "pair search (Gram + closed-form NNLS + argmin)",

@@ -546,8 +546,16 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
             const bool triple = et != 0;
             const int64_t lda = (bs.ntot + 1) & ~(int64_t)1;
             const int64_t strideA = (int64_t)M * lda;
+            // the blocks the triple scan searches: with the CSF column ([N, N, 1, E]) the fascicle and
+            // EAR blocks, projected off that column
+            BlockSpec bs3 = bs;
+            const int csf_col = (triple && ct) ? bs.start[2] : -1;
+            if (csf_col >= 0) {
+                bs3.nb = 3;
+                bs3.size[2] = bs.size[3]; bs3.start[2] = bs.start[3];
+            }
             auto fbytes = [&](int64_t n) {
-                return triple ? fast3_scratch_bytes(M, bs, n, 0) : fast_scratch_bytes(M, dp.N, dp.N, n, 1, 0);
+                return triple ? fast3_scratch_bytes(M, bs3, n, 0) : fast_scratch_bytes(M, dp.N, dp.N, n, 1, 0);
             };
             const size_t per_vox = (size_t)strideA * sizeof(double) + fbytes(1);
             int64_t sub = std::max<int64_t>(1, std::min<int64_t>(8192, 2 * pl->exact_budget / per_vox));
@@ -575,9 +583,9 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
                                                pl->abuf.as<double>(), lda, strideA, st));
                 cudaEvent_t *ev = timed ? next_events() : nullptr;
                 if (triple)
-                    MFB_TRY(launch_fast_search3(M, bs, pl->abuf.as<double>(), lda, strideA, ns, y, pl->fscratch.p,
+                    MFB_TRY(launch_fast_search3(M, bs3, pl->abuf.as<double>(), lda, strideA, ns, y, pl->fscratch.p,
                                                 pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev,
-                                                list + s0, 1, redo_local));
+                                                list + s0, 1, redo_local, csf_col));
                 else
                     MFB_TRY(launch_fast_search(dp, fp, ns, list + s0, peaks, pld, y, pl->fscratch.p,
                                                pl->tuple.as<long long>(), redo_list, redo_count, reasons, st, ev));

@@ -167,7 +167,10 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
                         int64_t V, const double *y, void *scratch, long long *tuple,
                         int32_t *redo_list, int32_t *redo_count, int32_t *reasons, cudaStream_t st,
                         cudaEvent_t *ev, const int32_t *vox_list = nullptr, int a_by_local = 0,
-                        int32_t *redo_local = nullptr);
+                        int32_t *redo_local = nullptr, int csf_col = -1);
+// csf_col >= 0: the three searched blocks of `bs` are projected off that single column of A (two
+// fascicles + CSF + EAR, reference `_4up`); tuples are returned in the product loop order of the
+// four blocks [N1, N2, 1, N3].
 bool fast3_supported_materialised(const DevPlan &p, int K, int csf, int ear);
 
 // ------------------------- Monte-Carlo average (mc.cu) ------------------------------

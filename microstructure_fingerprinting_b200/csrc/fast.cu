@@ -1274,6 +1274,61 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// Screening-precision NNLS of FOUR unit-norm columns (two fascicle atoms, an atom of the third
+// searched block, the CSF column) by support enumeration: G = unit-diagonal Gram (upper
+// triangle g[0..5] = 01 02 03 12 13 23), b = column . y.  Returns the best gain b_S . w_S over the
+// supports whose weights are all positive, the determinant of that support's Gram (conditioning
+// of the gain) and whether the third column is active.
+__device__ double nnls4_gain(const double *g, const double *b, double &det_best, bool &third_active)
+{
+    const int pr[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -1}};
+    double best = 0.0;
+    det_best = 1.0; third_active = false;
+#pragma unroll 1
+    for (int mask = 1; mask < 16; mask++) {
+        int id[4], n = 0;
+        for (int c = 0; c < 4; c++)
+            if (mask & (1 << c)) id[n++] = c;
+        double L[4][4], z[4], w[4], det = 1.0;
+        bool ok = true;
+        for (int i = 0; i < n && ok; i++)
+            for (int j = 0; j <= i; j++) {
+                double sacc = i == j ? 1.0 : g[pr[id[i]][id[j]]];
+                for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+                if (i == j) {
+                    if (!(sacc > 1e-14)) { ok = false; break; }
+                    det *= sacc;
+                    L[i][i] = sqrt(sacc);
+                } else {
+                    L[i][j] = sacc / L[j][j];
+                }
+            }
+        if (!ok) continue;
+        for (int i = 0; i < n; i++) {
+            double sacc = b[id[i]];
+            for (int k = 0; k < i; k++) sacc -= L[i][k] * z[k];
+            z[i] = sacc / L[i][i];
+        }
+        bool pos = true;
+        double gain = 0.0;
+        for (int i = n - 1; i >= 0; i--) {
+            double sacc = z[i];
+            for (int k = i + 1; k < n; k++) sacc -= L[k][i] * w[k];
+            w[i] = sacc / L[i][i];
+            pos = pos && w[i] > 0.0;
+            gain += b[id[i]] * w[i];
+        }
+        if (pos && gain > best) { best = gain; det_best = det; third_active = (mask & 4) != 0; }
+    }
+    return best;
+}
+
+// CSF: the three searched blocks are projected off a fourth, single-column block (two
+// fascicles + CSF + the EAR block of MFModel.fit, reference `_4up`).  The scan then tests the
+// UNCONSTRAINED gain of the projected triple against the threshold minus the CSF share -- a
+// necessary condition for any non-negative solution on the tuple's four columns -- and the
+// tuples that pass are solved exactly (nnls4_gain).
+template <int CSF>
 __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -1295,6 +1350,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
     const int tx = active ? tid % TXT : 0, ty = active ? tid / TXT : 0;
     const double *vp = a.voxp + v * FT_VP;
     const double c0 = vp[4];
+    const double gshift = CSF ? vp[3] : 0.0;      // CSF share of the gain: the projected scan works on thr - gshift
     const double *cpz1 = a.colp + ((v * 3 + 0) * (int64_t)FT_NPAR + 2) * a.Npad;
     const double *cpz2 = a.colp + ((v * 3 + 1) * (int64_t)FT_NPAR + 2) * a.Npad;
     const double *cpz3 = a.colp + ((v * 3 + 2) * (int64_t)FT_NPAR + 2) * a.Npad;
@@ -1320,7 +1376,8 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
         s_flag = 0;
     }
     // padding steps (i3 >= N3): zero correlations and z3 = -1 give D3 < 0, never a candidate
-    for (int i = tid; i < ((N3 + 3) & ~3); i += blockDim.x) z3s[i] = i < N3 ? cpz3[i] : -1.0;
+    // (CSF: the sign of D3 is not looked at; z3 = 0 and the competitive path skips the step)
+    for (int i = tid; i < ((N3 + 3) & ~3); i += blockDim.x) z3s[i] = i < N3 ? cpz3[i] : (CSF ? 0.0 : -1.0);
 
     // ---- chunk loader: rows i3 of R13^T[:, i1 tile] | R23^T[:, i2 tile] ----
     const int nchunks = (N3 + KC - 1) / KC;
@@ -1357,7 +1414,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
         for (int q = 0; q < 4; q++) z2[q] = zcol(q);
 #pragma unroll
         for (int e = 0; e < 8; e++)
-            Tp[e] = fma(th, c33[e], -fma(z1[e >> 2], U1[e], z2[e & 3] * U2[e]));
+            Tp[e] = fma(th - gshift, c33[e], -fma(z1[e >> 2], U1[e], z2[e & 3] * U2[e]));
     };
     cp_async_wait_all();
     __syncthreads();
@@ -1374,7 +1431,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
             c33[e] = fma(-r12[e], r12[e], 1.0);
             U1[e] = fma(-r12[e], zz2, zz1);
             U2[e] = fma(-r12[e], zz1, zz2);
-            Tp[e] = fma(thr, c33[e], -fma(zz1, U1[e], zz2 * U2[e]));
+            Tp[e] = fma(thr - gshift, c33[e], -fma(zz1, U1[e], zz2 * U2[e]));
         }
 
     double gb = -1.0, tb = 0.0, gill = -1.0;
@@ -1420,10 +1477,14 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                         const double q2 = fma(-r12[e], r13[p], r23[q]);
                         const double S = fma(-r23[q], q2, fma(-r13[p], q1, c33[e]));
                         const double D3 = fma(-r23[q], U2[e], fma(-r13[p], U1[e], c33[e] * z3));
-                        const double W1 = fma(-q1, D3, U1[e] * S);
-                        const double W2 = fma(-q2, D3, U2[e] * S);
                         const double t = fma(-Tp[e], S, fma(D3, D3, c0));
-                        sall &= (__double2hiint(W1) | __double2hiint(W2) | __double2hiint(D3)) | __double2hiint(t);
+                        if (CSF) {
+                            sall &= __double2hiint(t);
+                        } else {
+                            const double W1 = fma(-q1, D3, U1[e] * S);
+                            const double W2 = fma(-q2, D3, U2[e] * S);
+                            sall &= (__double2hiint(W1) | __double2hiint(W2) | __double2hiint(D3)) | __double2hiint(t);
+                        }
                     }
                 sgn[s4] = sall;
             }
@@ -1453,6 +1514,39 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                             const double S = fma(-a23, q2, fma(-a13, q1, k33));
                             const double D3 = fma(-a23, u2, fma(-a13, u1, k33 * z3));
                             const double W1 = fma(-q1, D3, u1 * S), W2 = fma(-q2, D3, u2 * S);
+                            if (CSF) {
+                                // four columns: the tuple's exact NNLS from the unprojected unit Gram
+                                if (c * KC + r >= N3) continue;
+                                if (!(fma(-Tp[e], S, fma(D3, D3, c0)) >= 0.0)) continue;
+                                const int i1 = i10 + 2 * tx + p, i2 = i20 + 4 * ty + q, i3 = c * KC + r;
+                                const double *P1 = a.colp + (v * 3 + 0) * (int64_t)FT_NPAR * a.Npad;
+                                const double *P2 = a.colp + (v * 3 + 1) * (int64_t)FT_NPAR * a.Npad;
+                                const double *P3 = a.colp + (v * 3 + 2) * (int64_t)FT_NPAR * a.Npad;
+                                const double ka = P1[(size_t)4 * a.Npad + i1], ga = P1[(size_t)5 * a.Npad + i1];
+                                const double kb = P2[(size_t)4 * a.Npad + i2], gbb = P2[(size_t)5 * a.Npad + i2];
+                                const double kc = P3[(size_t)4 * a.Npad + i3], gc = P3[(size_t)5 * a.Npad + i3];
+                                const double gg[6] = {fma(ka * kb, a12, ga * gbb), fma(ka * kc, a13, ga * gc), ga,
+                                                      fma(kb * kc, a23, gbb * gc), gbb, gc};
+                                const double bb[4] = {P1[(size_t)6 * a.Npad + i1], P2[(size_t)6 * a.Npad + i2],
+                                                      P3[(size_t)6 * a.Npad + i3], vp[2] * rsqrt(vp[1])};
+                                double dets;
+                                bool third;
+                                const double gq = nnls4_gain(gg, bb, dets, third);
+                                // a solution without the third block's atom belongs to the pair jobs (g2)
+                                if (!third) continue;
+                                const double tq = 8.0 * c0 / dets;
+                                if (!(gq + tq >= thr)) continue;
+                                if (tq > 16.0 * c0) gill = fmax(gill, gq + tq);
+                                const double wide4 = 4.0 * 16.0 * c0;
+                                if (gq > gb) {
+                                    flag = (bidx >= 0 && !(gq > gb + wide4)) ? 1 : 0;
+                                    gb = gq; tb = tq;
+                                    bidx = ((long long)i3 * N1 + i1) * N2 + i2;
+                                } else if (!(gb > gq + wide4)) {
+                                    flag = 1;
+                                }
+                                continue;
+                            }
                             if (!(W1 > 0.0 && W2 > 0.0 && D3 > 0.0)) continue;
                             const double dd = k33 * S;
                             if (!(dd > 1e-13 && S > 0.0)) { gill = INFINITY; continue; }   // numerically singular
@@ -1576,7 +1670,14 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
     if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     if (certain) {
-        a.tuple[row] = I;
+        if (a.csf) {
+            // four blocks [N1, N2, 1, N3]: product loop order of the reference's `_4up`
+            const long long N1 = a.Nb[0], N2 = a.Nb[1], N3 = a.Nb[2];
+            const long long i2 = I % N2, i1 = (I / N2) % N1, i3 = I / (N1 * N2);
+            a.tuple[row] = (i1 * N2 + i2) * N3 + i3;
+        } else {
+            a.tuple[row] = I;
+        }
     } else {
         int pos = atomicAdd(a.redo_count, 1);
         a.redo_list[pos] = (int32_t)row;
@@ -1664,7 +1765,7 @@ bool fast_supported_materialised(const DevPlan &p, int K, int csf, int ear)
 // two fascicles + the EAR block ([N, N, E]): triple scan on materialised dictionaries
 bool fast3_supported_materialised(const DevPlan &p, int K, int csf, int ear)
 {
-    return K == 2 && ear && !csf && p.sig_ear && p.E >= 2 && p.N >= 2 && p.N <= 4096 && p.M <= 16384;
+    return K == 2 && ear && (!csf || p.sig_csf) && p.sig_ear && p.E >= 2 && p.N >= 2 && p.N <= 4096 && p.M <= 16384;
 }
 
 // Explicit dictionaries (mfb_solve_batch): two searched blocks, optionally a third block of
@@ -1936,7 +2037,7 @@ size_t fast3_scratch_bytes(int M, const BlockSpec &bs, int64_t V, int shared_dic
 int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda, int64_t strideA,
                         int64_t V, const double *y, void *scratch, long long *tuple,
                         int32_t *redo_list, int32_t *redo_count, int32_t *reasons, cudaStream_t st,
-                        cudaEvent_t *ev, const int32_t *vox_list, int a_by_local, int32_t *redo_local)
+                        cudaEvent_t *ev, const int32_t *vox_list, int a_by_local, int32_t *redo_local, int csf_col)
 {
     if (V == 0) return MFB_OK;
     if (V > 65535) { set_error("triple scan: at most 65535 voxels per launch"); return MFB_EINVAL; }
@@ -1944,7 +2045,9 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     const Fast3Layout L = fast3_layout(M, bs, V, shared_dict);
     FastArgs a;
     memset(&a, 0, sizeof(a));
-    a.p.M = M; a.src = 1; a.csf = 0;
+    a.p.M = M; a.src = 1;
+    a.csf = csf_col >= 0 ? 1 : 0;        // the three searched blocks are projected off this column
+    a.start3 = csf_col >= 0 ? csf_col : 0;
     a.A = A; a.lda = lda; a.strideA = strideA;
     a.nblk = 3; a.njobs = 3; a.nsplit = 1;
     int off = 0;
@@ -1980,7 +2083,7 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[0], st));
     {
         const size_t smem = sizeof(double) * ((size_t)GP_NS * GP_STAGE + 8 * 5 * GP_TJ + 64);
-        void (*kern)(FastArgs) = k_gemm_pairs<0, 1>;
+        void (*kern)(FastArgs) = a.csf ? k_gemm_pairs<1, 1> : k_gemm_pairs<0, 1>;
         MFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(kern, dim3(a.ntI, (unsigned)V, 3), GP_THREADS, smem, st, a);
     }
@@ -1992,8 +2095,9 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
         if (kc < 4) { set_error("triple scan: third block too large for shared memory"); return MFB_EUNSUPPORTED; }
         a.tr_kc = kc;
         const size_t smem = sizeof(double) * (size_t)2 * kc * rowlen + fixed;
-        MFB_CUDA_TRY(cudaFuncSetAttribute(k_triples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MFB_LAUNCH(k_triples, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
+        void (*ktr)(FastArgs) = a.csf ? k_triples<1> : k_triples<0>;
+        MFB_CUDA_TRY(cudaFuncSetAttribute(ktr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MFB_LAUNCH(ktr, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
     }
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     MFB_LAUNCH(k_select3, (unsigned)((V + 127) / 128), 128, 0, st, a, V);

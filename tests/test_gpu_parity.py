@@ -653,6 +653,36 @@ def test_fit_two_fascicles_plus_ear_triple_scan():
     compare_rows(fast[sel], oracle_rows(ph, sel), ph, idx=sel, exact_bits=True)
 
 
+@pytest.mark.parametrize("n_atoms,n_ear,seed", [(90, 6, 33), (200, 10, 35)])
+def test_fit_two_fascicles_csf_ear_projected_triple_scan(n_atoms, n_ear, seed):
+    """[N, N, 1, E] voxels (two fascicles + CSF + EAR, mf.py:398-419 -> reference `_4up`): the
+    triple scan runs on the blocks projected off the CSF column, tuples that pass the
+    unconstrained-gain test are solved exactly by support enumeration.  Rows must equal the
+    reference-order tier's bit for bit and agree with the oracle (scipy.optimize.nnls per tuple)
+    to 1e-9; most voxels whose EAR compartment is active must be decided by the fast tier."""
+    ph = make_phantom(n_atoms=n_atoms, n_vox=240, seed=seed, frac_k=(0.0, 0.0, 1.0), csf_frac=1.0,
+                      ear=True, n_ear=n_ear, ear_frac=1.0, ear_max_k=2)
+    msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, ph.sig_ear)
+    fast = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, ph.ear, 2, True, True, flags=0)
+    st = plan.stats()
+    exact = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, ph.ear, 2, True, True, flags=1)
+    plan.close()
+    assert np.array_equal(fast, exact)
+    assert st[0] + st[1] == 240 and st[0] >= 120, st      # fast-tier share (EAR weight > 0 in every voxel)
+    sel = np.arange(0, 240, 24)
+    ref = oracle_rows(ph, sel)
+    got = fast[sel]
+    # 4 blocks: to rounding, indices wherever the weight is positive (the reference's per-tuple
+    # scipy NNLS leaves the index of a zero-weight block undetermined)
+    assert np.allclose(got[:, 0], ref[:, 0], rtol=1e-9)
+    for c in (1, 2, 5, 6):
+        assert np.allclose(got[:, c], ref[:, c], rtol=1e-9, atol=1e-12), c
+    for c_w, c_id in ((1, 3), (2, 4), (6, 7)):
+        act = (ref[:, c_w] > 1e-9) | (got[:, c_w] > 1e-9)
+        assert np.array_equal(got[act, c_id], ref[act, c_id]), c_id
+
+
 @pytest.fixture(scope="module")
 def mc_cases():
     import os
