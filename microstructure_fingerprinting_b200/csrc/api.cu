@@ -329,7 +329,15 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     // of every dictionary of the sub-batch)
     const bool no_fast = (flags & 1) != 0;
     const bool fast = fast_supported_explicit(M, bs) && !no_fast;
-    const bool fast3 = !fast && fast3_supported_explicit(M, bs) && !no_fast;
+    // three searched blocks, or [N1, N2, 1, N4]: the triple scan on blocks 1, 2, 4 projected off the
+    // single column of block 3 (two fascicles + CSF + EAR, reference `_4up`)
+    BlockSpec bs3 = bs;
+    int csf_col = -1;
+    if (bs.nb == 4 && bs.size[2] == 1) {
+        bs3.nb = 3; bs3.size[2] = bs.size[3]; bs3.start[2] = bs.start[3];
+        csf_col = bs.start[2];
+    }
+    const bool fast3 = !fast && fast3_supported_explicit(M, bs3) && !no_fast;
     const int shared_dict = strideA == 0;
     size_t per_vox = exact_scratch_bytes(1, bs) + 4096;
     size_t fixed = 0;
@@ -337,8 +345,8 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
         fixed = shared_dict ? fast_scratch_bytes(M, bs.size[0], bs.size[1], 0, 1, 1) : 0;
         per_vox = std::max(per_vox, fast_scratch_bytes(M, bs.size[0], bs.size[1], 1, 1, shared_dict) - fixed + 4096);
     } else if (fast3) {
-        fixed = shared_dict ? fast3_scratch_bytes(M, bs, 0, 1) : 0;
-        per_vox = std::max(per_vox, fast3_scratch_bytes(M, bs, 1, shared_dict) - fixed + 4096);
+        fixed = shared_dict ? fast3_scratch_bytes(M, bs3, 0, 1) : 0;
+        per_vox = std::max(per_vox, fast3_scratch_bytes(M, bs3, 1, shared_dict) - fixed + 4096);
     }
     const size_t budget = per_vox > ((size_t)1 << 20) ? (size_t)6 << 30 : (size_t)1 << 30;
     int64_t sub = std::max<int64_t>(1, std::min<int64_t>((fast || fast3) ? 8192 : 65535, budget / per_vox));
@@ -354,7 +362,7 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
     auto cleanup = [&]() {};
     size_t sbytes = exact_scratch_bytes(sub, bs);
     if (fast) sbytes = std::max(sbytes, fast_scratch_bytes(M, bs.size[0], bs.size[1], sub, 1, shared_dict));
-    if (fast3) sbytes = std::max(sbytes, fast3_scratch_bytes(M, bs, sub, shared_dict));
+    if (fast3) sbytes = std::max(sbytes, fast3_scratch_bytes(M, bs3, sub, shared_dict));
     if ((rc = scratch.ensure(sbytes)) || (rc = tuple.ensure(sizeof(long long) * sub)) ||
         (rc = asmall.ensure(sizeof(double) * sub * M * kMaxBlocks)) ||
         (rc = idx5.ensure(sizeof(int32_t) * sub * kMaxBlocks)) || (rc = w5.ensure(sizeof(double) * sub * kMaxBlocks)) ||
@@ -385,8 +393,8 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
                 rc = launch_fast_search(dummy, fp, nv, nullptr, nullptr, 0, yv, scratch.p, tuple.as<long long>(),
                                         redo_list, redo_count, reasons, st, nullptr);
             } else {
-                rc = launch_fast_search3(M, bs, Av, lda, strideA, nv, yv, scratch.p, tuple.as<long long>(),
-                                         redo_list, redo_count, reasons, st, nullptr);
+                rc = launch_fast_search3(M, bs3, Av, lda, strideA, nv, yv, scratch.p, tuple.as<long long>(),
+                                         redo_list, redo_count, reasons, st, nullptr, nullptr, 0, nullptr, csf_col);
             }
             if (rc) break;
             int32_t head[8] = {0, 0, 0, 0, 0, 0, 0, 0};

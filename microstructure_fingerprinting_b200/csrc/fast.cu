@@ -1278,12 +1278,13 @@ __device__ __forceinline__ void cp_async_wait_all()
 // searched block, the CSF column) by support enumeration: G = unit-diagonal Gram (upper
 // triangle g[0..5] = 01 02 03 12 13 23), b = column . y.  Returns the best gain b_S . w_S over the
 // supports whose weights are all positive, the determinant of that support's Gram (conditioning
-// of the gain) and whether the third column is active.
-__device__ double nnls4_gain(const double *g, const double *b, double &det_best, bool &third_active)
+// of the weights) and the weights themselves (zero off the support).
+__device__ double nnls4_gain(const double *g, const double *b, double &det_best, double *wbest)
 {
     const int pr[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -1}};
     double best = 0.0;
-    det_best = 1.0; third_active = false;
+    det_best = 1.0;
+    for (int c = 0; c < 4; c++) wbest[c] = 0.0;
 #pragma unroll 1
     for (int mask = 1; mask < 16; mask++) {
         int id[4], n = 0;
@@ -1318,7 +1319,11 @@ __device__ double nnls4_gain(const double *g, const double *b, double &det_best,
             pos = pos && w[i] > 0.0;
             gain += b[id[i]] * w[i];
         }
-        if (pos && gain > best) { best = gain; det_best = det; third_active = (mask & 4) != 0; }
+        if (pos && gain > best) {
+            best = gain; det_best = det;
+            for (int c = 0; c < 4; c++) wbest[c] = 0.0;
+            for (int i = 0; i < n; i++) wbest[id[i]] = w[i];
+        }
     }
     return best;
 }
@@ -1529,13 +1534,24 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                                                       fma(kb * kc, a23, gbb * gc), gbb, gc};
                                 const double bb[4] = {P1[(size_t)6 * a.Npad + i1], P2[(size_t)6 * a.Npad + i2],
                                                       P3[(size_t)6 * a.Npad + i3], vp[2] * rsqrt(vp[1])};
-                                double dets;
-                                bool third;
-                                const double gq = nnls4_gain(gg, bb, dets, third);
+                                double dets, w4[4];
+                                double gq = nnls4_gain(gg, bb, dets, w4);
                                 // a solution without the third block's atom belongs to the pair jobs (g2)
-                                if (!third) continue;
-                                const double tq = 8.0 * c0 / dets;
+                                if (!(w4[2] > 0.0)) continue;
+                                double tq = 8.0 * c0 / dets;
                                 if (!(gq + tq >= thr)) continue;
+                                {   // refined: stationary form 2 w.b - w'Gw at the computed weights (second order
+                                    // in their error); the input errors enter through |w|_1
+                                    const double y_sq = vp[0];
+                                    const double c1 = y_sq > 0 ? c0 / y_sq : 0.0, ynorm = sqrt(y_sq);
+                                    const double quad = fma(w4[0], w4[0], fma(w4[1], w4[1], fma(w4[2], w4[2], w4[3] * w4[3]))) +
+                                        2.0 * (w4[0] * (w4[1] * gg[0] + w4[2] * gg[1] + w4[3] * gg[2]) +
+                                               w4[1] * (w4[2] * gg[3] + w4[3] * gg[4]) + w4[2] * w4[3] * gg[5]);
+                                    const double gr = 2.0 * fma(w4[0], bb[0], fma(w4[1], bb[1], fma(w4[2], bb[2], w4[3] * bb[3]))) - quad;
+                                    const double sw = w4[0] + w4[1] + w4[2] + w4[3], rel = c1 / dets;
+                                    const double tr = 2.0 * c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq;
+                                    if (tr < tq) { gq = gr; tq = tr; }
+                                }
                                 if (tq > 16.0 * c0) gill = fmax(gill, gq + tq);
                                 const double wide4 = 4.0 * 16.0 * c0;
                                 if (gq > gb) {
@@ -1667,6 +1683,72 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
     }
     if (certain && !(G - tolG > g2 + 16.0 * c0)) { certain = false; reason = 3; }
     if (certain && fmax(fmax(vp[12], vp[13]), vp[14]) < kCramerScaleMin) { certain = false; reason = 3; }
+    if (!certain && !(fmax(fmax(vp[12], vp[13]), vp[14]) < kCramerScaleMin)) {
+        // The third block may simply be inactive: the best pair of blocks 1-2 (job 0: both weights
+        // positive, with the CSF column when there is one) wins when it is certain inside its own
+        // scan and clearly above (i) every solution of the other two jobs and every one-atom
+        // solution, (ii) every tuple in which the third block's atom is active (the tuples the scan
+        // did not look at lie below its threshold, which started at this pair's certified bound).
+        // The reference then returns the FIRST tuple of its loop order that contains the pair: the
+        // third index is 0 (`_3`: i3 outermost, identical 2-column sub-problem for every i3; `_4up`:
+        // product order, identical active set for every e).
+        const int nt0 = (a.Nb[a.job_rb[0]] + GP_TI - 1) / GP_TI;
+        double G0 = -1.0, tol0 = 0.0;
+        int I0 = -1, tb0 = -1;
+        for (int t = 0; t < nt0; t++) {
+            const int64_t o = (v * 3 + 0) * a.ntI + t;
+            if (a.cta_idx[o] >= 0 && (a.cta_gain[o] > G0 || (a.cta_gain[o] == G0 && a.cta_idx[o] < I0))) {
+                G0 = a.cta_gain[o]; tol0 = a.cta_tol[o]; I0 = a.cta_idx[o]; tb0 = t;
+            }
+        }
+        bool okb = I0 >= 0;
+        const double lower = G0 - tol0, sep = 16.0 * c0;
+        for (int t = 0; t < nt0 && okb; t++) {
+            const int64_t o = (v * 3 + 0) * a.ntI + t;
+            if (a.cta_ill[o] >= lower) okb = false;
+            if (t == tb0) { if (a.cta_flag[o]) okb = false; continue; }
+            if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] >= lower) okb = false;
+        }
+        for (int j = 1; j < 3 && okb; j++) {
+            const int ntj = (a.Nb[a.job_rb[j]] + GP_TI - 1) / GP_TI;
+            for (int t = 0; t < ntj && okb; t++) {
+                const int64_t o = (v * 3 + j) * a.ntI + t;
+                if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] + sep >= lower) okb = false;
+                if (a.cta_ill[o] + sep >= lower) okb = false;
+            }
+        }
+        if (okb && fmax(fmax(vp[5], vp[6]), vp[7]) + sep >= lower) okb = false;
+        for (int t = 0; t < a.tr_ntiles && okb; t++) {
+            const int64_t o = v * a.tr_ntiles + t;
+            if (a.t_idx[o] >= 0 && a.t_gain[o] + a.t_tol[o] + sep >= lower) okb = false;
+            if (a.t_ill[o] + sep >= lower) okb = false;
+        }
+        if (okb && !a.csf) {
+            // `_3` takes the unconstrained 3-column solution whenever its Cramer numerators are
+            // >= -tol (mfu:562), also when the third one is zero to rounding (noise-free data whose
+            // third weight is exactly 0): the residuals of the tuples (i3, pair) then differ only by
+            // rounding noise and the first minimum cannot be predicted.  Require, for every i3, a
+            // clearly negative numerator (the 2-column fall-back is certain).
+            const int N2 = a.Nb[1], N3 = a.Nb[2];
+            const int i1 = I0 / N2, i2 = I0 - i1 * N2;
+            const double *Z1 = a.colp + ((v * 3 + 0) * (int64_t)FT_NPAR + 2) * a.Npad;
+            const double *Z2 = a.colp + ((v * 3 + 1) * (int64_t)FT_NPAR + 2) * a.Npad;
+            const double *Z3 = a.colp + ((v * 3 + 2) * (int64_t)FT_NPAR + 2) * a.Npad;
+            const double r12 = a.R[0][v * a.r_stride[0] + (size_t)i1 * a.ldr[0] + i2];
+            const double z1 = Z1[i1], z2 = Z2[i2];
+            const double delta = 1e-9 * sqrt(vp[0]);
+            for (int i3 = 0; i3 < N3 && okb; i3++) {
+                const double r13 = a.R[1][v * a.r_stride[1] + (size_t)i3 * a.ldr[1] + i1];
+                const double r23 = a.R[2][v * a.r_stride[2] + (size_t)i3 * a.ldr[2] + i2];
+                const double z3 = Z3[i3];
+                const double D1 = z1 * (1.0 - r23 * r23) - z2 * (r12 - r13 * r23) + z3 * (r12 * r23 - r13);
+                const double D2 = -z1 * (r12 - r13 * r23) + z2 * (1.0 - r13 * r13) - z3 * (r23 - r12 * r13);
+                const double D3 = z1 * (r12 * r23 - r13) - z2 * (r23 - r12 * r13) + z3 * (1.0 - r12 * r12);
+                if (!(fmin(D1, fmin(D2, D3)) < -delta)) okb = false;
+            }
+        }
+        if (okb) { certain = true; reason = -1; I = (long long)I0; }      // third index 0 in both encodings below
+    }
     if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     if (certain) {

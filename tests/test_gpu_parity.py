@@ -683,6 +683,34 @@ def test_fit_two_fascicles_csf_ear_projected_triple_scan(n_atoms, n_ear, seed):
         assert np.array_equal(got[act, c_id], ref[act, c_id]), c_id
 
 
+@pytest.mark.parametrize("csf_frac", [0.0, 1.0])
+def test_fit_ear_flagged_but_inactive(csf_frac):
+    """Voxels flagged for the EAR compartment whose signal holds none: the non-negative optimum
+    puts no weight on the EAR block, the winner is the best pair of fascicle atoms (+ CSF).  The
+    triple scan certifies it from its pair job (third index 0, the first tuple of the reference's
+    loop order that contains the pair) instead of handing the voxel to the reference-order tier.
+    Rows must equal the reference-order tier's; for [N, N, E] also the oracle's, bit for bit."""
+    ph = make_phantom(n_atoms=120, n_vox=200, seed=51, frac_k=(0.0, 0.0, 1.0), csf_frac=csf_frac,
+                      ear=True, n_ear=5, ear_frac=0.5, ear_max_k=2)
+    ear_all = np.ones_like(ph.ear)                   # half of the voxels have no EAR signal
+    msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+    plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, ph.sig_ear)
+    csf_on = csf_frac > 0
+    fast = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, ear_all, 2, csf_on, True, flags=0)
+    st = plan.stats()
+    exact = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, ear_all, 2, csf_on, True, flags=1)
+    plan.close()
+    assert np.array_equal(fast, exact)
+    c_ear = 2 * 2 + int(csf_on) + 1
+    n_inactive = int(np.sum(fast[:, c_ear] == 0))
+    assert n_inactive >= 40, n_inactive
+    assert st[0] >= 150, st                          # most voxels, active or not, decided by the fast tier
+    if not csf_on:
+        ph.ear, ph.ear_on, ph.csf_on = ear_all, True, False
+        sel = np.where(fast[:, c_ear] == 0)[0][:8]
+        compare_rows(fast[sel], oracle_rows(ph, sel), ph, idx=sel, exact_bits=True)
+
+
 @pytest.fixture(scope="module")
 def mc_cases():
     import os

@@ -1,5 +1,6 @@
-"""Randomized shapes: the screening tiers of mfb_solve_batch (pair scan M <= 112, general-M
-pair scan, triple scan) must return exactly what the reference-order search returns.
+"""Randomized shapes: the screening tiers of mfb_solve_batch (pair scan M <= 111, general-M
+pair scan, triple scan, CSF-projected triple scan of [N1, N2, 1, N4]) must return exactly what
+the reference-order search returns.
 python tools/fuzz_solve_batch.py [cases] [seed]"""
 import os
 import sys
@@ -20,10 +21,12 @@ def run(ncases=60, seed=2026, verbose=True):
 
 
 def one_case(rng, verbose):
-    kind = rng.choice(["pair", "pair_iso", "triple"])
+    kind = rng.choice(["pair", "pair_iso", "triple", "quad"])
     M = int(rng.choice([5, 17, 60, 105, 112, 113, 140, 300]))
     if kind == "triple":
         sizes = [int(rng.integers(2, 90)) for _ in range(3)]
+    elif kind == "quad":        # two blocks + a single column + a small block (reference `_4up`)
+        sizes = [int(rng.integers(2, 40)), int(rng.integers(2, 40)), 1, int(rng.integers(2, 8))]
     else:
         sizes = [int(rng.integers(8, 400)), int(rng.integers(8, 400))] + ([1] if kind == "pair_iso" else [])
     V = int(rng.integers(1, 40))
