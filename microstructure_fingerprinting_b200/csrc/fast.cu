@@ -1274,65 +1274,11 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// Screening-precision NNLS of FOUR unit-norm columns (two fascicle atoms, an atom of the third
-// searched block, the CSF column) by support enumeration: G = unit-diagonal Gram (upper
-// triangle g[0..5] = 01 02 03 12 13 23), b = column . y.  Returns the best gain b_S . w_S over the
-// supports whose weights are all positive, the determinant of that support's Gram (conditioning
-// of the weights) and the weights themselves (zero off the support).
-__device__ double nnls4_gain(const double *g, const double *b, double &det_best, double *wbest)
-{
-    const int pr[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -1}};
-    double best = 0.0;
-    det_best = 1.0;
-    for (int c = 0; c < 4; c++) wbest[c] = 0.0;
-#pragma unroll 1
-    for (int mask = 1; mask < 16; mask++) {
-        int id[4], n = 0;
-        for (int c = 0; c < 4; c++)
-            if (mask & (1 << c)) id[n++] = c;
-        double L[4][4], z[4], w[4], det = 1.0;
-        bool ok = true;
-        for (int i = 0; i < n && ok; i++)
-            for (int j = 0; j <= i; j++) {
-                double sacc = i == j ? 1.0 : g[pr[id[i]][id[j]]];
-                for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
-                if (i == j) {
-                    if (!(sacc > 1e-14)) { ok = false; break; }
-                    det *= sacc;
-                    L[i][i] = sqrt(sacc);
-                } else {
-                    L[i][j] = sacc / L[j][j];
-                }
-            }
-        if (!ok) continue;
-        for (int i = 0; i < n; i++) {
-            double sacc = b[id[i]];
-            for (int k = 0; k < i; k++) sacc -= L[i][k] * z[k];
-            z[i] = sacc / L[i][i];
-        }
-        bool pos = true;
-        double gain = 0.0;
-        for (int i = n - 1; i >= 0; i--) {
-            double sacc = z[i];
-            for (int k = i + 1; k < n; k++) sacc -= L[k][i] * w[k];
-            w[i] = sacc / L[i][i];
-            pos = pos && w[i] > 0.0;
-            gain += b[id[i]] * w[i];
-        }
-        if (pos && gain > best) {
-            best = gain; det_best = det;
-            for (int c = 0; c < 4; c++) wbest[c] = 0.0;
-            for (int i = 0; i < n; i++) wbest[id[i]] = w[i];
-        }
-    }
-    return best;
-}
-
 // CSF: the three searched blocks are projected off a fourth, single-column block (two
 // fascicles + CSF + the EAR block of MFModel.fit, reference `_4up`).  The scan then tests the
 // UNCONSTRAINED gain of the projected triple against the threshold minus the CSF share -- a
 // necessary condition for any non-negative solution on the tuple's four columns -- and the
-// tuples that pass are solved exactly (nnls4_gain).
+// tuples that pass are solved in closed form on the two supports the pair jobs do not cover.
 template <int CSF>
 __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
 {
@@ -1520,7 +1466,11 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                             const double D3 = fma(-a23, u2, fma(-a13, u1, k33 * z3));
                             const double W1 = fma(-q1, D3, u1 * S), W2 = fma(-q2, D3, u2 * S);
                             if (CSF) {
-                                // four columns: the tuple's exact NNLS from the unprojected unit Gram
+                                // Four columns.  The tuple's non-negative optimum is the best of the supports whose
+                                // unconstrained solution is positive.  Supports without the third block's atom, or
+                                // with only one fascicle atom, belong to the pair jobs (bounded by g2); what is left:
+                                // the full support (all four positive) and {atom 1, atom 2, atom 3} without the CSF
+                                // column -- two closed forms instead of a 15-support enumeration.
                                 if (c * KC + r >= N3) continue;
                                 if (!(fma(-Tp[e], S, fma(D3, D3, c0)) >= 0.0)) continue;
                                 const int i1 = i10 + 2 * tx + p, i2 = i20 + 4 * ty + q, i3 = c * KC + r;
@@ -1530,30 +1480,52 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                                 const double ka = P1[(size_t)4 * a.Npad + i1], ga = P1[(size_t)5 * a.Npad + i1];
                                 const double kb = P2[(size_t)4 * a.Npad + i2], gbb = P2[(size_t)5 * a.Npad + i2];
                                 const double kc = P3[(size_t)4 * a.Npad + i3], gc = P3[(size_t)5 * a.Npad + i3];
-                                const double gg[6] = {fma(ka * kb, a12, ga * gbb), fma(ka * kc, a13, ga * gc), ga,
-                                                      fma(kb * kc, a23, gbb * gc), gbb, gc};
-                                const double bb[4] = {P1[(size_t)6 * a.Npad + i1], P2[(size_t)6 * a.Npad + i2],
-                                                      P3[(size_t)6 * a.Npad + i3], vp[2] * rsqrt(vp[1])};
-                                double dets, w4[4];
-                                double gq = nnls4_gain(gg, bb, dets, w4);
-                                // a solution without the third block's atom belongs to the pair jobs (g2)
-                                if (!(w4[2] > 0.0)) continue;
-                                double tq = 8.0 * c0 / dets;
-                                if (!(gq + tq >= thr)) continue;
-                                {   // refined: stationary form 2 w.b - w'Gw at the computed weights (second order
-                                    // in their error); the input errors enter through |w|_1
-                                    const double y_sq = vp[0];
-                                    const double c1 = y_sq > 0 ? c0 / y_sq : 0.0, ynorm = sqrt(y_sq);
-                                    const double quad = fma(w4[0], w4[0], fma(w4[1], w4[1], fma(w4[2], w4[2], w4[3] * w4[3]))) +
-                                        2.0 * (w4[0] * (w4[1] * gg[0] + w4[2] * gg[1] + w4[3] * gg[2]) +
-                                               w4[1] * (w4[2] * gg[3] + w4[3] * gg[4]) + w4[2] * w4[3] * gg[5]);
-                                    const double gr = 2.0 * fma(w4[0], bb[0], fma(w4[1], bb[1], fma(w4[2], bb[2], w4[3] * bb[3]))) - quad;
-                                    const double sw = w4[0] + w4[1] + w4[2] + w4[3], rel = c1 / dets;
-                                    const double tr = 2.0 * c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq;
-                                    if (tr < tq) { gq = gr; tq = tr; }
+                                const double y_sq = vp[0];
+                                const double c1 = y_sq > 0 ? c0 / y_sq : 0.0, ynorm = sqrt(y_sq);
+                                const double zc = vp[2] * rsqrt(vp[1]);              // csf . y on the unit CSF column
+                                const double zua = P1[(size_t)6 * a.Npad + i1], zub = P2[(size_t)6 * a.Npad + i2],
+                                             zuc = P3[(size_t)6 * a.Npad + i3];
+                                double gq = -1.0, tq = 0.0;
+                                const double dd = k33 * S;
+                                if (W1 > 0.0 && W2 > 0.0 && D3 > 0.0 && dd > 1e-13 && S > 0.0) {
+                                    // full support: weights on the unit columns from the projected solution
+                                    const double wa = W1 / (dd * ka), wb = W2 / (dd * kb), wcc = D3 / (S * kc);
+                                    const double wcsf = zc - fma(wa, ga, fma(wb, gbb, wcc * gc));
+                                    if (wcsf > 0.0) {
+                                        const double zz1 = zrow(p), zz2 = zcol(q);
+                                        gq = gshift + fma(fma(zz1, u1, zz2 * u2), S, D3 * D3) / dd;
+                                        const double sw = wa + wb + wcc + wcsf, rel = c1 / dd;
+                                        tq = fmin(4.0 * c0 / dd, 2.0 * c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq);
+                                    }
                                 }
-                                if (tq > 16.0 * c0) gill = fmax(gill, gq + tq);
-                                const double wide4 = 4.0 * 16.0 * c0;
+                                {   // support {1, 2, 3} without the CSF column: unprojected 3 x 3 Cramer on unit columns
+                                    const double r12 = fma(ka * kb, a12, ga * gbb), r13 = fma(ka * kc, a13, ga * gc),
+                                                 r23 = fma(kb * kc, a23, gbb * gc);
+                                    const double m1 = fma(-r23, r23, 1.0), m2 = fma(-r13, r23, r12), m3 = fma(r12, r23, -r13);
+                                    const double det = fma(-r12, m2, fma(r13, m3, m1));
+                                    if (det > 1e-13) {
+                                        const double e1 = fma(zua, m1, fma(-zub, m2, zuc * m3));
+                                        const double e2 = fma(-zua, m2, fma(zub, fma(-r13, r13, 1.0), -zuc * fma(-r12, r13, r23)));
+                                        const double e3 = fma(zua, m3, fma(-zub, fma(-r12, r13, r23), zuc * fma(-r12, r12, 1.0)));
+                                        if (e1 > 0.0 && e2 > 0.0 && e3 > 0.0) {
+                                            const double wa = e1 / det, wb = e2 / det, wcc = e3 / det;
+                                            // stationary form 2 w.z - w'Gw (second order in the weight error)
+                                            const double quad = fma(wa, wa, fma(wb, wb, wcc * wcc)) +
+                                                                2.0 * fma(wa * wb, r12, fma(wa * wcc, r13, wb * wcc * r23));
+                                            const double g3 = 2.0 * fma(wa, zua, fma(wb, zub, wcc * zuc)) - quad;
+                                            const double sw = wa + wb + wcc, rel = c1 / det;
+                                            const double t3 = 2.0 * c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq;
+                                            if (g3 > gq) { gq = g3; tq = t3; }
+                                        }
+                                    } else {
+                                        gill = INFINITY;         // numerically singular triple
+                                    }
+                                }
+                                if (gq < 0.0) continue;           // the tuple's optimum lies on a support of the pair jobs
+                                if (!(gq + tq >= thr)) continue;
+                                // (all of these margins are ~1e-11 of |y|^2, far below the gaps between tuples)
+                                const double tmax4 = 256.0 * c0, wide4 = 4.0 * tmax4;
+                                if (tq > tmax4) gill = fmax(gill, gq + tq);
                                 if (gq > gb) {
                                     flag = (bidx >= 0 && !(gq > gb + wide4)) ? 1 : 0;
                                     gb = gq; tb = tq;
@@ -1723,12 +1695,14 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
             if (a.t_idx[o] >= 0 && a.t_gain[o] + a.t_tol[o] + sep >= lower) okb = false;
             if (a.t_ill[o] + sep >= lower) okb = false;
         }
-        if (okb && !a.csf) {
+        if (okb) {
             // `_3` takes the unconstrained 3-column solution whenever its Cramer numerators are
             // >= -tol (mfu:562), also when the third one is zero to rounding (noise-free data whose
             // third weight is exactly 0): the residuals of the tuples (i3, pair) then differ only by
-            // rounding noise and the first minimum cannot be predicted.  Require, for every i3, a
-            // clearly negative numerator (the 2-column fall-back is certain).
+            // rounding noise and the first minimum cannot be predicted; the support enumeration of
+            // four blocks has the same degenerate tie (a third weight of +1e-16).  Require, for every
+            // i3, a clearly negative numerator of the (CSF-projected) three-column solution: the
+            // tuple's optimum then lies on a sub-support, all of which are accounted for above.
             const int N2 = a.Nb[1], N3 = a.Nb[2];
             const int i1 = I0 / N2, i2 = I0 - i1 * N2;
             const double *Z1 = a.colp + ((v * 3 + 0) * (int64_t)FT_NPAR + 2) * a.Npad;

@@ -30,6 +30,10 @@ for csf_frac, label in ((0.0, "[N,N,E]"), (1.0, "[N,N,1,E]")):
         st = plan.stats()
         n = 48
         ex = plan.fit_host(*[a[:n] if isinstance(a, np.ndarray) else a for a in args], flags=1)
-        print("%-10s N %d E %d V %d, %s: %.0f voxels/s; fast tier %d, exact tier %d voxels; first %d rows == exact tier: %s"
-              % (label, N, E, V, what, V / best, st[0], st[1], n, bool(np.array_equal(rows[:n], ex))))
+        t0 = time.perf_counter()
+        ex = plan.fit_host(*[a[:n] if isinstance(a, np.ndarray) else a for a in args], flags=1)
+        t_ex = (time.perf_counter() - t0) / n
+        print("%-10s N %d E %d V %d, %s: %.0f voxels/s; fast tier %d, exact tier %d voxels (ill-conditioned %d, near ties / fewer "
+              "columns %.6f); exact tier alone %.1f ms per voxel; first %d rows == exact tier: %s"
+              % (label, N, E, V, what, V / best, st[0], st[1], st[6], st[7], t_ex * 1e3, n, bool(np.array_equal(rows[:n], ex))))
         plan.close()

@@ -52,6 +52,11 @@ def one_case(rng, verbose):
     if verbose or not ok:
         print("%-8s M %3d sizes %-16s V %2d signed %d shared %d: screened %2d redone %2d %s" %
               (kind, M, sizes, V, signed, shared, stats[0], stats[1], "ok" if ok else "MISMATCH"))
+    if not ok:
+        for v in range(V):
+            if not all(np.array_equal(f[v], e[v]) for f, e in zip(fast, exact)):
+                print("   voxel %d: fast sub %s w %s obj %.17g | exact sub %s w %s obj %.17g" %
+                      (v, fast[1][v], fast[0][v], fast[3][v], exact[1][v], exact[0][v], exact[3][v]))
     return 0 if ok else 1
 
 
