@@ -443,7 +443,7 @@ def main():
         else:
             # the C ABI with host buffers on one GPU (mfb_fit_host)
             plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, None, device=local)
-            plan.fit_host(ph.Y[:65536], ph.peaks[:65536], ph.K[:65536], ph.csf[:65536], None, ph.maxfasc, True, False)
+            plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, None, ph.maxfasc, True, False)     # warm-up (workspace sizes)
             t0 = time.perf_counter()
             rows_host = plan.fit_host(ph.Y, ph.peaks, ph.K, ph.csf, None, ph.maxfasc, True, False)
             e2e["c_abi_voxels_per_s"] = V / (time.perf_counter() - t0)

@@ -170,11 +170,45 @@ def config5(peak, V=768, N=2000, chunk=96):
         "oracle_index_match": "%d/%d" % (ok, len(vox))}}
 
 
+def config_ear(peak, V=2048, N=1000, E=10):
+    """MFModel.fit path with the EAR compartment on every voxel: [N, N, E] (two fascicles + EAR,
+    triple scan) and [N, N, 1, E] (+ CSF: CSF-projected triple scan, reference `_4up`)."""
+    from microstructure_fingerprinting_b200 import mf_utils as mfu
+    from tests.phantom import make_phantom, oracle_rows
+    res = {}
+    for csf_frac, label in ((0.0, "[N, N, E]"), (1.0, "[N, N, 1, E]")):
+        ph = make_phantom(n_atoms=N, n_vox=V, seed=61, frac_k=(0, 0, 1), csf_frac=csf_frac, ear=True, n_ear=E,
+                          ear_frac=1.0, ear_max_k=2)
+        msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
+        plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, ph.sig_ear)
+        args = (ph.Y, ph.peaks, ph.K, ph.csf, ph.ear, 2, csf_frac > 0, True)
+        plan.fit_host(*[a[:256] if isinstance(a, np.ndarray) else a for a in args])
+        best = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            rows = plan.fit_host(*args)
+            best = min(best, time.perf_counter() - t0)
+        st = plan.stats()
+        plan.close()
+        # oracle on 4 voxels ([N, N, E]: the C restatement of `_3`, ~1 s per voxel; the 4-block oracle
+        # runs scipy.optimize.nnls on 10^7 tuples per voxel and is not run here)
+        match = None
+        if csf_frac == 0.0:
+            sel = np.arange(0, V, V // 4)[:4]
+            with ThreadPoolExecutor(4) as ex:
+                ref = list(ex.map(lambda i: oracle_rows(ph, np.array([i]))[0], sel))
+            match = "%d/4" % sum(bool(np.array_equal(r[3:5], rows[i, 3:5]) and r[-3] == rows[i, -3]) for r, i in zip(ref, sel))
+        F = 2.0 * 105 * (N * N + 2 * N * E) + 4.0 * 105 * (2 * N + E) + 65.0 * N * N * E
+        res[label] = {"voxels": V, "N": N, "E": E, "voxels_per_s": V / best, "handed_to_exact_tier": st[1] / max(1.0, st[0] + st[1]),
+                      "tflops_algorithmic": F * V / best / 1e12, "oracle_index_match": match}
+    return res
+
+
 def run_extra_configs(peak):
     from microstructure_fingerprinting_b200 import _lib
     out = {}
     for name, fn in (("config2_solve_batch_per_voxel_A", config2), ("config4_numfasc3", config4),
-                     ("config5_axcaliber_2D", config5)):
+                     ("config5_axcaliber_2D", config5), ("fit_with_ear_compartment", config_ear)):
         t0 = time.perf_counter()
         try:
             out[name] = fn(peak)
