@@ -1068,9 +1068,17 @@ __global__ void __launch_bounds__(256) k_single_fascicle(SfArgs a)
     if (threadIdx.x == 0) a.tuple[row] = (b.idx == LLONG_MAX) ? kNoTuple : b.idx;
 }
 
+static size_t single_fascicle_smem(const DevPlan &p, int csf, int ear)
+{
+    const int nIso = csf + ear * p.E;
+    return sizeof(double) * ((size_t)5 * p.M + (size_t)nIso * p.M + 3 * SF_MAXISO) + sizeof(int) * 4 * p.M;
+}
+
+// Long protocols (shared-memory plan above 200 KB, M beyond ~3000) are not an error: the
+// caller falls through to the materialising exact tier, which has no limit on M.
 bool single_fascicle_supported(const DevPlan &p, int K, int csf, int ear)
 {
-    return K == 1 && csf + ear * p.E <= SF_MAXISO;
+    return K == 1 && csf + ear * p.E <= SF_MAXISO && single_fascicle_smem(p, csf, ear) <= 200 * 1024;
 }
 
 int launch_single_fascicle(const DevPlan &p, int64_t nvox, const int32_t *vox_list,
@@ -1081,8 +1089,7 @@ int launch_single_fascicle(const DevPlan &p, int64_t nvox, const int32_t *vox_li
     SfArgs a;
     a.p = p; a.vox_list = vox_list; a.peaks = peaks; a.peaks_ld = peaks_ld; a.y = y;
     a.csf = csf; a.ear = ear; a.tuple = tuple;
-    const int nIso = csf + ear * p.E;
-    size_t smem = sizeof(double) * ((size_t)5 * p.M + (size_t)nIso * p.M + 3 * SF_MAXISO) + sizeof(int) * 4 * p.M;
+    const size_t smem = single_fascicle_smem(p, csf, ear);
     if (smem > 200 * 1024) { set_error("single-fascicle kernel: protocol too long for shared memory"); return MFB_EUNSUPPORTED; }
     if (smem > 48 * 1024)  // per device / context attribute
         MFB_CUDA_TRY(cudaFuncSetAttribute(k_single_fascicle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
