@@ -1432,14 +1432,9 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                         if (CSF) {
                             sall &= __double2hiint(t);
                         } else {
-#ifdef TR_SKIP_W
-                            // the signs of the two fascicle weights are left to the competitive path (9 ops per tuple)
-                            sall &= __double2hiint(D3) | __double2hiint(t);
-#else
                             const double W1 = fma(-q1, D3, U1[e] * S);
                             const double W2 = fma(-q2, D3, U2[e] * S);
                             sall &= (__double2hiint(W1) | __double2hiint(W2) | __double2hiint(D3)) | __double2hiint(t);
-#endif
                         }
                     }
                 sgn[s4] = sall;
