@@ -1656,37 +1656,42 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
     if (certain && !(G - tolG > g2 + 16.0 * c0)) { certain = false; reason = 3; }
     if (certain && fmax(fmax(vp[12], vp[13]), vp[14]) < kCramerScaleMin) { certain = false; reason = 3; }
     if (!certain && !(fmax(fmax(vp[12], vp[13]), vp[14]) < kCramerScaleMin)) {
-        // The third block may simply be inactive: the best pair of blocks 1-2 (job 0: both weights
-        // positive, with the CSF column when there is one) wins when it is certain inside its own
-        // scan and clearly above (i) every solution of the other two jobs and every one-atom
-        // solution, (ii) every tuple in which the third block's atom is active (the tuples the scan
-        // did not look at lie below its threshold, which started at this pair's certified bound).
-        // The reference then returns the FIRST tuple of its loop order that contains the pair: the
-        // third index is 0 (`_3`: i3 outermost, identical 2-column sub-problem for every i3; `_4up`:
-        // product order, identical active set for every e).
-        const int nt0 = (a.Nb[a.job_rb[0]] + GP_TI - 1) / GP_TI;
-        double G0 = -1.0, tol0 = 0.0;
-        int I0 = -1, tb0 = -1;
-        for (int t = 0; t < nt0; t++) {
-            const int64_t o = (v * 3 + 0) * a.ntI + t;
-            if (a.cta_idx[o] >= 0 && (a.cta_gain[o] > G0 || (a.cta_gain[o] == G0 && a.cta_idx[o] < I0))) {
-                G0 = a.cta_gain[o]; tol0 = a.cta_tol[o]; I0 = a.cta_idx[o]; tb0 = t;
+        // One of the three blocks may simply be inactive: the best two-block solution (job 0: blocks
+        // 1-2, job 1: blocks 3-1, job 2: blocks 3-2; both weights positive, with the CSF column when
+        // there is one) wins when it is certain inside its own scan and clearly above (i) every
+        // solution of the other two jobs and every one-atom solution, (ii) every tuple in which all
+        // three blocks are active (the tuples the scan did not look at lie below its threshold, which
+        // started at the jobs' certified bounds).  The reference then returns the FIRST tuple of its
+        // loop order that contains the pair: the inactive block's index is 0 (`_3`: the 2-column
+        // sub-problem is the same for every atom of the inactive block; `_4up`: same active set).
+        double Gj[3], tolj[3];
+        int Ij[3], tbj[3], jb = 0;
+        for (int j = 0; j < 3; j++) {
+            Gj[j] = -1.0; tolj[j] = 0.0; Ij[j] = -1; tbj[j] = -1;
+            const int ntj = (a.Nb[a.job_rb[j]] + GP_TI - 1) / GP_TI;
+            for (int t = 0; t < ntj; t++) {
+                const int64_t o = (v * 3 + j) * a.ntI + t;
+                if (a.cta_idx[o] >= 0 && (a.cta_gain[o] > Gj[j] || (a.cta_gain[o] == Gj[j] && a.cta_idx[o] < Ij[j]))) {
+                    Gj[j] = a.cta_gain[o]; tolj[j] = a.cta_tol[o]; Ij[j] = a.cta_idx[o]; tbj[j] = t;
+                }
             }
+            if (Gj[j] > Gj[jb]) jb = j;
         }
+        const int I0 = Ij[jb];
         bool okb = I0 >= 0;
-        const double lower = G0 - tol0, sep = 16.0 * c0;
-        for (int t = 0; t < nt0 && okb; t++) {
-            const int64_t o = (v * 3 + 0) * a.ntI + t;
-            if (a.cta_ill[o] >= lower) okb = false;
-            if (t == tb0) { if (a.cta_flag[o]) okb = false; continue; }
-            if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] >= lower) okb = false;
-        }
-        for (int j = 1; j < 3 && okb; j++) {
+        const double lower = Gj[jb] - tolj[jb], sep = 16.0 * c0;
+        for (int j = 0; j < 3 && okb; j++) {
             const int ntj = (a.Nb[a.job_rb[j]] + GP_TI - 1) / GP_TI;
             for (int t = 0; t < ntj && okb; t++) {
                 const int64_t o = (v * 3 + j) * a.ntI + t;
-                if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] + sep >= lower) okb = false;
-                if (a.cta_ill[o] + sep >= lower) okb = false;
+                if (j == jb) {      // inside the winner's own scan: the usual certainty test
+                    if (a.cta_ill[o] >= lower) okb = false;
+                    if (t == tbj[jb]) { if (a.cta_flag[o]) okb = false; continue; }
+                    if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] >= lower) okb = false;
+                } else {
+                    if (a.cta_idx[o] >= 0 && a.cta_gain[o] + a.cta_tol[o] + sep >= lower) okb = false;
+                    if (a.cta_ill[o] + sep >= lower) okb = false;
+                }
             }
         }
         if (okb && fmax(fmax(vp[5], vp[6]), vp[7]) + sep >= lower) okb = false;
@@ -1695,33 +1700,38 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
             if (a.t_idx[o] >= 0 && a.t_gain[o] + a.t_tol[o] + sep >= lower) okb = false;
             if (a.t_ill[o] + sep >= lower) okb = false;
         }
+        // the winner's atoms: job (rb, cb) index = i_rb * N_cb + i_cb; the third block is inactive
+        int iw[3] = {0, 0, 0};
+        const int rbw = a.job_rb[jb], cbw = a.job_cb[jb], obw = 3 - rbw - cbw;
+        if (okb) { iw[rbw] = I0 / a.Nb[cbw]; iw[cbw] = I0 - iw[rbw] * a.Nb[cbw]; }
         if (okb) {
             // `_3` takes the unconstrained 3-column solution whenever its Cramer numerators are
-            // >= -tol (mfu:562), also when the third one is zero to rounding (noise-free data whose
-            // third weight is exactly 0): the residuals of the tuples (i3, pair) then differ only by
-            // rounding noise and the first minimum cannot be predicted; the support enumeration of
-            // four blocks has the same degenerate tie (a third weight of +1e-16).  Require, for every
-            // i3, a clearly negative numerator of the (CSF-projected) three-column solution: the
-            // tuple's optimum then lies on a sub-support, all of which are accounted for above.
-            const int N2 = a.Nb[1], N3 = a.Nb[2];
-            const int i1 = I0 / N2, i2 = I0 - i1 * N2;
-            const double *Z1 = a.colp + ((v * 3 + 0) * (int64_t)FT_NPAR + 2) * a.Npad;
-            const double *Z2 = a.colp + ((v * 3 + 1) * (int64_t)FT_NPAR + 2) * a.Npad;
-            const double *Z3 = a.colp + ((v * 3 + 2) * (int64_t)FT_NPAR + 2) * a.Npad;
-            const double r12 = a.R[0][v * a.r_stride[0] + (size_t)i1 * a.ldr[0] + i2];
-            const double z1 = Z1[i1], z2 = Z2[i2];
+            // >= -tol (mfu:562), also when one is zero to rounding (noise-free data whose weight on
+            // the inactive block is exactly 0): the residuals of the tuples (pair, any atom of that
+            // block) then differ only by rounding noise and the first minimum cannot be predicted;
+            // the support enumeration of four blocks has the same degenerate tie (a weight of
+            // +1e-16).  Require, for every atom of the inactive block, a clearly negative numerator of
+            // the (CSF-projected) three-column solution: the tuple's optimum then lies on a
+            // sub-support, all of which are accounted for above.
+            const double *Zb[3];
+            for (int k = 0; k < 3; k++) Zb[k] = a.colp + ((v * 3 + k) * (int64_t)FT_NPAR + 2) * a.Npad;
+            const double *R12 = a.R[0] + v * a.r_stride[0], *R13T = a.R[1] + v * a.r_stride[1], *R23T = a.R[2] + v * a.r_stride[2];
             const double delta = 1e-9 * sqrt(vp[0]);
-            for (int i3 = 0; i3 < N3 && okb; i3++) {
-                const double r13 = a.R[1][v * a.r_stride[1] + (size_t)i3 * a.ldr[1] + i1];
-                const double r23 = a.R[2][v * a.r_stride[2] + (size_t)i3 * a.ldr[2] + i2];
-                const double z3 = Z3[i3];
+            for (int io = 0; io < a.Nb[obw] && okb; io++) {
+                iw[obw] = io;
+                const double r12 = R12[(size_t)iw[0] * a.ldr[0] + iw[1]];
+                const double r13 = R13T[(size_t)iw[2] * a.ldr[1] + iw[0]];
+                const double r23 = R23T[(size_t)iw[2] * a.ldr[2] + iw[1]];
+                const double z1 = Zb[0][iw[0]], z2 = Zb[1][iw[1]], z3 = Zb[2][iw[2]];
                 const double D1 = z1 * (1.0 - r23 * r23) - z2 * (r12 - r13 * r23) + z3 * (r12 * r23 - r13);
                 const double D2 = -z1 * (r12 - r13 * r23) + z2 * (1.0 - r13 * r13) - z3 * (r23 - r12 * r13);
                 const double D3 = z1 * (r12 * r23 - r13) - z2 * (r23 - r12 * r13) + z3 * (1.0 - r12 * r12);
                 if (!(fmin(D1, fmin(D2, D3)) < -delta)) okb = false;
             }
+            iw[obw] = 0;
         }
-        if (okb) { certain = true; reason = -1; I = (long long)I0; }      // third index 0 in both encodings below
+        // `_3` loop index (i3 outermost), re-encoded below for four blocks
+        if (okb) { certain = true; reason = -1; I = ((long long)iw[2] * a.Nb[0] + iw[0]) * a.Nb[1] + iw[1]; }
     }
     if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
