@@ -968,5 +968,16 @@ def test_c_abi_rejects_bad_arguments():
             plan.fit_host(ph.Y, ph.peaks, ph.K, np.ones(4, np.uint8), None, ph.maxfasc, True, False)
         with pytest.raises(ValueError):
             plan.fit_host(ph.Y, np.zeros((4, 9)), np.full(4, 3, np.int32), None, None, 3, False, False)
+        # mfb_fit_volume: unknown element type, missing data; an empty ROI is not an error; the
+        # plan still works after the failed calls (the pipeline threads and streams are left clean)
+        out = np.zeros((4, 1 + 2 * ph.maxfasc + 2))
+        vp = ctypes.c_void_p
+        args = lambda data, dt, V=4: (plan.handle, V, data, dt, None, ph.Y.shape[1], 1, ph.peaks.ctypes.data_as(vp),  # noqa: E731
+                                      ph.K.ctypes.data_as(vp), None, None, ph.maxfasc, 0, 0, out.ctypes.data_as(vp), 0)
+        assert lib.mfb_fit_volume(*args(ph.Y.ctypes.data_as(vp), 7)) == _lib.MFB_EINVAL
+        assert lib.mfb_fit_volume(*args(None, _lib.MFB_F64)) == _lib.MFB_EINVAL
+        assert lib.mfb_fit_volume(*args(ph.Y.ctypes.data_as(vp), _lib.MFB_F64, V=0)) == 0
+        assert lib.mfb_fit_volume(*args(ph.Y.ctypes.data_as(vp), _lib.MFB_F64)) == 0
+        assert np.array_equal(out, plan.fit_host(ph.Y, ph.peaks, ph.K, None, None, ph.maxfasc, False, False))
     finally:
         plan.close()
