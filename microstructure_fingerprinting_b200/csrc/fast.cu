@@ -1619,6 +1619,71 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
     }
 }
 
+// Seed of the triple scan's voxel-wide threshold.  The pair jobs give the best two-block
+// solutions; the optimum triple almost always contains one of those pairs, so the three LINES of
+// tuples through them (best pair of blocks 1-2 with every atom of block 3, best pair 3-1 with
+// every atom of block 2, best pair 3-2 with every atom of block 1) are evaluated first and their
+// best certified lower bound becomes the starting threshold: without it every CTA of k_triples
+// starts from the two-block bound and floods its competitive path until the first good triple is
+// met.  grid V, 128 threads.
+__global__ void __launch_bounds__(128) k_triple_seed(FastArgs a)
+{
+    __shared__ double s_red[4];
+    const int64_t v = blockIdx.x;
+    const double *vp = a.voxp + v * FT_VP;
+    const double c0 = vp[4], gshift = a.csf ? vp[3] : 0.0;
+    const double *R12 = a.R[0] + v * a.r_stride[0], *R13T = a.R[1] + v * a.r_stride[1], *R23T = a.R[2] + v * a.r_stride[2];
+    const double *P[3];
+    for (int k = 0; k < 3; k++) P[k] = a.colp + (v * 3 + k) * (int64_t)FT_NPAR * a.Npad;
+    const double zc = a.csf ? vp[2] * rsqrt(vp[1]) : 0.0;
+    double best = 0.0;
+    for (int j = 0; j < 3; j++) {
+        // best pair of job j
+        const int rb = a.job_rb[j], cb = a.job_cb[j], ob = 3 - rb - cb;
+        const int ntj = (a.Nb[rb] + GP_TI - 1) / GP_TI;
+        double G = -1.0;
+        int I = -1;
+        for (int t = 0; t < ntj; t++) {
+            const int64_t o = (v * 3 + j) * a.ntI + t;
+            if (a.cta_idx[o] >= 0 && a.cta_gain[o] > G) { G = a.cta_gain[o]; I = a.cta_idx[o]; }
+        }
+        if (I < 0) continue;
+        int iw[3];
+        iw[rb] = I / a.Nb[cb]; iw[cb] = I - iw[rb] * a.Nb[cb];
+        for (int io = threadIdx.x; io < a.Nb[ob]; io += blockDim.x) {
+            iw[ob] = io;
+            const double r12 = R12[(size_t)iw[0] * a.ldr[0] + iw[1]];
+            const double r13 = R13T[(size_t)iw[2] * a.ldr[1] + iw[0]];
+            const double r23 = R23T[(size_t)iw[2] * a.ldr[2] + iw[1]];
+            const double z1 = P[0][(size_t)2 * a.Npad + iw[0]], z2 = P[1][(size_t)2 * a.Npad + iw[1]],
+                         z3 = P[2][(size_t)2 * a.Npad + iw[2]];
+            const double c33 = fma(-r12, r12, 1.0), U1 = fma(-r12, z2, z1), U2 = fma(-r12, z1, z2);
+            const double q1 = fma(-r12, r23, r13), q2 = fma(-r12, r13, r23);
+            const double S = fma(-r23, q2, fma(-r13, q1, c33));
+            const double D3 = fma(-r23, U2, fma(-r13, U1, c33 * z3));
+            const double W1 = fma(-q1, D3, U1 * S), W2 = fma(-q2, D3, U2 * S);
+            const double dd = c33 * S;
+            if (!(W1 > 0.0 && W2 > 0.0 && D3 > 0.0 && S > 0.0 && dd > 1e-9)) continue;
+            if (a.csf) {    // the CSF weight of the four-column solution must be positive too
+                const double wa = W1 / (dd * P[0][(size_t)4 * a.Npad + iw[0]]), wb = W2 / (dd * P[1][(size_t)4 * a.Npad + iw[1]]),
+                             wc = D3 / (S * P[2][(size_t)4 * a.Npad + iw[2]]);
+                const double wcsf = zc - fma(wa, P[0][(size_t)5 * a.Npad + iw[0]],
+                                             fma(wb, P[1][(size_t)5 * a.Npad + iw[1]], wc * P[2][(size_t)5 * a.Npad + iw[2]]));
+                if (!(wcsf > 0.0)) continue;
+            }
+            const double gq = gshift + fma(fma(z1, U1, z2 * U2), S, D3 * D3) / dd;
+            best = fmax(best, gq - 4.0 * c0 / dd - c0);        // certified lower bound (Cramer-form error bound)
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        best = fmax(fmax(s_red[0], s_red[1]), fmax(s_red[2], s_red[3]));
+        if (best > 0.0) atomicMax(a.vthr + v, (unsigned long long)__double_as_longlong(best));
+    }
+}
+
 // select for the triple scan: one thread per voxel
 __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
 {
@@ -2161,6 +2226,7 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
         if (kc < 4) { set_error("triple scan: third block too large for shared memory"); return MFB_EUNSUPPORTED; }
         a.tr_kc = kc;
         const size_t smem = sizeof(double) * (size_t)2 * kc * rowlen + fixed;
+        MFB_LAUNCH(k_triple_seed, (unsigned)V, 128, 0, st, a);
         void (*ktr)(FastArgs) = a.csf ? k_triples<1> : k_triples<0>;
         MFB_CUDA_TRY(cudaFuncSetAttribute(ktr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(ktr, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
