@@ -105,6 +105,7 @@ struct FastArgs {
     int64_t r_stride[3];
     // triple scan (k_triples): thread layout, tiles, per-tile results, voxel-wide threshold
     int tr_txt, tr_tyt, tr_nt1, tr_ntiles, tr_kc;
+    int tr_perm[3];              // scan block k = caller's block tr_perm[k] (the scan streams its largest block)
     double *t_gain, *t_tol, *t_ill;
     long long *t_idx;
     int *t_flag;
@@ -1247,18 +1248,32 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 // screening pass also yields the best 2-column solutions, i.e. every branch of `_3` that
 // does not depend on the third index).  k_triples then enumerates all N1*N2*N3 tuples on the
 // FP64 pipe: a CTA owns a (T1 x T2) tile of (i1, i2) pairs, every thread keeps 2 x 4 pairs in
-// registers (r12, 1 - r12^2 and the 2-column Cramer numerators U1, U2) and streams over i3
-// through a cp.async double-buffered shared-memory ring of R13^T / R23^T rows.  Per tuple,
-// with q1 = r13 - r12 r23, q2 = r23 - r12 r13:
-//     S  = c33 - r13 q1 - r23 q2            (3x3 determinant of the correlation matrix)
-//     D3 = c33 z3 - r13 U1 - r23 U2         (Cramer numerator of w3)
-//     W1 = U1 S - q1 D3,  W2 = U2 S - q2 D3 (c33 x Cramer numerators of w1, w2)
-//     gain = (n2 S + D3^2) / (c33 S),  n2 = z1 U1 + z2 U2
-// 13 FP64 operations, no division; "all weights positive and gain + error bound >= thr" is
-// decided on the sign bits of four doubles with integer instructions.
+// registers and streams over i3 through a cp.async double-buffered shared-memory ring of
+// R13^T / R23^T rows.  Everything is written in the basis that eliminates atom 1 first, so that
+// what depends on (i1, i3) only is shared by the thread's four i2 columns.  With
+// c33 = 1 - r12^2, U2 = z2 - r12 z1 (per pair), m13 = 1 - r13^2, d13 = z3 - r13 z1 (per (i1, i3),
+// 2 operations for 4 tuples), q2 = r23 - r12 r13, q1 = r13 - r12 r23:
+//     S     = c33 m13 - q2^2                (3x3 determinant of the correlation matrix)
+//     delta = d13 - q2 (U2 / c33)           (Cramer numerator of w3 over c33)
+//     W1 / c33 = (U1 / c33) S - q1 delta,  W2 / c33 = (U2 / c33) S - q2 delta
+//     gain >= thr  <=>  delta^2 >= S (thr c33 - n2) / c33^2,   n2 = z1 U1 + z2 U2
+// 11.5 FP64 operations per tuple (6.5 for the CSF-projected scan, which does not look at the
+// signs of W1, W2), no division; "all weights positive and gain + error bound >= thr" is decided
+// on the sign bits of four doubles with integer instructions.  (Round 1 evaluated S, D3, W1, W2
+// in the symmetric form: 13 / 9 operations.)  The isolated loop (tools/triples_loop_bench.cu) runs
+// at 1.10 T tuples/s whatever the thread tile or the number of warps: FP64 instructions hold the
+// issue port for ~2.2 cycles each and every other instruction (sign logic, shared-memory loads)
+// adds its own cycle, so the count of instructions per tuple is what sets the pace.
 // ---------------------------------------------------------------------------------
 #define TR_KC_MAX 128        // i3 steps per chunk: as many as fit in shared memory, at most this
-#define TR_MAXTHREADS 384
+#ifndef TR_CTAS
+#define TR_CTAS 1            // CTAs per SM (2: measured slower, 25.6 k against 27.4 k voxels/s at [300,300,300])
+#endif
+#define TR_MAXTHREADS (384 / TR_CTAS)
+
+#ifdef TR_COUNT
+__device__ unsigned long long g_tr_counters[4];   // votes, CSF tuples passing the gain test, votes that hit, competitive tuples
+#endif
 
 struct TripleGeom {
     int txt, tyt, T1, T2, nt1, nt2, threads;
@@ -1280,7 +1295,7 @@ __device__ __forceinline__ void cp_async_wait_all()
 // necessary condition for any non-negative solution on the tuple's four columns -- and the
 // tuples that pass are solved in closed form on the two supports the pair jobs do not cover.
 template <int CSF>
-__global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
+__global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     const int TXT = a.tr_txt, TYT = a.tr_tyt;
@@ -1311,88 +1326,90 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
     const int ld12 = a.ldr[0], ld13 = a.ldr[1], ld23 = a.ldr[2];
     unsigned long long *vthr = a.vthr + v;
 
-    // ---- voxel-wide starting threshold: certified lower bounds of the 2-column solutions ----
+    // ---- voxel-wide starting threshold: k_triple_seed left the best certified lower bound of the
+    // 2-column solutions and of the seed lines there; other CTAs of the voxel keep raising it ----
     if (tid == 0) {
-        double t0 = fmax(fmax(vp[5], vp[6]), vp[7]);
-        for (int j = 0; j < 3; j++) {
-            const int ntj = (a.Nb[a.job_rb[j]] + GP_TI - 1) / GP_TI;
-            for (int t = 0; t < ntj; t++) {
-                const int64_t o = (v * 3 + j) * a.ntI + t;
-                if (a.cta_idx[o] >= 0) t0 = fmax(t0, a.cta_gain[o] - a.cta_tol[o]);
-            }
-        }
-        t0 = fmax(t0 - c0, 0.0);
-        const unsigned long long old = atomicMax(vthr, (unsigned long long)__double_as_longlong(t0));
-        s_thr = old > (unsigned long long)__double_as_longlong(t0) ? old : (unsigned long long)__double_as_longlong(t0);
+        s_thr = *(volatile unsigned long long *)vthr;
         s_flag = 0;
     }
-    // padding steps (i3 >= N3): zero correlations and z3 = -1 give D3 < 0, never a candidate
-    // (CSF: the sign of D3 is not looked at; z3 = 0 and the competitive path skips the step)
-    for (int i = tid; i < ((N3 + 3) & ~3); i += blockDim.x) z3s[i] = i < N3 ? cpz3[i] : (CSF ? 0.0 : -1.0);
+    // padding steps (i3 >= N3): zero correlations and a hugely negative z3 give delta |delta| = -1e300,
+    // never a candidate (CSF: the sign of delta is not looked at; z3 = 0 and the competitive path
+    // skips the step)
+    for (int i = tid; i < ((N3 + 3) & ~3); i += blockDim.x) z3s[i] = i < N3 ? cpz3[i] : (CSF ? 0.0 : -1e150);
 
     // ---- chunk loader: rows i3 of R13^T[:, i1 tile] | R23^T[:, i2 tile] ----
     const int nchunks = (N3 + KC - 1) / KC;
     auto load_chunk = [&](int c, double *dst) {
-        const int segs = rowlen >> 1;
+        const int segs = rowlen >> 1, segs1 = T1 >> 1;
         const int rows = min(KC, ((N3 + 3) & ~3) - c * KC);
-        for (int e = tid; e < rows * segs; e += blockDim.x) {
-            const int r = e / segs, sg = e - r * segs;
-            const int i3 = min(c * KC + r, N3 - 1);
-            double *d = dst + (size_t)r * rowlen + 2 * sg;
-            const double *src;
-            bool ok = c * KC + r < N3;
-            if (!ok) { d[0] = 0.0; d[1] = 0.0; continue; }
-            if (2 * sg < T1) { const int col = i10 + 2 * sg; ok = col + 1 < ld13; src = R13T + (size_t)i3 * ld13 + col; }
-            else { const int col = i20 + 2 * sg - T1; ok = col + 1 < ld23; src = R23T + (size_t)i3 * ld23 + col; }
-            if (ok) cp_async16(d, src);
-            else { d[0] = 0.0; d[1] = 0.0; }
+        for (int r = warp; r < rows; r += nwarps) {
+            const int i3 = c * KC + r;
+            double *drow = dst + (size_t)r * rowlen;
+            const double *s13 = R13T + (size_t)min(i3, N3 - 1) * ld13 + i10;
+            const double *s23 = R23T + (size_t)min(i3, N3 - 1) * ld23 + i20 - T1;
+            for (int sg = lane; sg < segs; sg += 32) {
+                const bool first = sg < segs1;
+                const int col = 2 * sg;
+                const bool ok = i3 < N3 && (first ? i10 + col + 1 < ld13 : i20 + col - T1 + 1 < ld23);
+                if (ok) cp_async16(drow + col, (first ? s13 : s23) + col);
+                else { drow[col] = 0.0; drow[col + 1] = 0.0; }
+            }
         }
     };
     load_chunk(0, smem);
 
     // ---- the thread's 2 x 4 pairs ----
-    // z1 / z2 are only needed when the threshold moves or a tuple is competitive: they are
-    // re-read from colp (L1 / L2) there instead of being kept in registers
-    double r12[8], c33[8], U1[8], U2[8], Tp[8];
+    // per pair: r12, c33, U1 / c33, U2 / c33 and Tq = (thr' c33 - n2) / c33^2; per thread: z1 of
+    // its two rows and c0t = max over its pairs of c0 / c33^2 (the screen's error margin in the
+    // scaled test; the largest one keeps the test necessary for every pair of the thread).
+    // z2 is only needed when the threshold moves or a tuple is competitive: re-read from colp.
+    double r12[8], c33[8], U1p[8], U2p[8], Tq[8], z1r[2];
+    double c0t = 0.0;
     unsigned valid = 0;
+    bool illpair = false;
     auto zrow = [&](int p) { const int i = i10 + 2 * tx + p; return (active && i < N1) ? __ldg(cpz1 + i) : 0.0; };
     auto zcol = [&](int q) { const int j = i20 + 4 * ty + q; return (active && j < N2) ? __ldg(cpz2 + j) : 0.0; };
     auto retarget = [&](double th) {
-        double z1[2], z2[4];
-#pragma unroll
-        for (int p = 0; p < 2; p++) z1[p] = zrow(p);
+        double z2[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) z2[q] = zcol(q);
 #pragma unroll
-        for (int e = 0; e < 8; e++)
-            Tp[e] = fma(th - gshift, c33[e], -fma(z1[e >> 2], U1[e], z2[e & 3] * U2[e]));
+        for (int e = 0; e < 8; e++) {
+            // n2 / c33^2 = z1 U1p / c33 + z2 U2p / c33
+            const double ic = 1.0 / c33[e];
+            Tq[e] = ic * ((th - gshift) - fma(z1r[e >> 2], U1p[e], z2[e & 3] * U2p[e]));
+        }
     };
     cp_async_wait_all();
     __syncthreads();
     double thr = __longlong_as_double((long long)s_thr);
 #pragma unroll
+    for (int p = 0; p < 2; p++) z1r[p] = zrow(p);
+#pragma unroll
     for (int p = 0; p < 2; p++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = i10 + 2 * tx + p, j = i20 + 4 * ty + q, e = p * 4 + q;
-            const bool ok = active && i < N1 && j < N2;
+            bool ok = active && i < N1 && j < N2;
+            const double zz2 = zcol(q);
+            double rr = ok ? R12[(size_t)i * ld12 + j] : 0.0;
+            // (numerically) identical atoms in blocks 1 and 2, e.g. two fascicles along the same
+            // peak: every tuple of the pair is singular -> the voxel goes to the exact tier
+            if (ok && fma(-rr, rr, 1.0) < 1e-10) { illpair = true; ok = false; rr = 0.0; }
             if (ok) valid |= 1u << e;
-            const double zz1 = zrow(p), zz2 = zcol(q);
-            r12[e] = ok ? R12[(size_t)i * ld12 + j] : 0.0;
-            c33[e] = fma(-r12[e], r12[e], 1.0);
-            U1[e] = fma(-r12[e], zz2, zz1);
-            U2[e] = fma(-r12[e], zz1, zz2);
-            Tp[e] = fma(thr - gshift, c33[e], -fma(zz1, U1[e], zz2 * U2[e]));
+            r12[e] = rr;
+            c33[e] = fma(-rr, rr, 1.0);
+            const double ic = 1.0 / c33[e];
+            U1p[e] = ok ? fma(-rr, zz2, z1r[p]) * ic : 0.0;
+            U2p[e] = ok ? fma(-rr, z1r[p], zz2) * ic : 0.0;
+            c0t = fmax(c0t, c0 * ic * ic);
         }
+    retarget(thr);
 
     double gb = -1.0, tb = 0.0, gill = -1.0;
     long long bidx = -1;
     int flag = 0;
-    // (numerically) identical atoms in blocks 1 and 2, e.g. two fascicles along the same
-    // peak: every tuple of the pair is singular -> the voxel goes to the exact tier
-#pragma unroll
-    for (int e = 0; e < 8; e++)
-        if ((valid >> e & 1u) && c33[e] < 1e-10) gill = INFINITY;
+    if (illpair) gill = INFINITY;
 
     for (int c = 0; c < nchunks; c++) {
         if (c + 1 < nchunks) load_chunk(c + 1, smem + (size_t)((c + 1) & 1) * KC * rowlen);
@@ -1406,8 +1423,10 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
 #pragma unroll 1
         for (int r0 = 0; r0 < rows; r0 += 4) {
             // four i3 steps per vote: one basic block of 32 independent tuples for the scheduler.
-            // sgn[s] keeps the AND of the tuples' sign words of step s: bit 31 clear <=> some
-            // tuple of that step has positive weights and gain + bound >= thr
+            // The gain test is t = delta |delta| + c0t - Tq S >= 0: the |delta| form makes a negative
+            // w3 fail (unless the pair alone already reaches the threshold) without a sign word of its
+            // own.  sgn[s] keeps the AND of the tuples' sign words of step s: bit 31 clear <=> some
+            // tuple of that step has positive weights and gain + bound >= thr.
             int sgn[4];
 #pragma unroll
             for (int s4 = 0; s4 < 4; s4++) {
@@ -1420,34 +1439,41 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                 const double r23[4] = {r23a.x, r23a.y, r23b.x, r23b.y};
                 int sall = -1;
 #pragma unroll
-                for (int p = 0; p < 2; p++)
+                for (int p = 0; p < 2; p++) {
+                    const double m13 = fma(-r13[p], r13[p], 1.0);
+                    const double d13 = fma(-r13[p], z1r[p], z3);
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int e = p * 4 + q;
-                        const double q1 = fma(-r12[e], r23[q], r13[p]);
                         const double q2 = fma(-r12[e], r13[p], r23[q]);
-                        const double S = fma(-r23[q], q2, fma(-r13[p], q1, c33[e]));
-                        const double D3 = fma(-r23[q], U2[e], fma(-r13[p], U1[e], c33[e] * z3));
-                        const double t = fma(-Tp[e], S, fma(D3, D3, c0));
+                        const double S = fma(-q2, q2, c33[e] * m13);
+                        const double dl = fma(-q2, U2p[e], d13);
+                        const double t = fma(-Tq[e], S, fma(dl, CSF ? dl : fabs(dl), c0t));
                         if (CSF) {
                             sall &= __double2hiint(t);
                         } else {
-                            const double W1 = fma(-q1, D3, U1[e] * S);
-                            const double W2 = fma(-q2, D3, U2[e] * S);
-                            sall &= (__double2hiint(W1) | __double2hiint(W2) | __double2hiint(D3)) | __double2hiint(t);
+                            const double W2 = fma(-q2, dl, U2p[e] * S);
+                            const double q1 = fma(-r12[e], r23[q], r13[p]);
+                            const double W1 = fma(-q1, dl, U1p[e] * S);
+                            sall &= (__double2hiint(W1) | __double2hiint(W2)) | __double2hiint(t);
                         }
                     }
+                }
                 sgn[s4] = sall;
             }
             const int sany = (sgn[0] & sgn[1]) & (sgn[2] & sgn[3]);
-            if (__any_sync(0xffffffffu, sany >= 0)) {
+            const bool hit = __any_sync(0xffffffffu, sany >= 0);
+#ifdef TR_COUNT
+            if (lane == 0) { atomicAdd(&g_tr_counters[0], 1ull); if (hit) atomicAdd(&g_tr_counters[2], 1ull); }
+#endif
+            if (hit) {
                 if (sany >= 0) {
                     const double y_sq = vp[0];
                     const double c1 = y_sq > 0 ? c0 / y_sq : 0.0, ynorm = sqrt(y_sq);
                     const double tmax = 16.0 * c0, wide = 4.0 * tmax;
-                    double pc[8][4];
+                    double pc[8];
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { pc[e][0] = r12[e]; pc[e][1] = c33[e]; pc[e][2] = U1[e]; pc[e][3] = U2[e]; }
+                    for (int e = 0; e < 8; e++) pc[e] = r12[e];
                     const int smask = (sgn[0] >= 0 ? 1 : 0) | (sgn[1] >= 0 ? 2 : 0) | (sgn[2] >= 0 ? 4 : 0) | (sgn[3] >= 0 ? 8 : 0);
 #pragma unroll 1
                     for (int s4 = 0; s4 < 4; s4++) {
@@ -1459,7 +1485,9 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                         for (int e = 0; e < 8; e++) {
                             if (!(valid >> e & 1u)) continue;
                             const int p = e >> 2, q = e & 3;
-                            const double a12 = pc[e][0], k33 = pc[e][1], u1 = pc[e][2], u2 = pc[e][3];
+                            const double zz1 = zrow(p), zz2 = zcol(q);
+                            const double a12 = pc[e], k33 = fma(-a12, a12, 1.0);
+                            const double u1 = fma(-a12, zz2, zz1), u2 = fma(-a12, zz1, zz2);
                             const double a13 = rowp[2 * tx + p], a23 = rowp[T1 + 4 * ty + q];
                             const double q1 = fma(-a12, a23, a13), q2 = fma(-a12, a13, a23);
                             const double S = fma(-a23, q2, fma(-a13, q1, k33));
@@ -1472,7 +1500,10 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                                 // the full support (all four positive) and {atom 1, atom 2, atom 3} without the CSF
                                 // column -- two closed forms instead of a 15-support enumeration.
                                 if (c * KC + r >= N3) continue;
-                                if (!(fma(-Tp[e], S, fma(D3, D3, c0)) >= 0.0)) continue;
+                                if (!(fma(-fma(thr - gshift, k33, -fma(zz1, u1, zz2 * u2)), S, fma(D3, D3, c0)) >= 0.0)) continue;
+#ifdef TR_COUNT
+                                atomicAdd(&g_tr_counters[1], 1ull);
+#endif
                                 const int i1 = i10 + 2 * tx + p, i2 = i20 + 4 * ty + q, i3 = c * KC + r;
                                 const double *P1 = a.colp + (v * 3 + 0) * (int64_t)FT_NPAR * a.Npad;
                                 const double *P2 = a.colp + (v * 3 + 1) * (int64_t)FT_NPAR * a.Npad;
@@ -1492,7 +1523,6 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                                     const double wa = W1 / (dd * ka), wb = W2 / (dd * kb), wcc = D3 / (S * kc);
                                     const double wcsf = zc - fma(wa, ga, fma(wb, gbb, wcc * gc));
                                     if (wcsf > 0.0) {
-                                        const double zz1 = zrow(p), zz2 = zcol(q);
                                         gq = gshift + fma(fma(zz1, u1, zz2 * u2), S, D3 * D3) / dd;
                                         const double sw = wa + wb + wcc + wcsf, rel = c1 / dd;
                                         tq = fmin(4.0 * c0 / dd, 2.0 * c1 * fma(sw, sw, sw * ynorm) + 4.0 * rel * rel * y_sq);
@@ -1523,6 +1553,9 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                                 }
                                 if (gq < 0.0) continue;           // the tuple's optimum lies on a support of the pair jobs
                                 if (!(gq + tq >= thr)) continue;
+#ifdef TR_COUNT
+                                atomicAdd(&g_tr_counters[3], 1ull);
+#endif
                                 // (all of these margins are ~1e-11 of |y|^2, far below the gaps between tuples)
                                 const double tmax4 = 256.0 * c0, wide4 = 4.0 * tmax4;
                                 if (tq > tmax4) gill = fmax(gill, gq + tq);
@@ -1539,7 +1572,6 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, 1) k_triples(FastArgs a)
                             const double dd = k33 * S;
                             if (!(dd > 1e-13 && S > 0.0)) { gill = INFINITY; continue; }   // numerically singular
                             // Cramer-form gain and its (pessimistic) evaluation error bound
-                            const double zz1 = zrow(p), zz2 = zcol(q);
                             const double n2 = fma(zz1, u1, zz2 * u2);
                             double gq = fma(n2, S, D3 * D3) / dd, tq = c0 / dd;
                             if (!(gq + tq >= thr)) continue;
@@ -1680,6 +1712,16 @@ __global__ void __launch_bounds__(128) k_triple_seed(FastArgs a)
     __syncthreads();
     if (threadIdx.x == 0) {
         best = fmax(fmax(s_red[0], s_red[1]), fmax(s_red[2], s_red[3]));
+        // certified lower bounds of the 1- and 2-column solutions (pair jobs)
+        double t0 = fmax(fmax(vp[5], vp[6]), vp[7]);
+        for (int j = 0; j < 3; j++) {
+            const int ntj = (a.Nb[a.job_rb[j]] + GP_TI - 1) / GP_TI;
+            for (int t = 0; t < ntj; t++) {
+                const int64_t o = (v * 3 + j) * a.ntI + t;
+                if (a.cta_idx[o] >= 0) t0 = fmax(t0, a.cta_gain[o] - a.cta_tol[o]);
+            }
+        }
+        best = fmax(best, fmax(t0 - c0, 0.0));
         if (best > 0.0) atomicMax(a.vthr + v, (unsigned long long)__double_as_longlong(best));
     }
 }
@@ -1801,14 +1843,14 @@ __global__ void __launch_bounds__(128) k_select3(FastArgs a, int64_t V)
     if (reason >= 0 && a.reasons) atomicAdd(&a.reasons[reason], 1);
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     if (certain) {
-        if (a.csf) {
-            // four blocks [N1, N2, 1, N3]: product loop order of the reference's `_4up`
-            const long long N1 = a.Nb[0], N2 = a.Nb[1], N3 = a.Nb[2];
-            const long long i2 = I % N2, i1 = (I / N2) % N1, i3 = I / (N1 * N2);
-            a.tuple[row] = (i1 * N2 + i2) * N3 + i3;
-        } else {
-            a.tuple[row] = I;
-        }
+        // scan order -> the caller's blocks -> loop index of the reference
+        const long long n1 = a.Nb[0], n2 = a.Nb[1];
+        long long is[3] = {(I / n2) % n1, I % n2, I / (n1 * n2)}, ic[3], nc[3];
+        for (int k = 0; k < 3; k++) { ic[a.tr_perm[k]] = is[k]; nc[a.tr_perm[k]] = a.Nb[k]; }
+        if (a.csf)      // four blocks [N1, N2, 1, N3]: product loop order of the reference's `_4up`
+            a.tuple[row] = (ic[0] * nc[1] + ic[1]) * nc[2] + ic[2];
+        else            // `_3`: i3 outermost
+            a.tuple[row] = (ic[2] * nc[0] + ic[0]) * nc[1] + ic[1];
     } else {
         int pos = atomicAdd(a.redo_count, 1);
         a.redo_list[pos] = (int32_t)row;
@@ -2092,8 +2134,11 @@ bool fast3_supported_explicit(int M, const BlockSpec &bs)
     return true;
 }
 
-// thread layout (txt x tyt threads, 2 x 4 pairs each) wasting the fewest lanes and tile slots
-static TripleGeom triple_geom(int N1, int N2)
+// thread layout (txt x tyt threads, 2 x 4 pairs each) wasting the fewest lanes and tile slots.
+// cost: CTAs x (steps over the streamed block + the fixed cost of a CTA -- first chunk, pair
+// constants, reduction -- expressed in steps) x lanes x tile slots per useful pair
+#define TR_CTA_OVERHEAD_STEPS 40
+static TripleGeom triple_geom(int N1, int N2, int N3, double *cost_out)
 {
     TripleGeom best;
     memset(&best, 0, sizeof(best));
@@ -2101,19 +2146,45 @@ static TripleGeom triple_geom(int N1, int N2)
     for (int txt = 4; txt <= 64; txt++)
         for (int tyt = 2; tyt <= 48; tyt++) {
             const int nthr = txt * tyt;
-            if (nthr < 192 || nthr > TR_MAXTHREADS) continue;
+            if (nthr < TR_MAXTHREADS / 2 || nthr > TR_MAXTHREADS) continue;
             const int T1 = 2 * txt, T2 = 4 * tyt;
             const int nt1 = (N1 + T1 - 1) / T1, nt2 = (N2 + T2 - 1) / T2;
             const int threads = (nthr + 31) / 32 * 32;
-            // lanes x tile slots spent per useful pair; mild preference for full CTAs
-            const double cost = (double)nt1 * T1 * nt2 * T2 * threads / nthr * (1.0 + 0.02 * (TR_MAXTHREADS - threads) / 32);
+            // mild preference for full CTAs
+            const double cost = (double)nt1 * T1 * nt2 * T2 * threads / nthr * (1.0 + 0.02 * (TR_MAXTHREADS - threads) / 32) *
+                                (((N3 + 3) & ~3) + TR_CTA_OVERHEAD_STEPS);
             if (cost < best_cost) {
                 best_cost = cost;
                 best.txt = txt; best.tyt = tyt; best.T1 = T1; best.T2 = T2; best.nt1 = nt1; best.nt2 = nt2;
                 best.threads = threads;
             }
         }
+    if (cost_out) *cost_out = best_cost;
     return best;
+}
+
+// The scan tiles two blocks over the CTAs and streams the third: with a short third block (the
+// EAR compartment of MFModel.fit: ~10 atoms against 1000 per fascicle) a CTA would spend its life
+// in its prologue.  The blocks are therefore permuted so that the scan is cheapest by the cost
+// model above; k_select3 maps the winner back to the caller's loop order.
+static BlockSpec triple_permute(const BlockSpec &bs, int csf, int perm[3], TripleGeom *tg)
+{
+    static const int P[6][3] = {{0, 1, 2}, {1, 0, 2}, {0, 2, 1}, {2, 0, 1}, {1, 2, 0}, {2, 1, 0}};
+    double best_cost = 1e300;
+    int bp = 0;
+    TripleGeom bg;
+    memset(&bg, 0, sizeof(bg));
+    // (CSF-projected scan: the caller's order is kept -- its competitive path, not the stream length,
+    // sets the pace, and measured 10-20 % slower with the short block tiled)
+    for (int k = 0; k < (csf ? 1 : 6); k++) {
+        double c;
+        const TripleGeom g = triple_geom(bs.size[P[k][0]], bs.size[P[k][1]], bs.size[P[k][2]], &c);
+        if (c < best_cost * (1.0 - 1e-9)) { best_cost = c; bp = k; bg = g; }   // ties keep the caller's order
+    }
+    BlockSpec out = bs;
+    for (int k = 0; k < 3; k++) { perm[k] = P[bp][k]; out.size[k] = bs.size[perm[k]]; out.start[k] = bs.start[perm[k]]; }
+    if (tg) *tg = bg;
+    return out;
 }
 
 struct Fast3Layout {
@@ -2124,16 +2195,17 @@ struct Fast3Layout {
     size_t r_elems[3];
 };
 
-static Fast3Layout fast3_layout(int M, const BlockSpec &bs, int64_t V, int shared_dict)
+static Fast3Layout fast3_layout(int M, const BlockSpec &bs_caller, int64_t V, int shared_dict, int csf)
 {
     Fast3Layout L;
+    int perm[3];
+    const BlockSpec bs = triple_permute(bs_caller, csf, perm, &L.tg);
     L.Mp2 = (M + GP_KC - 1) / GP_KC * GP_KC;
     int nmax = 0;
     for (int b = 0; b < 3; b++) { L.Np[b] = (bs.size[b] + GP_TI - 1) / GP_TI * GP_TI; nmax = nmax > L.Np[b] ? nmax : L.Np[b]; }
     L.Npad = nmax;
     L.ldn = L.Np[0] + L.Np[1] + L.Np[2];
     L.ntI = nmax / GP_TI;
-    L.tg = triple_geom(bs.size[0], bs.size[1]);
     const int64_t Vd = shared_dict ? 1 : V;
     const size_t ntile = (size_t)L.tg.nt1 * L.tg.nt2;
     size_t o = 0;
@@ -2162,10 +2234,12 @@ static Fast3Layout fast3_layout(int M, const BlockSpec &bs, int64_t V, int share
 
 size_t fast3_scratch_bytes(int M, const BlockSpec &bs, int64_t V, int shared_dict)
 {
-    return fast3_layout(M, bs, V, shared_dict).total;
+    // (the CSF-projected scan keeps the caller's block order: a different tiling, never a larger R)
+    const size_t t0 = fast3_layout(M, bs, V, shared_dict, 0).total, t1 = fast3_layout(M, bs, V, shared_dict, 1).total;
+    return t0 > t1 ? t0 : t1;
 }
 
-int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda, int64_t strideA,
+int launch_fast_search3(int M, const BlockSpec &bs_caller, const double *A, int64_t lda, int64_t strideA,
                         int64_t V, const double *y, void *scratch, long long *tuple,
                         int32_t *redo_list, int32_t *redo_count, int32_t *reasons, cudaStream_t st,
                         cudaEvent_t *ev, const int32_t *vox_list, int a_by_local, int32_t *redo_local, int csf_col)
@@ -2173,9 +2247,10 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     if (V == 0) return MFB_OK;
     if (V > 65535) { set_error("triple scan: at most 65535 voxels per launch"); return MFB_EINVAL; }
     const int shared_dict = strideA == 0;
-    const Fast3Layout L = fast3_layout(M, bs, V, shared_dict);
+    const Fast3Layout L = fast3_layout(M, bs_caller, V, shared_dict, csf_col >= 0);
     FastArgs a;
     memset(&a, 0, sizeof(a));
+    const BlockSpec bs = triple_permute(bs_caller, csf_col >= 0, a.tr_perm, nullptr);
     a.p.M = M; a.src = 1;
     a.csf = csf_col >= 0 ? 1 : 0;        // the three searched blocks are projected off this column
     a.start3 = csf_col >= 0 ? csf_col : 0;
@@ -2221,7 +2296,8 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     {
         const int rowlen = L.tg.T1 + L.tg.T2;
         const size_t fixed = sizeof(double) * (((bs.size[2] + 3) & ~3) + 64);
-        int kc = (int)(((size_t)216 * 1024 - fixed) / (sizeof(double) * 2 * rowlen)) & ~3;
+        // TR_CTAS CTAs per SM: each gets its share of the 227 KB (1 KB per CTA is reserved)
+        int kc = (int)(((size_t)(224 / TR_CTAS - 2) * 1024 - fixed) / (sizeof(double) * 2 * rowlen)) & ~3;
         kc = kc > TR_KC_MAX ? TR_KC_MAX : kc;
         if (kc < 4) { set_error("triple scan: third block too large for shared memory"); return MFB_EUNSUPPORTED; }
         a.tr_kc = kc;
@@ -2233,6 +2309,17 @@ int launch_fast_search3(int M, const BlockSpec &bs, const double *A, int64_t lda
     }
     if (ev) MFB_CUDA_TRY(cudaEventRecord(ev[1], st));
     MFB_LAUNCH(k_select3, (unsigned)((V + 127) / 128), 128, 0, st, a, V);
+#ifdef TR_COUNT
+    {
+        unsigned long long h[4];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_tr_counters, sizeof(h));
+        fprintf(stderr, "k_triples votes %llu, hits %llu (%.4f), CSF: tuples passing the gain test %llu (%.2f per hit), competitive %llu\n", h[0], h[2],
+                (double)h[2] / (double)(h[0] ? h[0] : 1), h[1], (double)h[1] / (double)(h[2] ? h[2] : 1), h[3]);
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_tr_counters, h, sizeof(h));
+    }
+#endif
     return MFB_OK;
 }
 

@@ -13,7 +13,10 @@ from tests.phantom import make_phantom  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 V = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+ONLY = sys.argv[4] if len(sys.argv) > 4 else ""          # e.g. "NNE" or "NN1E": run one composition only
 for csf_frac, label in ((0.0, "[N,N,E]"), (1.0, "[N,N,1,E]")):
+    if ONLY and ONLY != label.replace("[", "").replace("]", "").replace(",", ""):
+        continue
     for ear_frac, what in ((1.0, "EAR active in every voxel"), (0.5, "EAR signal in half of the voxels")):
         ph = make_phantom(n_atoms=N, n_vox=V, seed=61, frac_k=(0, 0, 1), csf_frac=csf_frac, ear=True, n_ear=E,
                           ear_frac=ear_frac, ear_max_k=2)
