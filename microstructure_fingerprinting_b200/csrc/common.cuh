@@ -96,7 +96,7 @@ int launch_exact_search(int64_t V, int M, const BlockSpec &bs, const double *A, 
 inline int exact_mask_ld(const BlockSpec &bs)
 {
     const int n = bs.size[0] > bs.size[1] ? bs.size[0] : bs.size[1];
-    return (n + 63) / 64;
+    return (n + 63) / 64 * 64;     // one byte per atom, padded to the 64-atom tiles of k_pairs
 }
 
 // Copy the winning tuple's columns into Asmall[row(v)] (M x kMaxBlocks, row-major) and
@@ -146,8 +146,8 @@ struct FastProblem {
     int csf;            // a third, single-column block is present
     int a_by_local;     // explicit + vox_list: local voxel v reads A + v*strideA (vox_list maps y / tuple rows only)
     int32_t *redo_local;  // optional: local indices of the voxels handed to the exact tier
-    uint8_t *redo_mask;   // optional: [redo position][2][mask_ld] row / column tiles (64 atoms) the exact
-    int mask_ld;          // tier must scan for that voxel (see k_fast_select)
+    uint8_t *redo_mask;   // optional: [redo position][2][mask_ld] atoms of block 1 / block 2 whose rows / columns
+    int mask_ld;          // the exact tier must scan for that voxel (see k_fast_select)
 };
 bool fast_supported(const DevPlan &p, int K, int csf, int ear);
 bool fast_supported_explicit(int M, const BlockSpec &bs);

@@ -366,7 +366,7 @@ struct ExactArgs {
     long long *tile_idx;
     int ntiles;
     const int32_t *a_list;   // optional: dictionary index of voxel v (default: v itself)
-    const uint8_t *tile_mask;  // optional: [v][2][mask_ld] row / column tiles to scan (others are skipped)
+    const uint8_t *tile_mask;  // optional: [v][2][mask_ld] atoms of block 1 / 2 whose rows / columns are scanned (others are skipped)
     int mask_ld;
 };
 
@@ -465,10 +465,19 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
     __shared__ double sy[EX_KC];
     __shared__ Best red[32];
     const int64_t v = blockIdx.z;
+    const int tI = blockIdx.y * EX_T, tJ = blockIdx.x * EX_T;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    // `mine`: some pair of this thread lies in a row / column the search is restricted to
+    bool mine = true;
     if (a.tile_mask) {
         // the screening tier certified that the minimum lies in the rows / columns of a few atoms
+        // (one byte per atom, mask_ld a multiple of the tile size): tiles without such an atom are
+        // skipped, and inside a tile only the threads that own one of those rows / columns work
         const uint8_t *mk = a.tile_mask + (size_t)v * 2 * a.mask_ld;
-        if (!mk[blockIdx.y] && !mk[a.mask_ld + blockIdx.x]) {
+        const int t = threadIdx.x;
+        const bool any = t < EX_T ? (tI + t < a.mask_ld && mk[tI + t])
+                                  : (t < 2 * EX_T && tJ + t - EX_T < a.mask_ld && mk[a.mask_ld + tJ + t - EX_T]);
+        if (!__syncthreads_or(any)) {
             if (threadIdx.x == 0) {
                 const int tile = blockIdx.y * gridDim.x + blockIdx.x;
                 a.tile_res[v * a.ntiles + tile] = INFINITY;
@@ -476,11 +485,15 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
             }
             return;
         }
+        mine = false;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (tI + ty + 16 * r < a.mask_ld && mk[tI + ty + 16 * r]) mine = true;
+            if (tJ + tx + 16 * r < a.mask_ld && mk[a.mask_ld + tJ + tx + 16 * r]) mine = true;
+        }
     }
     const int64_t row = a.vox_list ? a.vox_list[v] : v;
     const int N1 = a.bs.size[0], N2 = a.bs.size[1];
-    const int tI = blockIdx.y * EX_T, tJ = blockIdx.x * EX_T;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const double *A = ex_A(a, v);
     const double *B1 = A + a.bs.start[0], *B2 = A + a.bs.start[1];
     const double *yv = a.y + row * a.y_ld;
@@ -505,7 +518,7 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
             s2[kk][cc] = x2;
         }
         __syncthreads();
-        for (int kk = 0; kk < kc; kk++) {
+        for (int kk = 0; mine && kk < kc; kk++) {
             double av[4], bv[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) av[r] = s1[kk][ty + 16 * r];
@@ -543,7 +556,7 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 int i1 = tI + ty + 16 * r, i2 = tJ + tx + 16 * c;
-                if (i1 < N1 && i2 < N2) {
+                if (mine && i1 < N1 && i2 < N2) {
                     double w0, w1;
                     double res = lsq2(y_sq, A11[r], acc[r][c], A22[c], Y1[r], Y2[c], w0, w1);
                     if (res < y_sq) best_take(b, res, (long long)i1 * N2 + i2);
@@ -565,7 +578,7 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
                         const int r = half * 2 + rr, q = rr * 4 + c;
                         const int i1 = tI + ty + 16 * r, i2 = tJ + tx + 16 * c;
                         res[q] = 0.0; w0[q] = w1[q] = w2[q] = 0.0;
-                        if (i1 < N1 && i2 < N2) {
+                        if (mine && i1 < N1 && i2 < N2) {
                             double a13 = a.cross13[(v * N1 + i1) * N3 + i3];
                             double a23 = a.cross23[(v * N2 + i2) * N3 + i3];
                             if (cramer3(A11[r], acc[r][c], a13, A22[c], a23, a33, Y1[r], Y2[c], Y3,
@@ -618,7 +631,7 @@ __global__ void __launch_bounds__(256) k_pairs(ExactArgs a)
                     for (int c = 0; c < 4; c++) {
                         const int r = half * 2 + rr, q = rr * 4 + c;
                         const int i1 = tI + ty + 16 * r, i2 = tJ + tx + 16 * c;
-                        if (i1 < N1 && i2 < N2) {
+                        if (mine && i1 < N1 && i2 < N2) {
                             double rs = res[q];
                             if (!(posmask & (1u << q))) {
                                 double a13 = a.cross13[(v * N1 + i1) * N3 + i3];

@@ -93,7 +93,7 @@ struct FastArgs {
     int64_t dn_stride;
     int ldn, N1pad, Mp2;
     int32_t *redo_local;  // local indices of the voxels handed to the exact tier
-    uint8_t *redo_mask;   // [redo position][2][mask_ld]: 64-atom row / column tiles the exact tier must scan
+    uint8_t *redo_mask;   // [redo position][2][mask_ld]: atoms whose rows / columns the exact tier must scan
     int mask_ld;
     int nblk;          // searched blocks (2, or 3 for the triple scan)
     int Nb[3], startb[3], dnoff[3];   // atoms, first column in A, first column in Dn of each block
@@ -1900,7 +1900,7 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
             // No competitive pair at all: the winner is a solution with one fascicle atom
             // (alone or with the CSF column).  Every tuple that can reach the minimum then lies
             // in the row of an atom of block 1, or the column of an atom of block 2, whose
-            // single-solution gain is within the margin of the best: only those 64-atom tiles
+            // single-solution gain is within the margin of the best: only those rows / columns
             // need the reference-order search.  Not applicable when the CSF-only or the
             // all-zero solution could win (their first tuple in loop order can be anywhere).
             uint8_t *mk = a.redo_mask + (size_t)pos * 2 * a.mask_ld;
@@ -1912,7 +1912,7 @@ __global__ void __launch_bounds__(128) k_fast_select(FastArgs a, int64_t V)
                     const double *gs = a.colp + ((v * a.nblk + k) * (int64_t)FT_NPAR + 7) * a.Npad;
                     const int Nk = a.Nb[k];
                     for (int i = 0; i < Nk; i++)
-                        if (gs[i] >= gpre - margin) mk[k * a.mask_ld + (i >> 6)] = 1;
+                        if (gs[i] >= gpre - margin) mk[k * a.mask_ld + i] = 1;
                 }
         }
     }

@@ -1,5 +1,5 @@
 """Device-resident fit throughput at the benchmark shape, small and quick (kernel A/B runs:
-MFB_LIB selects the library build).  usage: quick_fit_bench.py [voxels] [csf_frac]"""
+MFB_LIB selects the library build).  usage: quick_fit_bench.py [voxels] [csf_frac] [flags] [snr]"""
 import sys
 import time
 
@@ -13,7 +13,8 @@ from tests.phantom import make_phantom  # noqa: E402
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 csf_frac = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 2     # 2: kernel bracketed by events (single stream); 0: production path
-ph = make_phantom(n_atoms=1000, n_vox=V, seed=100, frac_k=(0, 0, 1), csf_frac=csf_frac)
+snr = float(sys.argv[4]) if len(sys.argv) > 4 else 30.0
+ph = make_phantom(n_atoms=1000, n_vox=V, seed=100, frac_k=(0, 0, 1), csf_frac=csf_frac, snr=snr)
 msi = mfu.init_PGSE_multishell_interp(ph.dic["dictionary"], ph.dic["sch_mat"], ph.dic["orientation"])
 plan = mfu.GpuPlan(msi, mfu.SchemePlan(msi, ph.sch), ph.sig_csf, None)
 dev = torch.device("cuda")
@@ -31,6 +32,6 @@ for rep in range(3):
 st = plan.stats()
 F = 0.7 * (2.0 * 105 * 1e6 + 4.0 * 105 * 2000 + 210 + 25e6 + 3.0 * 105 * 2000) + \
     0.3 * (2.0 * 105 * (1e6 + 2000) + 4.0 * 105 * 2001 + 210 + 65e6 + 3.0 * 105 * 2000)
-print("%s: %.0f voxels/s; pair kernel %.2f TFLOP/s algorithmic (%.1f ms per launch); exact-tier voxels %d; checksum %.6f"
-      % (_lib.LIB_PATH.split("/")[-1], V / best, F * st[4] / (st[2] / 1e3) / 1e12 if st[2] else 0, st[2] / max(st[3], 1), st[1],
+print("SNR %g, %s: %.0f voxels/s; pair kernel %.2f TFLOP/s algorithmic (%.1f ms per launch); exact-tier voxels %d; checksum %.6f"
+      % (snr, _lib.LIB_PATH.split("/")[-1], V / best, F * st[4] / (st[2] / 1e3) / 1e12 if st[2] else 0, st[2] / max(st[3], 1), st[1],
          float(out[:, 0].sum())))
