@@ -56,3 +56,23 @@ hit = float(np.mean(np.all(sub[okv] == truth[okv], axis=1)))
 print("M %d N %d V %d: %.1f voxels/s end to end (%.2f TFLOP/s algorithmic, %.0f%% of DGEMM peak 35.47); "
       "screened %d redone %d reasons %s; valid voxels %d; planted pairs recovered %.3f"
       % (M, N, V, V / best, F * V / best / 1e12, 100 * F * V / best / 35.47e12, st[0], st[1], st[2:], int(okv.sum()), hit))
+
+# search only: one chunk's dictionaries already assembled on the GPU (what the pipeline would reach
+# if the host plans, the uploads and the assembly cost nothing)
+import torch  # noqa: E402
+dev = torch.device("cuda")
+nv = min(V, CHUNK)
+A = torch.empty((nv, M, 2 * N), dtype=torch.float64, device=dev)
+for k in range(2):
+    A[:, :, k * N:(k + 1) * N] = mfu.rotate_atom_2Dprotocol(sig, sch, ref, peaks[:nv, k], DIFF, return_device=True)
+Yg = torch.from_numpy(Y[:nv]).to(dev)
+sizes = np.array([N, N], dtype=np.int64)
+best_s = 1e30
+for rep in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = mfu.solve_exhaustive_posweights_batch(A, Yg, sizes, return_device=True)
+    torch.cuda.synchronize()
+    best_s = min(best_s, time.perf_counter() - t0)
+print("search only (%d voxels resident): %.1f voxels/s = %.0f%% of DGEMM peak; end to end / search only = %.3f"
+      % (nv, nv / best_s, 100 * F * nv / best_s / 35.47e12, (V / best) / (nv / best_s)))
