@@ -1257,10 +1257,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 //     delta = d13 - q2 (U2 / c33)           (Cramer numerator of w3 over c33)
 //     W1 / c33 = (U1 / c33) S - q1 delta,  W2 / c33 = (U2 / c33) S - q2 delta
 //     gain >= thr  <=>  delta^2 >= S (thr c33 - n2) / c33^2,   n2 = z1 U1 + z2 U2
-// 11.5 FP64 operations per tuple (6.5 for the CSF-projected scan, which does not look at the
-// signs of W1, W2), no division; "all weights positive and gain + error bound >= thr" is decided
-// on the sign bits of four doubles with integer instructions.  (Round 1 evaluated S, D3, W1, W2
-// in the symmetric form: 13 / 9 operations.)  The isolated loop (tools/triples_loop_bench.cu) runs
+// No division; signs are read off the high words with integer instructions.  The vote over 4 i3
+// steps (32 tuples per thread) tests gain + error bound >= thr (in the delta |delta| form, which
+// also asks for w3 > 0) and w2 > 0: 8.5 FP64 operations per tuple (6.5 for the CSF-projected scan,
+// which tests the gain only).  Only when some lane passes does the warp evaluate the sign of W1
+// as well -- 3 more operations, q1 is needed for nothing else -- straight-line for the flagged
+// steps, and only what passes both levels is walked tuple by tuple.  (Round 1 evaluated S, D3, W1,
+// W2 in the symmetric form, all in the vote: 13 / 9 operations; with W1 in the first level the
+// scan ran at 28.0 k instead of 34.6 k voxels/s at [300, 300, 300].)  The isolated loop (tools/triples_loop_bench.cu) runs
 // at 1.10 T tuples/s whatever the thread tile or the number of warps: FP64 instructions hold the
 // issue port for ~2.2 cycles each and every other instruction (sign logic, shared-memory loads)
 // adds its own cycle, so the count of instructions per tuple is what sets the pace.
@@ -1270,6 +1274,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 #define TR_CTAS 1            // CTAs per SM (2: measured slower, 25.6 k against 27.4 k voxels/s at [300,300,300])
 #endif
 #define TR_MAXTHREADS (384 / TR_CTAS)
+#ifndef TR_W1VOTE
+#define TR_W1VOTE 0          // 1: the sign of W1 is part of the first-level vote (11.5 operations per tuple)
+#endif
 
 #ifdef TR_COUNT
 __device__ unsigned long long g_tr_counters[4];   // votes, CSF tuples passing the gain test, votes that hit, competitive tuples
@@ -1453,16 +1460,61 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
                             sall &= __double2hiint(t);
                         } else {
                             const double W2 = fma(-q2, dl, U2p[e] * S);
+#if TR_W1VOTE
                             const double q1 = fma(-r12[e], r23[q], r13[p]);
                             const double W1 = fma(-q1, dl, U1p[e] * S);
                             sall &= (__double2hiint(W1) | __double2hiint(W2)) | __double2hiint(t);
+#else
+                            sall &= __double2hiint(W2) | __double2hiint(t);
+#endif
                         }
                     }
                 }
                 sgn[s4] = sall;
             }
-            const int sany = (sgn[0] & sgn[1]) & (sgn[2] & sgn[3]);
-            const bool hit = __any_sync(0xffffffffu, sany >= 0);
+            int sany = (sgn[0] & sgn[1]) & (sgn[2] & sgn[3]);
+            bool hit = __any_sync(0xffffffffu, sany >= 0);
+#if !TR_W1VOTE
+            if (!CSF && hit) {
+                // second level, only for the steps in which some lane passed the first (warp-uniform
+                // mask): the same test with the sign of W1 as well, straight-line over the thread's 8
+                // tuples, before any lane walks its tuples one by one
+                const unsigned m1 = __reduce_or_sync(0xffffffffu, (sgn[0] >= 0 ? 1u : 0u) | (sgn[1] >= 0 ? 2u : 0u) |
+                                                                      (sgn[2] >= 0 ? 4u : 0u) | (sgn[3] >= 0 ? 8u : 0u));
+#pragma unroll 1
+                for (int s4 = 0; s4 < 4; s4++) {
+                    if (!(m1 >> s4 & 1u)) continue;
+                    const double *rowp = B + (size_t)(r0 + s4) * rowlen;
+                    const double2 r13v = *reinterpret_cast<const double2 *>(rowp + 2 * tx);
+                    const double2 r23a = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty);
+                    const double2 r23b = *reinterpret_cast<const double2 *>(rowp + T1 + 4 * ty + 2);
+                    const double z3 = z3s[c * KC + r0 + s4];
+                    const double r13[2] = {r13v.x, r13v.y};
+                    const double r23[4] = {r23a.x, r23a.y, r23b.x, r23b.y};
+                    int sall = -1;
+#pragma unroll
+                    for (int p = 0; p < 2; p++) {
+                        const double m13 = fma(-r13[p], r13[p], 1.0);
+                        const double d13 = fma(-r13[p], z1r[p], z3);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int e = p * 4 + q;
+                            const double q2 = fma(-r12[e], r13[p], r23[q]);
+                            const double S = fma(-q2, q2, c33[e] * m13);
+                            const double dl = fma(-q2, U2p[e], d13);
+                            const double t = fma(-Tq[e], S, fma(dl, fabs(dl), c0t));
+                            const double W2 = fma(-q2, dl, U2p[e] * S);
+                            const double q1 = fma(-r12[e], r23[q], r13[p]);
+                            const double W1 = fma(-q1, dl, U1p[e] * S);
+                            sall &= (__double2hiint(W1) | __double2hiint(W2)) | __double2hiint(t);
+                        }
+                    }
+                    if (s4 == 0) sgn[0] = sall; else if (s4 == 1) sgn[1] = sall; else if (s4 == 2) sgn[2] = sall; else sgn[3] = sall;
+                }
+                sany = (sgn[0] & sgn[1]) & (sgn[2] & sgn[3]);
+                hit = __any_sync(0xffffffffu, sany >= 0);
+            }
+#endif
 #ifdef TR_COUNT
             if (lane == 0) { atomicAdd(&g_tr_counters[0], 1ull); if (hit) atomicAdd(&g_tr_counters[2], 1ull); }
 #endif

@@ -37,9 +37,9 @@ for rep in range(int(os.environ.get("REPS", "3"))):
 st = _lib.solve_stats()
 rec = [float((out[1][:, k] == idx[k]).double().mean()) for k in range(3)]
 F_ref = 2.0 * M * 3 * N * N + 4.0 * M * nt + 65.0 * N ** 3     # SURVEY 8d count (c3 = 65)
-F_own = 2.0 * M * 3 * N * N + 4.0 * M * nt + 23.0 * N ** 3     # 11.5 FP64 ops per tuple executed here
+F_own = 2.0 * M * 3 * N * N + 4.0 * M * nt + 17.0 * N ** 3     # 8.5 FP64 ops per tuple in the first-level vote
 print("sizes %s V %d: %.1f voxels/s; %.2f TFLOP/s at the reference's 65 flop/tuple, %.2f TFLOP/s executed "
-      "(11.5 FMA-pipe ops/tuple, %.0f%% of the 37.1 TFLOP/s FP64 pipe); screened %d, redone %d, reasons %s; planted recovered %s"
+      "(8.5 FMA-pipe ops/tuple in the first-level vote, %.0f%% of the 37.1 TFLOP/s FP64 pipe); screened %d, redone %d, reasons %s; planted recovered %s"
       % (sizes.tolist(), V, V / best, F_ref * V / best / 1e12, F_own * V / best / 1e12,
          100 * F_own * V / best / 37.1e12, st[0], st[1], st[2:], rec))
 if os.environ.get("BENCH_EXACT"):
