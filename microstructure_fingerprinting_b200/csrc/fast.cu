@@ -1044,9 +1044,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
             mbar_wait(&s_full[st], (unsigned)(s / GP_NS) & 1u);
             const double *A_ = stages + (size_t)st * GP_STAGE + (size_t)t4 * GP_S1 + wrow + g;
             const double *B_ = stages + (size_t)st * GP_STAGE + GP_KC * GP_S1 + (size_t)t4 * GP_S2 + g;
+            // the rows of the last chunk beyond M are zero padding: their k-steps are skipped
+            // (M = 105: 3 instead of 8 k-steps in the fourth chunk, 16 % of the kernel's DMMA work)
+            const int nks = ch == nch - 1 ? (a.p.M - ch * GP_KC + 3) >> 2 : GP_KC / 4;
             if (ntv == 8 && mtv == 2) {
 #pragma unroll 2
-                for (int ks = 0; ks < GP_KC / 4; ks++) {
+                for (int ks = 0; ks < nks; ks++) {
                     double af[2], bf[8];
 #pragma unroll
                     for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * GP_S1 + 8 * mt];
@@ -1062,7 +1065,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
                 }
             } else {
 #pragma unroll 1
-                for (int ks = 0; ks < GP_KC / 4; ks++) {
+                for (int ks = 0; ks < nks; ks++) {
                     double af[2], bf[8];
 #pragma unroll
                     for (int mt = 0; mt < 2; mt++) af[mt] = A_[(size_t)ks * 4 * GP_S1 + 8 * mt];
