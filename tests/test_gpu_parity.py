@@ -607,7 +607,10 @@ def test_solve_batch_tiny_magnitude_follows_reference_tolerance(sizes, M, scale)
 
 @pytest.mark.parametrize("sizes,M,planted,signed", [([60, 70, 50], 100, 3, False), ([300, 300, 300], 100, 3, False),
                                                     ([90, 90, 6], 105, 3, False), ([33, 47, 129], 150, 3, False),
-                                                    ([64, 64, 64], 60, 2, False), ([50, 40, 30], 80, 3, True)])
+                                                    ([64, 64, 64], 60, 2, False), ([50, 40, 30], 80, 3, True),
+                                                    # the scan streams its largest block: every position of a short one
+                                                    ([6, 90, 90], 105, 3, False), ([90, 6, 90], 105, 3, False),
+                                                    ([5, 200, 37], 64, 3, False), ([150, 9, 11], 100, 2, False)])
 def test_solve_batch_triple_scan_equals_exact(sizes, M, planted, signed):
     """Three searched blocks (reference `_3`, mf_utils.py:470-607; BASELINE config 4 shape
     [300, 300, 300]): the DMMA + FP64 triple scan must return exactly what the
