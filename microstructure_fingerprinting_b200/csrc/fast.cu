@@ -1251,8 +1251,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 // screening pass also yields the best 2-column solutions, i.e. every branch of `_3` that
 // does not depend on the third index).  k_triples then enumerates all N1*N2*N3 tuples on the
 // FP64 pipe: a CTA owns a (T1 x T2) tile of (i1, i2) pairs, every thread keeps 2 x 4 pairs in
-// registers and streams over i3 through a cp.async double-buffered shared-memory ring of
-// R13^T / R23^T rows.  Everything is written in the basis that eliminates atom 1 first, so that
+// registers and streams over i3 through a double-buffered shared-memory ring of R13^T / R23^T rows
+// filled by TMA bulk copies.  Everything is written in the basis that eliminates atom 1 first, so that
 // what depends on (i1, i3) only is shared by the thread's four i2 columns.  With
 // c33 = 1 - r12^2, U2 = z2 - r12 z1 (per pair), m13 = 1 - r13^2, d13 = z3 - r13 z1 (per (i1, i3),
 // 2 operations for 4 tuples), q2 = r23 - r12 r13, q1 = r13 - r12 r23:
@@ -1289,16 +1289,6 @@ struct TripleGeom {
     int txt, tyt, T1, T2, nt1, nt2, threads;
 };
 
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
 // CSF: the three searched blocks are projected off a fourth, single-column block (two
 // fascicles + CSF + the EAR block of MFModel.fit, reference `_4up`).  The scan then tests the
 // UNCONSTRAINED gain of the projected triple against the threshold minus the CSF share -- a
@@ -1315,6 +1305,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
     double *z3s = smem + (size_t)2 * KC * rowlen;       // [N3]
     double *red = z3s + ((N3 + 3) & ~3);                   // [64]
     __shared__ unsigned long long s_thr;
+    __shared__ unsigned long long s_cfull[2];            // chunk ring: bytes landed (TMA bulk copies)
     __shared__ double s_tolG;
     __shared__ int s_flag;
 
@@ -1341,32 +1332,38 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
     if (tid == 0) {
         s_thr = *(volatile unsigned long long *)vthr;
         s_flag = 0;
+        mbar_init(&s_cfull[0], 1);
+        mbar_init(&s_cfull[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
     // padding steps (i3 >= N3): zero correlations and a hugely negative z3 give delta |delta| = -1e300,
     // never a candidate (CSF: the sign of delta is not looked at; z3 = 0 and the competitive path
     // skips the step)
     for (int i = tid; i < ((N3 + 3) & ~3); i += blockDim.x) z3s[i] = i < N3 ? cpz3[i] : (CSF ? 0.0 : -1e150);
 
-    // ---- chunk loader: rows i3 of R13^T[:, i1 tile] | R23^T[:, i2 tile] ----
+    // ---- chunk loader: rows i3 of R13^T[:, i1 tile] | R23^T[:, i2 tile], two TMA bulk copies per
+    // row issued by the row's thread, completion counted in bytes on the buffer's mbarrier (the
+    // cp.async loader of the first version was 5 % of the kernel in address arithmetic) ----
     const int nchunks = (N3 + KC - 1) / KC;
-    auto load_chunk = [&](int c, double *dst) {
-        const int segs = rowlen >> 1, segs1 = T1 >> 1;
-        const int rows = min(KC, ((N3 + 3) & ~3) - c * KC);
-        for (int r = warp; r < rows; r += nwarps) {
+    const int w1 = min(T1, ld13 - i10), w2 = min(T2, ld23 - i20);     // tile columns inside the padded R
+    auto load_chunk = [&](int c, double *dst, unsigned long long *bar) {
+        const int rows = min(KC, ((N3 + 3) & ~3) - c * KC), real = min(KC, N3 - c * KC);
+        if (tid == 0) mbar_expect_tx(bar, (unsigned)(real * (w1 + w2) * sizeof(double)));
+        for (int r = tid; r < rows; r += blockDim.x) {
             const int i3 = c * KC + r;
             double *drow = dst + (size_t)r * rowlen;
-            const double *s13 = R13T + (size_t)min(i3, N3 - 1) * ld13 + i10;
-            const double *s23 = R23T + (size_t)min(i3, N3 - 1) * ld23 + i20 - T1;
-            for (int sg = lane; sg < segs; sg += 32) {
-                const bool first = sg < segs1;
-                const int col = 2 * sg;
-                const bool ok = i3 < N3 && (first ? i10 + col + 1 < ld13 : i20 + col - T1 + 1 < ld23);
-                if (ok) cp_async16(drow + col, (first ? s13 : s23) + col);
-                else { drow[col] = 0.0; drow[col + 1] = 0.0; }
+            if (r < real) {
+                bulk_g2s(drow, R13T + (size_t)i3 * ld13 + i10, (unsigned)(w1 * sizeof(double)), bar);
+                bulk_g2s(drow + T1, R23T + (size_t)i3 * ld23 + i20, (unsigned)(w2 * sizeof(double)), bar);
+                for (int col = w1; col < T1; col++) drow[col] = 0.0;
+                for (int col = w2; col < T2; col++) drow[T1 + col] = 0.0;
+            } else {
+                for (int col = 0; col < rowlen; col++) drow[col] = 0.0;
             }
         }
     };
-    load_chunk(0, smem);
+    load_chunk(0, smem, &s_cfull[0]);
 
     // ---- the thread's 2 x 4 pairs ----
     // per pair: r12, c33, U1 / c33, U2 / c33 and Tq = (thr' c33 - n2) / c33^2; per thread: z1 of
@@ -1390,7 +1387,6 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
             Tq[e] = ic * ((th - gshift) - fma(z1r[e >> 2], U1p[e], z2[e & 3] * U2p[e]));
         }
     };
-    cp_async_wait_all();
     __syncthreads();
     double thr = __longlong_as_double((long long)s_thr);
 #pragma unroll
@@ -1422,8 +1418,9 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
     if (illpair) gill = INFINITY;
 
     for (int c = 0; c < nchunks; c++) {
-        if (c + 1 < nchunks) load_chunk(c + 1, smem + (size_t)((c + 1) & 1) * KC * rowlen);
+        if (c + 1 < nchunks) load_chunk(c + 1, smem + (size_t)((c + 1) & 1) * KC * rowlen, &s_cfull[(c + 1) & 1]);
         const double *B = smem + (size_t)(c & 1) * KC * rowlen;
+        mbar_wait(&s_cfull[c & 1], (unsigned)(c >> 1) & 1u);
         const int rows = min(KC, N3 - c * KC);
         {   // pick up the voxel-wide threshold raised by other CTAs / warps
             double tn = fmax(__longlong_as_double((long long)s_thr),
@@ -1662,8 +1659,7 @@ __global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
                 if (tn > thr) { thr = tn; retarget(thr); }
             }
         }
-        cp_async_wait_all();
-        __syncthreads();
+        __syncthreads();       // every thread is done with this buffer before its next load is issued
     }
 
     // ---- reduction over the CTA: best gain, tie -> lower loop index ----
