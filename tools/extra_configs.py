@@ -245,10 +245,49 @@ def config_real_dictionary(peak, V=32768):
         "oracle_index_match": "%d/8" % ok}}
 
 
+def config1(peak):
+    """BASELINE config 1, the reference's own CPU-runnable case: MFModel.fit on the 16 x 16 x 4
+    numfasc = 1 (+ CSF) phantom with the real 986-atom dictionary, NumPy arrays in and maps out.
+    Inputs and expected maps: tests/golden/full_config1.npz, written by the unmodified reference
+    (parallel=False, 2.3 s there).  Reports the wall time of a whole fit call (plans cached, i.e. the
+    second and later calls of a session) and of the first call, and checks every map."""
+    from microstructure_fingerprinting_b200 import MFModel
+    from tests import phantom
+    g = np.load(os.path.join(ROOT, "tests", "golden", "full_config1.npz"))
+    d = np.load(os.path.join(ROOT, "tests", "golden", "ukbb_dictionary.npz"))
+    dic = {k: d[k] for k in d.files}
+    dic.update(num_atom=int(dic["num_atom"]), num_ear=int(dic["num_ear"]), fasc_propnames=["rad", "fin"])
+    sch = phantom.load_schemes()[1]
+    shape = (16, 16, 4)
+    Y = g["Y"].astype(np.float64).reshape(shape + (-1,))
+    args = (Y, np.ones(shape), g["K"].astype(float).reshape(shape))
+    kw = dict(peaks=g["peaks"].reshape(shape + (6,)), pgse_scheme=sch, csf_mask=g["csf"].reshape(shape), verbose=0)
+    model = MFModel(dic)
+    t0 = time.perf_counter()
+    fit = model.fit(*args, **kw)
+    t_first = time.perf_counter() - t0
+    best = 1e30
+    for rep in range(5):
+        t0 = time.perf_counter()
+        fit = model.fit(*args, **kw)
+        best = min(best, time.perf_counter() - t0)
+    model.close()
+    ok = True
+    for name in ("M0", "frac_f0", "frac_csf", "rad_f0", "fin_f0", "MSE", "R2"):
+        key = "fit_" + name
+        if key in g.files:
+            # (MSE: floor of 1e-12 |y|^2 / M as in the tests -- noise-free voxels have residuals of rounding size)
+            atol = 1e-12 * float(np.max(np.sum(Y ** 2, axis=-1))) / Y.shape[-1] if name == "MSE" else 1e-12
+            ok = ok and bool(np.allclose(getattr(fit, name).ravel(), g[key].ravel(), rtol=1e-9, atol=atol))
+    return {"MFModel.fit 16x16x4 numfasc=1 + CSF, real 986-atom dictionary": {
+        "voxels": 1024, "fit_call_ms": best * 1e3, "first_call_ms": t_first * 1e3, "voxels_per_s": 1024 / best,
+        "reference_s": float(g["ref_seconds"]) if "ref_seconds" in g.files else 2.3, "maps_match_reference_golden": ok}}
+
+
 def run_extra_configs(peak):
     from microstructure_fingerprinting_b200 import _lib
     out = {}
-    for name, fn in (("config2_solve_batch_per_voxel_A", config2), ("config4_numfasc3", config4),
+    for name, fn in (("config1_reference_cpu_case", config1), ("config2_solve_batch_per_voxel_A", config2), ("config4_numfasc3", config4),
                      ("config5_axcaliber_2D", config5), ("fit_with_ear_compartment", config_ear),
                      ("real_ukbb_dictionary", config_real_dictionary)):
         t0 = time.perf_counter()
