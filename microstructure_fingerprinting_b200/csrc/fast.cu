@@ -21,11 +21,13 @@
 //                  TMA bulk copies (cp.async.bulk + mbarrier complete_tx) from a normalised
 //                  copy of the dictionaries; same epilogue.  With STORE it also writes the
 //                  correlation matrices for the triple scan;
-//   k_triples      three searched blocks: 13 FP64 operations per tuple from the correlation
-//                  matrices, sign-bit test, warp vote every four steps;
+//   k_triple_seed + k_triples   three searched blocks (permuted so that the largest is the
+//                  streamed one): 8.5 FP64 operations per tuple from the correlation matrices in
+//                  the first-level warp vote (every four steps, sign-bit tests), the last weight
+//                  sign in a straight-line second level, chunk ring filled by TMA bulk copies;
 //   k_fast_select / k_select3   merge the tiles of a voxel and decide whether the winner is
 //                  certain; k_fast_select also restricts the reference-order search of voxels
-//                  won by a one-atom solution to the tiles that can hold the minimum.
+//                  won by a one-atom solution to the rows / columns that can hold the minimum.
 // Screening works on gains (|y|^2 - residual) in a different summation order than the
 // reference, so it only *selects*: the winning tuple is re-evaluated in the reference's
 // arithmetic by the exact tier's evaluate kernel, and every voxel whose winner is not
