@@ -10,7 +10,8 @@ from tests.phantom import make_phantom  # noqa: E402
 
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
 cases = [(1000, 30.0, 0.3, "exact"), (1000, 100.0, 0.5, "exact"), (500, 10.0, 0.3, "exact"), (257, 1e6, 0.5, "exact"),
-         (300, 30.0, 0.4, "between")]
+         (300, 30.0, 0.4, "between"),
+         (1000, 5.0, 0.3, "exact"), (777, 3.0, 0.5, "exact")]      # low SNR: one-atom winners, per-atom restriction masks
 bad = 0
 for n_atoms, snr, csf_frac, scheme in cases:
     nv = V if scheme == "exact" else V // 4
