@@ -1275,10 +1275,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 // adds its own cycle, so the count of instructions per tuple is what sets the pace.
 // ---------------------------------------------------------------------------------
 #define TR_KC_MAX 128        // i3 steps per chunk: as many as fit in shared memory, at most this
-#ifndef TR_CTAS
-#define TR_CTAS 1            // CTAs per SM (2: measured slower, 25.6 k against 27.4 k voxels/s at [300,300,300])
-#endif
-#define TR_MAXTHREADS (384 / TR_CTAS)
+#define TR_MAXTHREADS 384     // per SM: one CTA of up to 384 threads, or two of up to 192 (k_triples<CSF, 2>) when
+                              // the tiling cannot use more than 256 threads in one CTA (a short tiled block: T1 = 2 x 5
+                              // for the 10-atom EAR block leaves 240 threads) -- [N,N,E] +6 %, [300,300,300] -1 %
 #ifndef TR_W1VOTE
 #define TR_W1VOTE 0          // 1: the sign of W1 is part of the first-level vote (11.5 operations per tuple)
 #endif
@@ -1288,7 +1287,7 @@ __device__ unsigned long long g_tr_counters[4];   // votes, CSF tuples passing t
 #endif
 
 struct TripleGeom {
-    int txt, tyt, T1, T2, nt1, nt2, threads;
+    int txt, tyt, T1, T2, nt1, nt2, threads, ctas;
 };
 
 // CSF: the three searched blocks are projected off a fourth, single-column block (two
@@ -1296,8 +1295,8 @@ struct TripleGeom {
 // UNCONSTRAINED gain of the projected triple against the threshold minus the CSF share -- a
 // necessary condition for any non-negative solution on the tuple's four columns -- and the
 // tuples that pass are solved in closed form on the two supports the pair jobs do not cover.
-template <int CSF>
-__global__ void __launch_bounds__(TR_MAXTHREADS, TR_CTAS) k_triples(FastArgs a)
+template <int CSF, int CTAS>
+__global__ void __launch_bounds__(TR_MAXTHREADS / CTAS, CTAS) k_triples(FastArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     const int TXT = a.tr_txt, TYT = a.tr_tyt;
@@ -2191,7 +2190,7 @@ bool fast3_supported_explicit(int M, const BlockSpec &bs)
 // cost: CTAs x (steps over the streamed block + the fixed cost of a CTA -- first chunk, pair
 // constants, reduction -- expressed in steps) x lanes x tile slots per useful pair
 #define TR_CTA_OVERHEAD_STEPS 40
-static TripleGeom triple_geom(int N1, int N2, int N3, double *cost_out)
+static TripleGeom triple_geom1(int N1, int N2, int N3, int maxthr, double *cost_out)
 {
     TripleGeom best;
     memset(&best, 0, sizeof(best));
@@ -2199,12 +2198,12 @@ static TripleGeom triple_geom(int N1, int N2, int N3, double *cost_out)
     for (int txt = 4; txt <= 64; txt++)
         for (int tyt = 2; tyt <= 48; tyt++) {
             const int nthr = txt * tyt;
-            if (nthr < TR_MAXTHREADS / 2 || nthr > TR_MAXTHREADS) continue;
+            if (nthr < maxthr / 2 || nthr > maxthr) continue;
             const int T1 = 2 * txt, T2 = 4 * tyt;
             const int nt1 = (N1 + T1 - 1) / T1, nt2 = (N2 + T2 - 1) / T2;
             const int threads = (nthr + 31) / 32 * 32;
             // mild preference for full CTAs
-            const double cost = (double)nt1 * T1 * nt2 * T2 * threads / nthr * (1.0 + 0.02 * (TR_MAXTHREADS - threads) / 32) *
+            const double cost = (double)nt1 * T1 * nt2 * T2 * threads / nthr * (1.0 + 0.02 * (maxthr - threads) / 32) *
                                 (((N3 + 3) & ~3) + TR_CTA_OVERHEAD_STEPS);
             if (cost < best_cost) {
                 best_cost = cost;
@@ -2214,6 +2213,19 @@ static TripleGeom triple_geom(int N1, int N2, int N3, double *cost_out)
         }
     if (cost_out) *cost_out = best_cost;
     return best;
+}
+
+// one CTA per SM, or two when one cannot use more than 256 threads
+static TripleGeom triple_geom(int N1, int N2, int N3, double *cost_out)
+{
+    TripleGeom g = triple_geom1(N1, N2, N3, TR_MAXTHREADS, cost_out);
+    g.ctas = 1;
+    if (g.threads <= 256) {
+        double c2;
+        TripleGeom g2 = triple_geom1(N1, N2, N3, TR_MAXTHREADS / 2, &c2);
+        if (g2.threads > 0) { g = g2; g.ctas = 2; if (cost_out) *cost_out = c2; }
+    }
+    return g;
 }
 
 // The scan tiles two blocks over the CTAs and streams the third: with a short third block (the
@@ -2349,14 +2361,15 @@ int launch_fast_search3(int M, const BlockSpec &bs_caller, const double *A, int6
     {
         const int rowlen = L.tg.T1 + L.tg.T2;
         const size_t fixed = sizeof(double) * (((bs.size[2] + 3) & ~3) + 64);
-        // TR_CTAS CTAs per SM: each gets its share of the 227 KB (1 KB per CTA is reserved)
-        int kc = (int)(((size_t)(224 / TR_CTAS - 2) * 1024 - fixed) / (sizeof(double) * 2 * rowlen)) & ~3;
+        // ctas CTAs per SM: each gets its share of the 227 KB (1 KB per CTA is reserved)
+        int kc = (int)(((size_t)(224 / L.tg.ctas - 2) * 1024 - fixed) / (sizeof(double) * 2 * rowlen)) & ~3;
         kc = kc > TR_KC_MAX ? TR_KC_MAX : kc;
         if (kc < 4) { set_error("triple scan: third block too large for shared memory"); return MFB_EUNSUPPORTED; }
         a.tr_kc = kc;
         const size_t smem = sizeof(double) * (size_t)2 * kc * rowlen + fixed;
         MFB_LAUNCH(k_triple_seed, (unsigned)V, 128, 0, st, a);
-        void (*ktr)(FastArgs) = a.csf ? k_triples<1> : k_triples<0>;
+        void (*ktr)(FastArgs) = L.tg.ctas == 2 ? (a.csf ? k_triples<1, 2> : k_triples<0, 2>)
+                                               : (a.csf ? k_triples<1, 1> : k_triples<0, 1>);
         MFB_CUDA_TRY(cudaFuncSetAttribute(ktr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(ktr, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
     }
