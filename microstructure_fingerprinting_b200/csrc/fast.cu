@@ -1275,6 +1275,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) k_gemm_pairs(FastArgs a)
 // adds its own cycle, so the count of instructions per tuple is what sets the pace.
 // ---------------------------------------------------------------------------------
 #define TR_KC_MAX 128        // i3 steps per chunk: as many as fit in shared memory, at most this
+#define TR_CSF_CTAS 3         // CSF-projected scan: CTAs per SM.  It keeps the caller's block order (336 CTAs of 12 steps
+                              // per voxel at N = 1000, E = 10) and is bound by the prologue / reduction of its CTAs: three
+                              // small CTAs per SM overlap them (1 / 2 / 3 / 4 CTAs: 17.1 k / 19.1 k / 20.5 k / 19.3 k voxels/s)
 #define TR_MAXTHREADS 384     // per SM: one CTA of up to 384 threads, or two of up to 192 (k_triples<CSF, 2>) when
                               // the tiling cannot use more than 256 threads in one CTA (a short tiled block: T1 = 2 x 5
                               // for the 10-atom EAR block leaves 240 threads) -- [N,N,E] +6 %, [300,300,300] -1 %
@@ -2216,14 +2219,15 @@ static TripleGeom triple_geom1(int N1, int N2, int N3, int maxthr, double *cost_
 }
 
 // one CTA per SM, or two when one cannot use more than 256 threads
-static TripleGeom triple_geom(int N1, int N2, int N3, double *cost_out)
+static TripleGeom triple_geom(int N1, int N2, int N3, double *cost_out, int force_ctas = 0)
 {
     TripleGeom g = triple_geom1(N1, N2, N3, TR_MAXTHREADS, cost_out);
     g.ctas = 1;
-    if (g.threads <= 256) {
+    if (g.threads <= 256 || force_ctas > 1) {
+        const int nc = force_ctas > 1 ? force_ctas : 2;
         double c2;
-        TripleGeom g2 = triple_geom1(N1, N2, N3, TR_MAXTHREADS / 2, &c2);
-        if (g2.threads > 0) { g = g2; g.ctas = 2; if (cost_out) *cost_out = c2; }
+        TripleGeom g2 = triple_geom1(N1, N2, N3, TR_MAXTHREADS / nc, &c2);
+        if (g2.threads > 0) { g = g2; g.ctas = nc; if (cost_out) *cost_out = c2; }
     }
     return g;
 }
@@ -2243,7 +2247,7 @@ static BlockSpec triple_permute(const BlockSpec &bs, int csf, int perm[3], Tripl
     // sets the pace, and measured 10-20 % slower with the short block tiled)
     for (int k = 0; k < (csf ? 1 : 6); k++) {
         double c;
-        const TripleGeom g = triple_geom(bs.size[P[k][0]], bs.size[P[k][1]], bs.size[P[k][2]], &c);
+        const TripleGeom g = triple_geom(bs.size[P[k][0]], bs.size[P[k][1]], bs.size[P[k][2]], &c, csf ? TR_CSF_CTAS : 0);
         if (c < best_cost * (1.0 - 1e-9)) { best_cost = c; bp = k; bg = g; }   // ties keep the caller's order
     }
     BlockSpec out = bs;
@@ -2369,6 +2373,7 @@ int launch_fast_search3(int M, const BlockSpec &bs_caller, const double *A, int6
         const size_t smem = sizeof(double) * (size_t)2 * kc * rowlen + fixed;
         MFB_LAUNCH(k_triple_seed, (unsigned)V, 128, 0, st, a);
         void (*ktr)(FastArgs) = L.tg.ctas == 2 ? (a.csf ? k_triples<1, 2> : k_triples<0, 2>)
+                                : L.tg.ctas == 3 ? k_triples<1, 3>
                                                : (a.csf ? k_triples<1, 1> : k_triples<0, 1>);
         MFB_CUDA_TRY(cudaFuncSetAttribute(ktr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MFB_LAUNCH(ktr, dim3((unsigned)a.tr_ntiles, (unsigned)V), L.tg.threads, smem, st, a);
