@@ -52,7 +52,7 @@ typedef struct mfb_plan mfb_plan;
 
 /* ABI version (bumped on any signature change); mfb_version() returns the value the
  * library was built with, the Python binding refuses a library whose version differs. */
-#define MFB_ABI_VERSION 3
+#define MFB_ABI_VERSION 4
 int mfb_version(void);
 
 /* element types of the host volume handed to mfb_fit_volume */
@@ -111,6 +111,32 @@ int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *table,
                   const int32_t *row_lo, const int32_t *row_hi, const double *w_lo,
                   const double *w_hi, const double *scale, double *out, int64_t ldd,
                   void *stream);
+
+/*
+ * Interpolation plan of rotate_atom_2Dprotocol (reference mf_utils.py:1440-1690) for V
+ * directions, expanded on the device from the host's per-direction decisions; replaces the
+ * per-sequence part of the reference's per-direction loop (mf_utils.py:1560-1688).  Outputs
+ * feed mfb_lerp_rows.  All pointers are device pointers.
+ *   per sequence m (M):   m_class (class = (Delta, delta) pair x laboratory direction of a
+ *       b > 0 sequence, -1 for b0 sequences, which keep their own table row), m_lab (unique
+ *       laboratory direction, < U), m_isb0, m_b0row (table row of the pair's mean b0 signal),
+ *       m_G, m_gd = gamma*delta, m_tt = Delta - delta/3; DIFF = free diffusivity
+ *   per direction v:      nrm, gz (V x U: in-plane norm and |g_z| of the rotated laboratory
+ *       directions), ok (V: 0 = the direction breaks the protocol's assumptions, scale = 0);
+ *       kind, line, sgn (V x C: 0 = no rule reaches the class -> zero signal, 2 = gradient
+ *       parallel to the fascicle -> b0 row, 3 = interpolate along reference line `line` with
+ *       sign `sgn` of the perpendicular gradient)
+ *   reference lines:      line_off (L+1), line_nodes (sorted signed G), line_rows (table rows)
+ *   outputs (V x M each): row_lo, row_hi, w_lo, w_hi (scipy's two-weight linear form, interval
+ *       index clipped to [1, n-1]), scale = exp(-(gamma delta |g_z| G)^2 (Delta - delta/3) DIFF)
+ */
+int mfb_plan2d(int device, int64_t V, int M, int U, int C, const int32_t *m_class,
+               const int32_t *m_lab, const uint8_t *m_isb0, const int32_t *m_b0row,
+               const double *m_G, const double *m_gd, const double *m_tt, double DIFF,
+               const double *nrm, const double *gz, const uint8_t *kind, const int32_t *line,
+               const double *sgn, const uint8_t *ok, const int32_t *line_off,
+               const double *line_nodes, const int32_t *line_rows, int32_t *row_lo,
+               int32_t *row_hi, double *w_lo, double *w_hi, double *scale, void *stream);
 
 /*
  * Batched solve_exhaustive_posweights on explicit dictionaries.

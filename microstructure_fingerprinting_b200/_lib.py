@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MFB_LIB") or os.path.join(_HERE, "libmfb200.so")   # MFB_LIB: A/B builds
 
 MFB_OK, MFB_EINVAL, MFB_ECUDA, MFB_ENOMEM, MFB_EUNSUPPORTED = 0, -1, -2, -3, -4
-MFB_ABI_VERSION = 3          # include/mfb200.h; a library built from other sources is refused
+MFB_ABI_VERSION = 4          # include/mfb200.h; a library built from other sources is refused
 MFB_F64, MFB_F32 = 0, 1
 
 c_dp = ctypes.POINTER(ctypes.c_double)
@@ -44,6 +44,10 @@ SYMBOLS = {
     "mfb_fit_stats": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int]),
     "mfb_solve_stats": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "mfb_trim": (ctypes.c_int, [ctypes.c_int]),
+    "mfb_plan2d": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mfb_mc_average": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, c_vp, ctypes.c_int64, c_vp,
                                       c_vp, ctypes.c_double, ctypes.c_int64, c_vp, c_vp]),
 }

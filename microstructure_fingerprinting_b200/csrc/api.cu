@@ -284,6 +284,27 @@ extern "C" int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *
     return launch_lerp_rows(V, M, N, table, row_lo, row_hi, w_lo, w_hi, scale, out, ldd, (cudaStream_t)stream);
 }
 
+extern "C" int mfb_plan2d(int device, int64_t V, int M, int U, int C, const int32_t *m_class,
+                          const int32_t *m_lab, const uint8_t *m_isb0, const int32_t *m_b0row,
+                          const double *m_G, const double *m_gd, const double *m_tt, double DIFF,
+                          const double *nrm, const double *gz, const uint8_t *kind, const int32_t *line,
+                          const double *sgn, const uint8_t *ok, const int32_t *line_off,
+                          const double *line_nodes, const int32_t *line_rows, int32_t *row_lo,
+                          int32_t *row_hi, double *w_lo, double *w_hi, double *scale, void *stream)
+{
+    if (V < 0 || M <= 0 || U <= 0 || C < 0 ||
+        (V > 0 && (!m_class || !m_lab || !m_isb0 || !m_b0row || !m_G || !m_gd || !m_tt || !nrm || !gz || !ok ||
+                   !line_off || !row_lo || !row_hi || !w_lo || !w_hi || !scale)) ||
+        (V > 0 && C > 0 && (!kind || !line || !sgn || !line_nodes || !line_rows))) {
+        set_error("mfb_plan2d: invalid argument");
+        return MFB_EINVAL;
+    }
+    MFB_ON_DEVICE(device);
+    return launch_plan2d(V, M, U, C, m_class, m_lab, m_isb0, m_b0row, m_G, m_gd, m_tt, DIFF, nrm, gz, kind, line,
+                         sgn, ok, line_off, line_nodes, line_rows, row_lo, row_hi, w_lo, w_hi, scale,
+                         (cudaStream_t)stream);
+}
+
 extern "C" int mfb_mc_average(int device, int64_t n_entries, int dim, const double *sim_phases,
                               int64_t n_seq, const int64_t *delta_mapping, const double *gscaling,
                               double Dscaling, int64_t num_spins, double *signal, void *stream)

@@ -83,6 +83,13 @@ int launch_lerp_rows(int64_t V, int M, int N, const double *table, const int32_t
                      const int32_t *row_hi, const double *w_lo, const double *w_hi,
                      const double *scale, double *out, int64_t ldd, cudaStream_t st);
 
+int launch_plan2d(int64_t V, int M, int U, int C, const int32_t *m_class, const int32_t *m_lab,
+                  const uint8_t *m_isb0, const int32_t *m_b0row, const double *m_G, const double *m_gd,
+                  const double *m_tt, double DIFF, const double *nrm, const double *gz, const uint8_t *kind,
+                  const int32_t *line, const double *sgn, const uint8_t *ok, const int32_t *line_off,
+                  const double *line_nodes, const int32_t *line_rows, int32_t *row_lo, int32_t *row_hi,
+                  double *w_lo, double *w_hi, double *scale, cudaStream_t st);
+
 size_t exact_scratch_bytes(int64_t V, const BlockSpec &bs);
 
 // Exhaustive search in the reference's arithmetic on explicit dictionaries.

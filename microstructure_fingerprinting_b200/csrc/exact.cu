@@ -246,6 +246,77 @@ int launch_lerp_rows(int64_t V, int M, int N, const double *table, const int32_t
 }
 
 // ---------------------------------------------------------------------------------
+// rotate_atom_2Dprotocol (mfu:1440-1690): expansion of the per-direction, per-class decisions of
+// the host (which gradient line of the reference a class of sequences interpolates along, its sign,
+// vanished perpendicular gradients) into the per-sequence interpolation plan that k_lerp_rows
+// consumes.  One thread per (direction, sequence); the arithmetic is the host's, operation by
+// operation (this file is compiled without FMA contraction): G_perp = G nrm, G_par = |g_z| G,
+// S_par = exp(-(gamma delta G_par)^2 (Delta - delta/3) D), scipy's two-weight lerp in the signed
+// perpendicular gradient with the interval index clipped to [1, n-1].
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_plan2d(int64_t total, int M, int U, int C, const int32_t *m_class, const int32_t *m_lab, const uint8_t *m_isb0,
+         const int32_t *m_b0row, const double *m_G, const double *m_gd, const double *m_tt, double DIFF,
+         const double *nrm, const double *gz, const uint8_t *kind, const int32_t *line, const double *sgn,
+         const uint8_t *ok, const int32_t *line_off, const double *line_nodes, const int32_t *line_rows,
+         int32_t *row_lo, int32_t *row_hi, double *w_lo, double *w_hi, double *scale)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int64_t v = idx / M;
+    const int m = (int)(idx - v * M);
+    const int u = m_lab[m];
+    const double G = m_G[m];
+    const double a = DM(m_gd[m], DM(gz[v * U + u], G));
+    const double S_par = exp(DM(DM(-DM(a, a), m_tt[m]), DIFF));
+    int rl = m, rh = m;
+    double wl = 1.0, wh = 0.0;
+    bool covered = m_isb0[m] != 0;
+    if (!covered) {
+        const int c = m_class[m];
+        const int k = kind[v * C + c];
+        if (k == 2) {                       // gradient parallel to the new fascicle: mean b0 signal of the shell
+            rl = rh = m_b0row[m];
+            covered = true;
+        } else if (k == 3) {                // interpolate along the closest reference line
+            const int li = line[v * C + c];
+            const int o = line_off[li], n = line_off[li + 1] - o;
+            const double *xs = line_nodes + o;
+            const double x = DM(DM(G, nrm[v * U + u]), sgn[v * C + c]);
+            int lo = 0, hi = n;             // np.searchsorted(xs, x, side='left')
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (xs[mid] < x) lo = mid + 1; else hi = mid;
+            }
+            const int j = max(1, min(n - 1, lo));
+            const double x_lo = xs[j - 1], x_hi = xs[j];
+            wl = DD(DS(x_hi, x), DS(x_hi, x_lo));
+            wh = DD(DS(x, x_lo), DS(x_hi, x_lo));
+            rl = line_rows[o + j - 1];
+            rh = line_rows[o + j];
+            covered = true;
+        }
+    }
+    row_lo[idx] = rl; row_hi[idx] = rh; w_lo[idx] = wl; w_hi[idx] = wh;
+    scale[idx] = (covered && ok[v]) ? S_par : 0.0;
+}
+
+int launch_plan2d(int64_t V, int M, int U, int C, const int32_t *m_class, const int32_t *m_lab,
+                  const uint8_t *m_isb0, const int32_t *m_b0row, const double *m_G, const double *m_gd,
+                  const double *m_tt, double DIFF, const double *nrm, const double *gz, const uint8_t *kind,
+                  const int32_t *line, const double *sgn, const uint8_t *ok, const int32_t *line_off,
+                  const double *line_nodes, const int32_t *line_rows, int32_t *row_lo, int32_t *row_hi,
+                  double *w_lo, double *w_hi, double *scale, cudaStream_t st)
+{
+    const int64_t total = V * M;
+    if (total == 0) return MFB_OK;
+    MFB_LAUNCH(k_plan2d, (unsigned)((total + 255) / 256), 256, 0, st, total, M, U, C, m_class, m_lab, m_isb0, m_b0row,
+               m_G, m_gd, m_tt, DIFF, nrm, gz, kind, line, sgn, ok, line_off, line_nodes, line_rows, row_lo, row_hi,
+               w_lo, w_hi, scale);
+    return MFB_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // closed forms
 // ---------------------------------------------------------------------------------
 // mfu:404-459 lsqnonneg_2var_opt (also inlined at mfu:331-381)

@@ -858,28 +858,60 @@ class _Protocol2D(object):
         np.divide(gp, nrm[:, :, np.newaxis], out=gp, where=(nrm > 0)[:, :, np.newaxis])
         return gp, nrm, np.abs(g[:, :, 2])
 
-    def plan(self, newdirs, strict=True):
-        """Interpolation plan of every sequence for every direction: (row_lo, row_hi, w_lo,
-        w_hi, scale), each (V, M).  strict=True raises the reference's AssertionError when a
-        direction breaks the protocol's assumptions (e.g. a fascicle in the gradient plane,
-        which projects both gradient lines onto one); strict=False returns a sixth array
-        ok (V,) instead and gives those directions an all-zero plan."""
+    def _static_tables(self):
+        """Per-measurement constants of the plan (they do not depend on the new directions): class
+        (pair, laboratory direction) of every b > 0 sequence, and the reference lines of all pairs
+        concatenated (sorted signed-G nodes and their table rows)."""
+        if getattr(self, "_static", None) is not None:
+            return self._static
+        M = self.M
+        m_class = np.full(M, -1, dtype=np.int32)          # -1: b0 sequence (keeps its own row)
+        m_b0row = np.full(M, -1, dtype=np.int32)
+        classes = []                                       # (pair, position in the pair's lab list, measurements)
+        line_id, line_off, line_nodes, line_rows = {}, [0], [], []
+        for ip, pr in enumerate(self.pairs):
+            ind, lab = pr["ind"], pr["lab"]
+            for j in range(lab.size):
+                m_rows = ind[self.lab_id[ind] == lab[j]]
+                if not np.any(self.is_b[m_rows]):
+                    continue                               # the b0 "direction"
+                mb = m_rows[self.is_b[m_rows]]
+                m_class[mb] = len(classes)
+                m_b0row[mb] = self.b0_row[ip]
+                classes.append((ip, j, mb))
+            for im in sorted(pr["lines"]):
+                nodes, node_rows = pr["lines"][im]
+                line_id[(ip, im)] = len(line_off) - 1
+                line_nodes.append(nodes)
+                line_rows.append(node_rows)
+                line_off.append(line_off[-1] + nodes.size)
+        self._static = {
+            "m_class": m_class, "m_b0row": m_b0row, "classes": classes, "line_id": line_id,
+            "line_off": np.asarray(line_off, dtype=np.int32),
+            "line_nodes": np.ascontiguousarray(np.concatenate(line_nodes)),
+            "line_rows": np.ascontiguousarray(np.concatenate(line_rows).astype(np.int32)),
+            "m_lab": np.ascontiguousarray(self.lab_id.astype(np.int32)),
+            "m_isb0": np.ascontiguousarray(self.is_b0.astype(np.uint8)),
+            "m_gd": np.ascontiguousarray(self.gam * self.delta), "m_tt": np.ascontiguousarray(self.Delta - self.delta / 3)}
+        return self._static
+
+    def classify(self, newdirs, strict=True):
+        """Direction-dependent decisions of the plan, per direction and per class (pair, laboratory
+        direction) instead of per sequence: kind (0 = no rule reaches the class, 2 = the gradient became
+        parallel to the new fascicle: mean b0 signal of the shell, 3 = interpolate along a reference
+        line), the reference line and the sign of the perpendicular gradient along it; plus the in-plane
+        norm and |g_z| of every unique laboratory direction and the directions that break the
+        protocol's assumptions (`bad`; with strict=True they raise the reference's AssertionError).
+        Everything of size (V, M) is left to the expansion (`plan` on the host, mfb_plan2d on the GPU)."""
+        st = self._static_tables()
         gp, nrm, gz = self.frames(newdirs)
-        bad = np.zeros(gp.shape[0], dtype=bool)
-        V, M = gp.shape[0], self.M
-        G = self.G
-        Gperp = G[np.newaxis, :] * nrm[:, self.lab_id]
-        Gpar = gz[:, self.lab_id] * G[np.newaxis, :]
-        assert np.all(np.isclose(G[np.newaxis, :] ** 2, Gperp ** 2 + Gpar ** 2)), \
-            "Inconsistency in parallel and perpendicular gradient components for new fascicle."
-        S_par = np.exp(-(self.gam * self.delta[np.newaxis, :] * Gpar) ** 2 *
-                       (self.Delta - self.delta / 3)[np.newaxis, :] * self.DIFF)
-        assert np.all(np.isclose(S_par[:, self.is_b0], 1)), \
-            "New fascicle: parallel signal should  be equal to 1 in b0 sequences."
-        row_lo = np.broadcast_to(np.arange(M, dtype=np.int32), (V, M)).copy()   # b0: own row
-        row_hi = row_lo.copy()
-        w_lo, w_hi = np.ones((V, M)), np.zeros((V, M))
-        covered = np.broadcast_to(self.is_b0, (V, M)).copy()
+        V = gp.shape[0]
+        C = len(st["classes"])
+        kind = np.zeros((V, C), dtype=np.uint8)
+        line = np.zeros((V, C), dtype=np.int32)
+        sgn_c = np.zeros((V, C))
+        bad = np.zeros(V, dtype=bool)
+        c = 0
         for ip, pr in enumerate(self.pairs):
             ind, lab, ref_un = pr["ind"], pr["lab"], pr["ref_un"]
             P = lab.size
@@ -916,12 +948,14 @@ class _Protocol2D(object):
             lower = opp.any(axis=2)                                      # (V, P) sorted position i of (i, j)
             upper = opp.any(axis=1)
             partner_of_upper = np.argmax(opp, axis=1)                    # for sorted j: its i
-            # gradients that became parallel to the new fascicle: mean b0 signal of the shell
+            ar = np.arange(V)
             for j in range(P):
                 m_rows = ind[self.lab_id[ind] == lab[j]]
                 if not np.any(self.is_b[m_rows]):
                     continue                                             # the b0 "direction"
-                mb = m_rows[self.is_b[m_rows]]
+                assert st["classes"][c][0] == ip and st["classes"][c][1] == j
+                mb = st["classes"][c][2]
+                # gradients that became parallel to the new fascicle: mean b0 signal of the shell
                 van = ~(nrm[:, lab[j]] > 0)                              # (V,)
                 if np.any(van):
                     assert self.b0_row[ip] >= 0, (
@@ -929,41 +963,120 @@ class _Protocol2D(object):
                         "implying free diffusion. However, no b0 measurements in the reference signal are "
                         "available for this shell. We therefore can't properly scale the new signal."
                         % (ip + 1, self.n_pairs))
-                    vv = np.where(van)[0][:, np.newaxis]
-                    row_lo[vv, mb[np.newaxis, :]] = row_hi[vv, mb[np.newaxis, :]] = self.b0_row[ip]
-                    w_lo[vv, mb[np.newaxis, :]], w_hi[vv, mb[np.newaxis, :]] = 1.0, 0.0
-                    covered[vv, mb[np.newaxis, :]] = True
+                    kind[van, c] = 2
                 # the first sorted row of this direction's unique class carries the line flags
-                ar = np.arange(V)
                 rep = np.argmax(uid_sorted == new_id[:, j][:, np.newaxis], axis=1)
                 is_lo, is_up = lower[ar, rep], upper[ar, rep]
                 on_line = (is_lo | is_up) & ~van & ~bad
-                if not np.any(on_line):
-                    continue
-                assert np.all(self.is_b[mb]), (
-                    "Problem at delta pair %d/%d: trying to interpolate b0 sequences." % (ip + 1, self.n_pairs))
-                line_pos = np.where(is_lo, rep, partner_of_upper[ar, rep])   # sorted position of line_new
-                line_new = srt[ar, line_pos, :]                          # (V, 2)
-                sgn = np.sign(np.sum(rows[:, j, :] * line_new, axis=1))  # (V,)
-                i_max = np.argmax(line_new @ ref_un.T, axis=1)           # closest reference line
-                for im in np.unique(i_max[on_line]):
-                    vs = np.where(on_line & (i_max == im))[0]
-                    if int(im) not in pr["lines"]:
-                        raise ValueError("rotate_atom_2Dprotocol: no reference line matches a new line "
-                                         "direction at delta pair %d/%d" % (ip + 1, self.n_pairs))
-                    nodes, node_rows = pr["lines"][int(im)]
-                    x = Gperp[vs[:, np.newaxis], mb[np.newaxis, :]] * sgn[vs][:, np.newaxis]
-                    lo, hi, wl, wh = _lerp_plan(nodes, x)
-                    vv = vs[:, np.newaxis]
-                    row_lo[vv, mb[np.newaxis, :]], row_hi[vv, mb[np.newaxis, :]] = node_rows[lo], node_rows[hi]
-                    w_lo[vv, mb[np.newaxis, :]], w_hi[vv, mb[np.newaxis, :]] = wl, wh
-                    covered[vv, mb[np.newaxis, :]] = True
+                if np.any(on_line):
+                    assert np.all(self.is_b[mb]), (
+                        "Problem at delta pair %d/%d: trying to interpolate b0 sequences." % (ip + 1, self.n_pairs))
+                    line_pos = np.where(is_lo, rep, partner_of_upper[ar, rep])   # sorted position of line_new
+                    line_new = srt[ar, line_pos, :]                          # (V, 2)
+                    sgn = np.sign(np.sum(rows[:, j, :] * line_new, axis=1))  # (V,)
+                    i_max = np.argmax(line_new @ ref_un.T, axis=1)           # closest reference line
+                    for im in np.unique(i_max[on_line]):
+                        if int(im) not in pr["lines"]:
+                            raise ValueError("rotate_atom_2Dprotocol: no reference line matches a new line "
+                                             "direction at delta pair %d/%d" % (ip + 1, self.n_pairs))
+                        vs = on_line & (i_max == im)
+                        kind[vs, c] = 3
+                        line[vs, c] = st["line_id"][(ip, int(im))]
+                        sgn_c[vs, c] = sgn[vs]
+                c += 1
+        return {"nrm": nrm, "gz": gz, "kind": kind, "line": line, "sgn": sgn_c, "bad": bad}
+
+    def plan(self, newdirs, strict=True):
+        """Interpolation plan of every sequence for every direction: (row_lo, row_hi, w_lo,
+        w_hi, scale), each (V, M).  strict=True raises the reference's AssertionError when a
+        direction breaks the protocol's assumptions (e.g. a fascicle in the gradient plane,
+        which projects both gradient lines onto one); strict=False returns a sixth array
+        ok (V,) instead and gives those directions an all-zero plan.  (Host expansion of
+        `classify`; the batched pipeline expands on the GPU, mfb_plan2d.)"""
+        cl = self.classify(newdirs, strict)
+        st = self._static_tables()
+        nrm, gz, bad = cl["nrm"], cl["gz"], cl["bad"]
+        V, M = nrm.shape[0], self.M
+        G = self.G
+        Gperp = G[np.newaxis, :] * nrm[:, self.lab_id]
+        Gpar = gz[:, self.lab_id] * G[np.newaxis, :]
+        assert np.all(np.isclose(G[np.newaxis, :] ** 2, Gperp ** 2 + Gpar ** 2)), \
+            "Inconsistency in parallel and perpendicular gradient components for new fascicle."
+        S_par = np.exp(-(self.gam * self.delta[np.newaxis, :] * Gpar) ** 2 *
+                       (self.Delta - self.delta / 3)[np.newaxis, :] * self.DIFF)
+        assert np.all(np.isclose(S_par[:, self.is_b0], 1)), \
+            "New fascicle: parallel signal should  be equal to 1 in b0 sequences."
+        row_lo = np.broadcast_to(np.arange(M, dtype=np.int32), (V, M)).copy()   # b0: own row
+        row_hi = row_lo.copy()
+        w_lo, w_hi = np.ones((V, M)), np.zeros((V, M))
+        covered = np.broadcast_to(self.is_b0, (V, M)).copy()
+        for c, (ip, j, mb) in enumerate(st["classes"]):
+            van = cl["kind"][:, c] == 2
+            if np.any(van):
+                vv = np.where(van)[0][:, np.newaxis]
+                row_lo[vv, mb[np.newaxis, :]] = row_hi[vv, mb[np.newaxis, :]] = self.b0_row[ip]
+                w_lo[vv, mb[np.newaxis, :]], w_hi[vv, mb[np.newaxis, :]] = 1.0, 0.0
+                covered[vv, mb[np.newaxis, :]] = True
+            on = cl["kind"][:, c] == 3
+            for li in np.unique(cl["line"][on, c]):
+                vs = np.where(on & (cl["line"][:, c] == li))[0]
+                nodes = st["line_nodes"][st["line_off"][li]:st["line_off"][li + 1]]
+                node_rows = st["line_rows"][st["line_off"][li]:st["line_off"][li + 1]]
+                x = Gperp[vs[:, np.newaxis], mb[np.newaxis, :]] * cl["sgn"][vs, c][:, np.newaxis]
+                lo, hi, wl, wh = _lerp_plan(nodes, x)
+                vv = vs[:, np.newaxis]
+                row_lo[vv, mb[np.newaxis, :]], row_hi[vv, mb[np.newaxis, :]] = node_rows[lo], node_rows[hi]
+                w_lo[vv, mb[np.newaxis, :]], w_hi[vv, mb[np.newaxis, :]] = wl, wh
+                covered[vv, mb[np.newaxis, :]] = True
         # sequences no rule reached keep a zero perpendicular signal, like the reference
         scale = np.where(covered, S_par, 0.0)
         if strict:
             return row_lo, row_hi, w_lo, w_hi, scale
         scale[bad, :] = 0.0
         return row_lo, row_hi, w_lo, w_hi, scale, ~bad
+
+
+    def plan_device(self, newdirs, device=0):
+        """The same plan with the per-sequence expansion on the GPU (mfb_plan2d): the host only takes
+        the per-direction decisions (`classify`, ~1/7 of the work of `plan`), uploads V x (2 U + 3 C)
+        values and leaves the V x M x 5 plan entries to one kernel on the current CUDA stream.
+        Returns (row_lo, row_hi, w_lo, w_hi, scale) as CUDA tensors (V, M) and ok (V,) as a NumPy
+        array.  Rows and weights are the host plan's bit for bit; `scale` goes through the device's
+        exp() and can differ from NumPy's in the last bit."""
+        torch = _lib.require_cuda()
+        dev = torch.device('cuda', device)
+        st = self._static_tables()
+        cache = getattr(self, "_dev_static", None)
+        if cache is None or cache[0] != device:
+            up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+            cache = (device, {k: up(st[k]) for k in ("m_class", "m_lab", "m_isb0", "m_b0row", "m_gd", "m_tt",
+                                                      "line_off", "line_nodes", "line_rows")},
+                     up(self.G))
+            self._dev_static = cache
+        ds, d_G = cache[1], cache[2]
+        cl = self.classify(newdirs, strict=False)
+        V, M, U, C = cl["nrm"].shape[0], self.M, cl["nrm"].shape[1], cl["kind"].shape[1]
+        ok = ~cl["bad"]
+        d = {k: torch.from_numpy(np.ascontiguousarray(cl[k])).to(dev, non_blocking=True)
+             for k in ("nrm", "gz", "kind", "line", "sgn")}
+        d_ok = torch.from_numpy(np.ascontiguousarray(ok.astype(np.uint8))).to(dev, non_blocking=True)
+        row_lo = torch.empty((V, M), dtype=torch.int32, device=dev)
+        row_hi = torch.empty((V, M), dtype=torch.int32, device=dev)
+        w_lo = torch.empty((V, M), dtype=torch.float64, device=dev)
+        w_hi = torch.empty((V, M), dtype=torch.float64, device=dev)
+        scale = torch.empty((V, M), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().mfb_plan2d(
+                device, V, M, U, C, ds["m_class"].data_ptr(), ds["m_lab"].data_ptr(), ds["m_isb0"].data_ptr(),
+                ds["m_b0row"].data_ptr(), d_G.data_ptr(), ds["m_gd"].data_ptr(), ds["m_tt"].data_ptr(), float(self.DIFF),
+                d["nrm"].data_ptr(), d["gz"].data_ptr(), d["kind"].data_ptr(), d["line"].data_ptr(), d["sgn"].data_ptr(),
+                d_ok.data_ptr(), ds["line_off"].data_ptr(), ds["line_nodes"].data_ptr(), ds["line_rows"].data_ptr(),
+                row_lo.data_ptr(), row_hi.data_ptr(), w_lo.data_ptr(), w_hi.data_ptr(), scale.data_ptr(),
+                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "mfb_plan2d")
+        for t in list(d.values()) + [d_ok]:
+            t.record_stream(torch.cuda.current_stream(dev))
+        return row_lo, row_hi, w_lo, w_hi, scale, ok
 
 
 def rotate_atom_2Dprotocol(sig, sch_mat, refdir, newdir, DIFF, return_device=False):
@@ -1035,10 +1148,12 @@ def _solve_rotated_batch(table, plan_fn, N, peaks, Y, sig_iso, chunk, device):
         try:
             s0, s1 = chunks[c]
             nv = s1 - s0
-            rl, rh, wl, wh, sc, ok = plan_fn(peaks[s0:s1].reshape(-1, 3))
-            good = np.where(ok.reshape(nv, K).all(axis=1))[0]
             with torch.cuda.device(dev), torch.cuda.stream(side):
-                d_pl = [None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev, non_blocking=True)
+                # (a plan function may expand its plan on the GPU: it then runs on the side stream and returns tensors)
+                rl, rh, wl, wh, sc, ok = plan_fn(peaks[s0:s1].reshape(-1, 3))
+                good = np.where(ok.reshape(nv, K).all(axis=1))[0]
+                d_pl = [None if x is None else (x if isinstance(x, torch.Tensor) else
+                                                torch.from_numpy(np.ascontiguousarray(x)).to(dev, non_blocking=True))
                         for x in (rl, rh, wl, wh, sc)]
                 A = torch.empty((nv, M, ntot), dtype=torch.float64, device=dev)
                 if iso:
@@ -1100,7 +1215,7 @@ def solve_rotated_2Dprotocol_batch(sig, sch_mat, refdir, peaks, Y, DIFF, sig_iso
     if sig.ndim != 2 or np.asarray(Y).shape[1] != sig.shape[0]:
         raise ValueError("sig should be (M, N) and Y (V, M)")
     proto = _Protocol2D(sch_mat, refdir, DIFF)
-    return _solve_rotated_batch(proto.table(sig), lambda d: proto.plan(d, strict=False), sig.shape[1], peaks, Y,
+    return _solve_rotated_batch(proto.table(sig), lambda d: proto.plan_device(d, device), sig.shape[1], peaks, Y,
                                 sig_iso, chunk, device)
 
 

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "mfb200.h")).read()
-    declared = set(re.findall(r"\b(mfb_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(mfb_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     lib = _lib.load()
     for name in declared:

@@ -1,6 +1,8 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the
 C ABI of libmfb200.so.  Comparisons: committed reference goldens (tests/golden), the CPU
 oracle on the same seeded inputs, and size-independent properties at larger sizes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -773,9 +775,10 @@ def test_get_PGSE_from_phases_matches_reference(mc_cases, tmp_path):
 
 def test_rotate_atom_2d_batched_and_pipeline(lowlevel):
     """Batched rotate_atom_2Dprotocol (one vectorised host plan, one launch) equals the
-    per-direction calls, and the chunked AxCaliber pipeline (plans on the host in a worker
-    thread, dictionaries assembled and searched on the GPU) equals the hand-written
-    per-voxel sequence rotate_atom_2Dprotocol x 2 + solve_exhaustive_posweights."""
+    per-direction calls, and the chunked AxCaliber pipeline (per-direction decisions on the host in a
+    worker thread, plans expanded, dictionaries assembled and searched on the GPU) agrees with the
+    hand-written per-voxel sequence rotate_atom_2Dprotocol x 2 + solve_exhaustive_posweights:
+    indices exact, weights to 1e-12."""
     g = lowlevel
     ref = np.array([0.0, 0.0, 1.0])
     sig, sch, DIFF = g["ax_sig"], g["ax_sch"], float(g["ax_DIFF"])
@@ -810,7 +813,10 @@ def test_rotate_atom_2d_batched_and_pipeline(lowlevel):
     for v in (0, 1, 5, 19):
         D = np.hstack([mfu.rotate_atom_2Dprotocol(dic, sch, ref, peaks[v, k], DIFF) for k in range(2)])
         w1, sub1, tot1, obj1, _ = mfu.solve_exhaustive_posweights(D, Y[v].copy(), np.array([N, N]))
-        assert np.array_equal(sub[v], sub1) and np.array_equal(w[v], w1) and obj[v] == obj1
+        # (the pipeline expands its plans on the GPU: the parallel-signal factor goes through the device's
+        # exp(), the dictionaries can differ from the host path's in the last bit)
+        assert np.array_equal(sub[v], sub1) and np.allclose(w[v], w1, rtol=1e-12, atol=0.0)
+        assert abs(obj[v] - obj1) <= 1e-12 * float(Y[v] @ Y[v])
         assert np.array_equal(sub[v], truth[v])
 
 
@@ -984,3 +990,28 @@ def test_c_abi_rejects_bad_arguments():
         assert np.array_equal(out, plan.fit_host(ph.Y, ph.peaks, ph.K, None, None, ph.maxfasc, False, False))
     finally:
         plan.close()
+
+
+@pytest.mark.gpu
+def test_plan2d_device_equals_host_plan():
+    """rotate_atom_2Dprotocol's interpolation plan (reference mf_utils.py:1440-1690): the GPU
+    expansion of the host's per-direction decisions (mfb_plan2d) must give the rows and the two
+    lerp weights of the host plan bit for bit, and the parallel-signal factor to the last bits of
+    exp(); directions that break the protocol's assumptions get a zero plan in both."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lowlevel_rotation.npz"))
+    proto = mfu._Protocol2D(g["ax_sch"], np.array([0.0, 0.0, 1.0]), 2.0e-9)
+    rng = np.random.default_rng(20)
+    d = rng.standard_normal((700, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[3] = [1.0, 0.0, 0.0]                     # in the gradient plane: breaks the protocol
+    d[4] = [0.0, 0.0, 1.0]                     # the reference direction itself
+    d[5] = [0.0, 0.0, -1.0]
+    d[6] = [np.sqrt(0.5), np.sqrt(0.5), 0.0]   # along a gradient line
+    host = proto.plan(d, strict=False)
+    devp = proto.plan_device(d)
+    assert np.array_equal(host[5], devp[5]) and not host[5].all() and host[5].sum() > 600
+    for k in range(4):
+        assert np.array_equal(host[k], devp[k].cpu().numpy()), k
+    sc = devp[4].cpu().numpy()
+    assert np.allclose(sc, host[4], rtol=4e-16, atol=0.0)
+    assert np.array_equal(sc == 0.0, host[4] == 0.0)
