@@ -115,7 +115,7 @@ int mfb_lerp_rows(int device, int64_t V, int M, int N, const double *table,
 /*
  * Interpolation plan of rotate_atom_2Dprotocol (reference mf_utils.py:1440-1690) for V
  * directions, expanded on the device from the host's per-direction decisions; replaces the
- * per-sequence part of the reference's per-direction loop (mf_utils.py:1560-1688).  Outputs
+ * per-sequence part of the reference's per-direction loop (mf_utils.py:1557-1686).  Outputs
  * feed mfb_lerp_rows.  All pointers are device pointers.
  *   per sequence m (M):   m_class (class = (Delta, delta) pair x laboratory direction of a
  *       b > 0 sequence, -1 for b0 sequences, which keep their own table row), m_lab (unique
