@@ -1013,5 +1013,5 @@ def test_plan2d_device_equals_host_plan():
     for k in range(4):
         assert np.array_equal(host[k], devp[k].cpu().numpy()), k
     sc = devp[4].cpu().numpy()
-    assert np.allclose(sc, host[4], rtol=4e-16, atol=0.0)
+    assert np.allclose(sc, host[4], rtol=1e-15, atol=0.0)      # exp(): 1 ulp on the device + < 1 ulp in NumPy
     assert np.array_equal(sc == 0.0, host[4] == 0.0)
