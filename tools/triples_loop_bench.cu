@@ -111,7 +111,7 @@ void run(const char *name)
     const double tuples = (double)nsteps * P * Q * THREADS * 148 * CTAS;
     printf("%-34s P%dxQ%d W1=%d VS=%d CSF=%d %3d thr x %d CTA, %3d regs, spill %zu B: %.2f ms, %.3f T tuples/s, %.1f ops/tuple, %.1f%% of the FP64 pipe\n",
            name, P, Q, W1, VS, CSF, THREADS, CTAS, fa.numRegs, (size_t)fa.localSizeBytes, ms, tuples / ms / 1e9,
-           per_tuple, 100.0 * tuples * per_tuple * 2.0 / ms / 1e9 / 37.1e3);
+           per_tuple, 100.0 * tuples * per_tuple * 2.0 / ms / 1e9 / 37.1);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) printf("  CUDA error: %s\n", cudaGetErrorString(err));
     cudaFree(out);
@@ -237,7 +237,7 @@ void runstage(const char *name)
     const double tuples = (double)nsteps * 8 * THREADS * 148;
     printf("%-28s width %d pinned %d %3d thr, %3d regs, spill %zu B: %.2f ms, %.3f T tuples/s, %.1f%% of the FP64 pipe at 11.5 ops\n",
            name, WD, PIN, THREADS, fa.numRegs, (size_t)fa.localSizeBytes, ms, tuples / ms / 1e9,
-           100.0 * tuples * 23.0 / ms / 1e9 / 37.1e3);
+           100.0 * tuples * 23.0 / ms / 1e9 / 37.1);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) printf("  CUDA error: %s\n", cudaGetErrorString(err));
     cudaFree(out);
