@@ -369,7 +369,8 @@ extern "C" int mfb_solve_batch(int device, int64_t V, int M, int nblocks, const 
         fixed = shared_dict ? fast3_scratch_bytes(M, bs3, 0, 1) : 0;
         per_vox = std::max(per_vox, fast3_scratch_bytes(M, bs3, 1, shared_dict) - fixed + 4096);
     }
-    const size_t budget = per_vox > ((size_t)1 << 20) ? (size_t)6 << 30 : (size_t)1 << 30;
+    // (sub-chunks of ~1000 voxels left 10 % on the table at [800, 800]: launch tails, one preparation pass per sub-chunk)
+    const size_t budget = per_vox > ((size_t)1 << 18) ? (size_t)6 << 30 : (size_t)1 << 30;
     int64_t sub = std::max<int64_t>(1, std::min<int64_t>((fast || fast3) ? 8192 : 65535, budget / per_vox));
     sub = std::min(sub, V);
     // workspace of the device, kept between calls (mfb_trim releases it): allocating and
