@@ -588,7 +588,9 @@ static int fit_chunk(mfb_plan *pl, int64_t nv, const double *y, const double *pe
                 return triple ? fast3_scratch_bytes(M, bs3, n, 0) : fast_scratch_bytes(M, dp.N, dp.N, n, 1, 0);
             };
             const size_t per_vox = (size_t)strideA * sizeof(double) + fbytes(1);
-            int64_t sub = std::max<int64_t>(1, std::min<int64_t>(8192, 2 * pl->exact_budget / per_vox));
+            // (triple scan: ~14 MB per voxel at N = 1000 -- the three correlation matrices; with 6 GB a sub-chunk
+            // is 440 voxels and the scan's 6 CTAs per voxel make 9 waves: a budget of 24 GB keeps the tail small)
+            int64_t sub = std::max<int64_t>(1, std::min<int64_t>(8192, (triple ? 8 : 2) * pl->exact_budget / per_vox));
             sub = std::min(sub, cnt);
             MFB_TRY(pl->abuf.ensure((size_t)strideA * sizeof(double) * sub));
             MFB_TRY(pl->fscratch.ensure(fbytes(sub)));
